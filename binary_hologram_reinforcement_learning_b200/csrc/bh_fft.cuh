@@ -1,0 +1,248 @@
+// Shared-memory tile FFT primitives for the hologram propagation kernels (sm_100a).
+//
+// A "tile" is W independent length-N complex sequences interleaved in shared
+// memory: element i of sequence w lives at s[i * WP + w] (WP >= W, WP = W + 1
+// pads the transposing loads of the row passes off the same banks).  Threads
+// are laid out across sequences first (w = tid % W, q = tid / W), so every
+// warp-wide shared access touches consecutive 8-byte words: conflict free by
+// construction for both the row passes and the column pass.
+//
+// One Stockham autosort pass of radix R (Ns = product of the radices already
+// applied) does, for butterfly j in [0, N/R):
+//     k  = j mod Ns
+//     v[r] = in[j + r*N/R] * exp(-+2 pi i r k / (Ns R))        r = 0..R-1
+//     V = DFT_R(v)
+//     out[(j / Ns) * Ns * R + k + r * Ns] = V[r]
+// All butterflies of a thread are held in registers between the read and the
+// write, so the pass is in place with one barrier either side.
+//
+// Everything here is __host__ __device__ so tests/host_check.cu can run the
+// exact index math and butterflies on the CPU.
+#pragma once
+#include <cuda_runtime.h>
+
+#ifndef BH_HD
+#define BH_HD __host__ __device__ __forceinline__
+#endif
+
+namespace bh {
+
+BH_HD float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+BH_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+BH_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV> BH_HD float2 mul_mi(float2 a) {
+    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+template <bool INV> BH_HD float2 cmulw(float2 a, float wr, float wi_fwd) {
+    // multiply by (wr + i*wi) where wi = wi_fwd (forward) or -wi_fwd (inverse)
+    const float wi = INV ? -wi_fwd : wi_fwd;
+    return make_float2(fmaf(a.x, wr, -a.y * wi), fmaf(a.x, wi, a.y * wr));
+}
+
+// ---------------------------------------------------------------------------
+// small DFTs in registers; forward kernel exp(-2 pi i r q / R), INV conjugates.
+// Elements are addressed as v[off + idx*stride] so composite sizes can recurse.
+// ---------------------------------------------------------------------------
+template <bool INV> BH_HD void dft2(float2& a, float2& b) {
+    const float2 t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+
+template <bool INV> BH_HD void dft4(float2& a, float2& b, float2& c, float2& d) {
+    const float2 s0 = cadd(a, c), d0 = csub(a, c);
+    const float2 s1 = cadd(b, d), d1 = mul_mi<INV>(csub(b, d));
+    a = cadd(s0, s1);
+    b = cadd(d0, d1);
+    c = csub(s0, s1);
+    d = csub(d0, d1);
+}
+
+// natural-order in, natural-order out
+template <bool INV> BH_HD void dft8(float2* v) {
+    // R1 = 2 (a), R2 = 4 (b): r = a*4 + b ; X[c + 2 d]
+    const float h = 0.70710678118654752440f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) dft2<INV>(v[b], v[4 + b]);
+    // twiddle Y[c=1][b] *= W8^b
+    v[5] = cmulw<INV>(v[5], h, -h);
+    v[6] = mul_mi<INV>(v[6]);
+    v[7] = cmulw<INV>(v[7], -h, -h);
+    dft4<INV>(v[0], v[1], v[2], v[3]);   // c = 0 -> X[0], X[2], X[4], X[6]
+    dft4<INV>(v[4], v[5], v[6], v[7]);   // c = 1 -> X[1], X[3], X[5], X[7]
+    const float2 x0 = v[0], x2 = v[1], x4 = v[2], x6 = v[3];
+    const float2 x1 = v[4], x3 = v[5], x5 = v[6], x7 = v[7];
+    v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3;
+    v[4] = x4; v[5] = x5; v[6] = x6; v[7] = x7;
+}
+
+template <bool INV> BH_HD void dft16(float2* v) {
+    // R1 = 4 (a), R2 = 4 (b): r = a*4 + b ; X[c + 4 d]
+    const float c1 = 0.92387953251128675613f;  // cos(pi/8)
+    const float s1 = 0.38268343236508977173f;  // sin(pi/8)
+    const float h = 0.70710678118654752440f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) dft4<INV>(v[b], v[4 + b], v[8 + b], v[12 + b]);
+    // Y[c][b] = v[c*4 + b]; twiddle by W16^(c*b) = exp(-2 pi i c b / 16)
+    v[5] = cmulw<INV>(v[5], c1, -s1);     // 1
+    v[6] = cmulw<INV>(v[6], h, -h);       // 2
+    v[7] = cmulw<INV>(v[7], s1, -c1);     // 3
+    v[9] = cmulw<INV>(v[9], h, -h);       // 2
+    v[10] = mul_mi<INV>(v[10]);           // 4
+    v[11] = cmulw<INV>(v[11], -h, -h);    // 6
+    v[13] = cmulw<INV>(v[13], s1, -c1);   // 3
+    v[14] = cmulw<INV>(v[14], -h, -h);    // 6
+    v[15] = cmulw<INV>(v[15], -c1, s1);   // 9
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dft4<INV>(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    // v[c*4 + d] holds X[c + 4 d]  -> transpose the 4x4
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int d = c + 1; d < 4; ++d) {
+            const float2 t = v[c * 4 + d];
+            v[c * 4 + d] = v[d * 4 + c];
+            v[d * 4 + c] = t;
+        }
+}
+
+template <bool INV> BH_HD void dft7(float2* v) {
+    // direct 7-point DFT, exploiting the conjugate symmetry of the roots
+    const float c1 = 0.62348980185873353053f, s1 = 0.78183148246802980871f;
+    const float c2 = -0.22252093395631440429f, s2 = 0.97492791218182360702f;
+    const float c3 = -0.90096886790241912624f, s3 = 0.43388373911755812048f;
+    const float2 p1 = cadd(v[1], v[6]), m1 = csub(v[1], v[6]);
+    const float2 p2 = cadd(v[2], v[5]), m2 = csub(v[2], v[5]);
+    const float2 p3 = cadd(v[3], v[4]), m3 = csub(v[3], v[4]);
+    const float2 x0 = v[0];
+    // real-coefficient parts
+    const float2 a1 = make_float2(x0.x + c1 * p1.x + c2 * p2.x + c3 * p3.x,
+                                  x0.y + c1 * p1.y + c2 * p2.y + c3 * p3.y);
+    const float2 a2 = make_float2(x0.x + c2 * p1.x + c3 * p2.x + c1 * p3.x,
+                                  x0.y + c2 * p1.y + c3 * p2.y + c1 * p3.y);
+    const float2 a3 = make_float2(x0.x + c3 * p1.x + c1 * p2.x + c2 * p3.x,
+                                  x0.y + c3 * p1.y + c1 * p2.y + c2 * p3.y);
+    // sine parts: b_q = sum_r sin(2 pi r q / 7) m_r
+    const float2 b1 = make_float2(s1 * m1.x + s2 * m2.x + s3 * m3.x,
+                                  s1 * m1.y + s2 * m2.y + s3 * m3.y);
+    const float2 b2 = make_float2(s2 * m1.x - s3 * m2.x - s1 * m3.x,
+                                  s2 * m1.y - s3 * m2.y - s1 * m3.y);
+    const float2 b3 = make_float2(s3 * m1.x - s1 * m2.x + s2 * m3.x,
+                                  s3 * m1.y - s1 * m2.y + s2 * m3.y);
+    // forward: X[q] = a_q - i b_q ; X[7-q] = a_q + i b_q   (inverse swaps)
+    v[0] = make_float2(x0.x + p1.x + p2.x + p3.x, x0.y + p1.y + p2.y + p3.y);
+    const float2 ib1 = mul_mi<INV>(b1), ib2 = mul_mi<INV>(b2), ib3 = mul_mi<INV>(b3);
+    v[1] = cadd(a1, ib1); v[6] = csub(a1, ib1);
+    v[2] = cadd(a2, ib2); v[5] = csub(a2, ib2);
+    v[3] = cadd(a3, ib3); v[4] = csub(a3, ib3);
+}
+
+template <int R, bool INV> BH_HD void dft(float2* v) {
+    if (R == 2) dft2<INV>(v[0], v[1]);
+    else if (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
+    else if (R == 8) dft8<INV>(v);
+    else if (R == 16) dft16<INV>(v);
+    else if (R == 7) dft7<INV>(v);
+}
+
+// ---------------------------------------------------------------------------
+// one Stockham pass split in two phases around a barrier
+// ---------------------------------------------------------------------------
+template <int N, int R, int Ns, int Q>
+struct PassShape {
+    static constexpr int NBF = N / R;                 // butterflies per sequence
+    static constexpr int NB = (NBF + Q - 1) / Q;      // butterflies per thread
+};
+
+// phase 1: gather + twiddle + butterfly into registers.
+// s points at sequence w (already offset by w); q is the thread's slot in [0,Q).
+// tw: forward twiddle table exp(-2 pi i m / N), m in [0, N).
+template <int N, int R, int Ns, int Q, int WP, bool INV>
+BH_HD void pass_read(const float2* s, int q, const float2* __restrict__ tw,
+                     float2 (&v)[PassShape<N, R, Ns, Q>::NB][R]) {
+    constexpr int NBF = N / R;
+    constexpr int NB = PassShape<N, R, Ns, Q>::NB;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int j = q + b * Q;
+        if ((NBF % Q == 0) || j < NBF) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[b][r] = s[(j + r * NBF) * WP];
+            if (Ns > 1) {
+                const int k = j % Ns;
+                constexpr int step = N / (Ns * R);
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    float2 w = tw[r * k * step];
+                    if (INV) w.y = -w.y;
+                    v[b][r] = cmul(v[b][r], w);
+                }
+            }
+            dft<R, INV>(v[b]);
+        }
+    }
+}
+
+// phase 2: scatter to the autosorted positions.
+template <int N, int R, int Ns, int Q, int WP>
+BH_HD void pass_write(float2* s, int q, const float2 (&v)[PassShape<N, R, Ns, Q>::NB][R]) {
+    constexpr int NBF = N / R;
+    constexpr int NB = PassShape<N, R, Ns, Q>::NB;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int j = q + b * Q;
+        if ((NBF % Q == 0) || j < NBF) {
+            const int k = j % Ns;
+            const int j0 = (j / Ns) * Ns * R + k;
+#pragma unroll
+            for (int r = 0; r < R; ++r) s[(j0 + r * Ns) * WP] = v[b][r];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// radix plans.  The product of the radices is N; larger radices first keeps the
+// twiddle-free first pass the most expensive one.
+// ---------------------------------------------------------------------------
+template <int N> struct Plan;
+template <> struct Plan<32>   { static constexpr int n = 2; static constexpr int r[3] = {8, 4, 1}; };
+template <> struct Plan<64>   { static constexpr int n = 2; static constexpr int r[3] = {8, 8, 1}; };
+template <> struct Plan<128>  { static constexpr int n = 2; static constexpr int r[3] = {16, 8, 1}; };
+template <> struct Plan<256>  { static constexpr int n = 2; static constexpr int r[3] = {16, 16, 1}; };
+template <> struct Plan<512>  { static constexpr int n = 3; static constexpr int r[3] = {8, 8, 8}; };
+template <> struct Plan<896>  { static constexpr int n = 3; static constexpr int r[3] = {16, 8, 7}; };
+template <> struct Plan<1024> { static constexpr int n = 3; static constexpr int r[3] = {16, 16, 4}; };
+template <> struct Plan<1792> { static constexpr int n = 3; static constexpr int r[3] = {16, 16, 7}; };
+template <> struct Plan<2048> { static constexpr int n = 3; static constexpr int r[3] = {16, 16, 8}; };
+
+#ifdef __CUDACC__
+#define BH_SYNC() __syncthreads()
+#else
+#define BH_SYNC() ((void)0)
+#endif
+
+#ifdef __CUDACC__
+// Full in-place tile FFT executed cooperatively by the CTA (device only).
+template <int N, int Q, int WP, bool INV, int R, int Ns>
+__device__ __forceinline__ void tile_pass(float2* s, int q, const float2* __restrict__ tw) {
+    float2 v[PassShape<N, R, Ns, Q>::NB][R];
+    pass_read<N, R, Ns, Q, WP, INV>(s, q, tw, v);
+    __syncthreads();
+    pass_write<N, R, Ns, Q, WP>(s, q, v);
+    __syncthreads();
+}
+
+template <int N, int Q, int WP, bool INV>
+__device__ __forceinline__ void tile_fft(float2* s, int q, const float2* __restrict__ tw) {
+    using P = Plan<N>;
+    constexpr int R0 = P::r[0], R1 = P::r[1], R2 = P::r[2];
+    tile_pass<N, Q, WP, INV, R0, 1>(s, q, tw);
+    tile_pass<N, Q, WP, INV, R1, R0>(s, q, tw);
+    if constexpr (P::n == 3) tile_pass<N, Q, WP, INV, R2, R0 * R1>(s, q, tw);
+}
+#endif
+
+}  // namespace bh

@@ -1,0 +1,489 @@
+// CUDA kernels of the hologram reward / DBS hot path (sm_100a).
+//
+//  propagation (reset / re-sync):  k_rows_fwd -> k_cols -> k_rows_inv  (+ k_loss_sums)
+//      restates tt.simulate + .abs()**2 + mean(dim=1) + tt.relativeLoss
+//      (reference env.py:123-132, env_1024_24.py:149-166)
+//  incremental path (every step / candidate):  k_eval -> k_commit
+//      replaces the per-step full re-simulation of env.py:170-174,
+//      DBS.py:259-270, DBS_1024_24.py:324-352, env_group.py:96-119 by the
+//      delta identity U' = U + s * shift(h)   (SURVEY.md 8c).
+#pragma once
+#include <cstdint>
+#include "bh_fft.cuh"
+
+namespace bh {
+
+// ---------------------------------------------------------------------------
+// data layout in HBM (per context; E environments)
+//   U     float2 [E][F][N][N]   propagated field of every frame
+//   I     float  [E][G][N][N]   frame-averaged intensity per colour group
+//   T     float  [E][G][N][N]   target
+//   state int8   [E][F][N][N]   binary hologram
+//   sums  double [E][4]         sum I^2, sum I*T, sum T^2, current PSNR
+//   H     float2 [G][P][P]      transfer function, pre-scaled by 1/P^2
+//   h     float2 [G][P][P]      impulse response ifft2(H)
+// ---------------------------------------------------------------------------
+
+struct Result {            // mirrored by bh_result in include/bholo.h (40 bytes)
+    double psnr_after;
+    double d_sii;
+    double d_sit;
+    long long action;
+    int32_t accept;
+    int32_t sgn;
+};
+
+enum { RULE_ENV = 0, RULE_DBS = 1, RULE_NEVER = 2 };
+
+constexpr int TILE_W = 8;          // sequences per FFT tile
+constexpr int TILE_WP = TILE_W + 1;
+
+template <int P> struct FftCfg {
+    static constexpr int T = (P >= 1792) ? 512 : 256;   // threads per CTA
+    static constexpr int Q = T / TILE_W;                // threads per sequence
+    static constexpr size_t smem = size_t(P) * TILE_WP * sizeof(float2);
+};
+
+__device__ __forceinline__ float ld_real(const int8_t* p, size_t i) { return float(p[i]); }
+__device__ __forceinline__ float ld_real(const float* p, size_t i) { return p[i]; }
+
+// ---------------------------------------------------------------------------
+// pass A: FFT along x of W canvas rows.  in: [frames][N][N] real (int8/float)
+// or complex (float2, IS_CPLX); out: buf [frames][P][P].
+// ---------------------------------------------------------------------------
+template <int P, int PAD, typename InT, bool IS_CPLX>
+__global__ void __launch_bounds__(FftCfg<P>::T)
+k_rows_fwd(const InT* __restrict__ in, float2* __restrict__ buf, const float2* __restrict__ tw) {
+    constexpr int N = P / PAD, O = (P - N) / 2, T = FftCfg<P>::T, Q = FftCfg<P>::Q;
+    extern __shared__ float2 s[];
+    const int tid = threadIdx.x, f = blockIdx.y, Y0 = blockIdx.x * TILE_W;
+    float2* out = buf + size_t(f) * P * P;
+    if (PAD > 1 && (Y0 + TILE_W <= O || Y0 >= O + N)) {     // all-zero canvas rows
+        for (int i = tid; i < TILE_W * P; i += T) out[size_t(Y0) * P + i] = make_float2(0.f, 0.f);
+        return;
+    }
+#pragma unroll
+    for (int w = 0; w < TILE_W; ++w) {
+        const int y = Y0 + w - O;
+        const bool rowok = (y >= 0 && y < N);
+        for (int X = tid; X < P; X += T) {
+            const int x = X - O;
+            float2 v = make_float2(0.f, 0.f);
+            if (rowok && x >= 0 && x < N) {
+                const size_t idx = (size_t(f) * N + y) * N + x;
+                if constexpr (IS_CPLX) v = reinterpret_cast<const float2*>(in)[idx];
+                else v.x = ld_real(in, idx);
+            }
+            s[X * TILE_WP + w] = v;
+        }
+    }
+    __syncthreads();
+    tile_fft<P, Q, TILE_WP, false>(s + (tid % TILE_W), tid / TILE_W, tw);
+#pragma unroll
+    for (int w = 0; w < TILE_W; ++w)
+        for (int X = tid; X < P; X += T) out[size_t(Y0 + w) * P + X] = s[X * TILE_WP + w];
+}
+
+// ---------------------------------------------------------------------------
+// pass B: for W canvas columns: FFT along y, multiply by H, inverse FFT along y.
+// In place on buf.  H is pre-scaled by 1/P^2 so no later normalisation.
+// ---------------------------------------------------------------------------
+template <int P, int PAD>
+__global__ void __launch_bounds__(FftCfg<P>::T)
+k_cols(float2* __restrict__ buf, const float2* __restrict__ H, const float2* __restrict__ tw,
+       int Fg) {
+    constexpr int N = P / PAD, O = (P - N) / 2, T = FftCfg<P>::T, Q = FftCfg<P>::Q;
+    extern __shared__ float2 s[];
+    const int tid = threadIdx.x, f = blockIdx.y, X0 = blockIdx.x * TILE_W;
+    float2* b = buf + size_t(f) * P * P + X0;
+    const float2* Hg = H + size_t(f / Fg) * P * P + X0;
+    const int w = tid % TILE_W, q = tid / TILE_W;
+    for (int y = q; y < P; y += Q) {
+        float2 v = make_float2(0.f, 0.f);
+        if (PAD == 1 || (y >= O && y < O + N)) v = b[size_t(y) * P + w];
+        s[y * TILE_WP + w] = v;
+    }
+    __syncthreads();
+    tile_fft<P, Q, TILE_WP, false>(s + w, q, tw);
+    for (int y = q; y < P; y += Q)
+        s[y * TILE_WP + w] = cmul(s[y * TILE_WP + w], __ldg(Hg + size_t(y) * P + w));
+    __syncthreads();
+    tile_fft<P, Q, TILE_WP, true>(s + w, q, tw);
+    for (int y = q; y < P; y += Q)
+        if (PAD == 1 || (y >= O && y < O + N)) b[size_t(y) * P + w] = s[y * TILE_WP + w];
+}
+
+// ---------------------------------------------------------------------------
+// pass C: inverse FFT along x of W window rows for every frame of one colour
+// group; writes the field U and the frame-averaged intensity I.
+// grid (N / W, groups).  buf may alias U when PAD == 1 (in place).
+// WRITE_I = false gives the bare tt.simulate operator.
+// ---------------------------------------------------------------------------
+template <int P, int PAD, bool WRITE_I>
+__global__ void __launch_bounds__(FftCfg<P>::T)
+k_rows_inv(const float2* buf, float2* U, float* __restrict__ I,
+           const float2* __restrict__ tw, int Fg) {
+    constexpr int N = P / PAD, O = (P - N) / 2, T = FftCfg<P>::T, Q = FftCfg<P>::Q;
+    constexpr int NX = (N + T - 1) / T;
+    extern __shared__ float2 s[];
+    const int tid = threadIdx.x, g = blockIdx.y, y0 = blockIdx.x * TILE_W;
+    float acc[TILE_W][NX];
+#pragma unroll
+    for (int w = 0; w < TILE_W; ++w)
+#pragma unroll
+        for (int i = 0; i < NX; ++i) acc[w][i] = 0.f;
+    for (int fi = 0; fi < Fg; ++fi) {
+        const int f = g * Fg + fi;
+        const float2* src = buf + size_t(f) * P * P + size_t(y0 + O) * P;
+        float2* dst = U + size_t(f) * N * N + size_t(y0) * N;
+#pragma unroll
+        for (int w = 0; w < TILE_W; ++w)
+            for (int X = tid; X < P; X += T) s[X * TILE_WP + w] = src[size_t(w) * P + X];
+        __syncthreads();
+        tile_fft<P, Q, TILE_WP, true>(s + (tid % TILE_W), tid / TILE_W, tw);
+#pragma unroll
+        for (int w = 0; w < TILE_W; ++w)
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+                const int x = tid + i * T;
+                if (N % T == 0 || x < N) {
+                    const float2 v = s[(x + O) * TILE_WP + w];
+                    dst[size_t(w) * N + x] = v;
+                    acc[w][i] = fmaf(v.x, v.x, fmaf(v.y, v.y, acc[w][i]));
+                }
+            }
+        __syncthreads();
+    }
+    if (WRITE_I) {
+        const float inv = 1.f / float(Fg);
+        float* Ig = I + size_t(g) * N * N + size_t(y0) * N;
+#pragma unroll
+        for (int w = 0; w < TILE_W; ++w)
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+                const int x = tid + i * T;
+                if (N % T == 0 || x < N) Ig[size_t(w) * N + x] = acc[w][i] * inv;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// deterministic block reduction of two doubles (fixed shuffle/tree order)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum I^2, sum I*T, sum T^2 of one environment -> sums[0..2], PSNR -> sums[3].
+// grid = LOSS_BLOCKS CTAs of 256; the last CTA to finish folds the partials in
+// index order, so the result does not depend on scheduling.
+constexpr int LOSS_BLOCKS = 128;
+__global__ void __launch_bounds__(256)
+k_loss_sums(const float* __restrict__ I, const float* __restrict__ T, size_t n,
+            double* __restrict__ partial /*[LOSS_BLOCKS][3]*/, unsigned* ticket,
+            double* __restrict__ sums /*[4]*/, int relative) {
+    __shared__ double sh[3][8];
+    __shared__ bool last;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t n4 = n / 4;
+    const size_t per = (n4 + gridDim.x - 1) / gridDim.x;
+    const size_t beg = blockIdx.x * per, end = (beg + per < n4) ? beg + per : n4;
+    double a = 0, b = 0, c = 0;
+    for (size_t i = beg + tid; i < end; i += 256) {
+        const float4 iv = __ldg(reinterpret_cast<const float4*>(I) + i);
+        const float4 tv = __ldg(reinterpret_cast<const float4*>(T) + i);
+        a += double(iv.x) * iv.x + double(iv.y) * iv.y + double(iv.z) * iv.z + double(iv.w) * iv.w;
+        b += double(iv.x) * tv.x + double(iv.y) * tv.y + double(iv.z) * tv.z + double(iv.w) * tv.w;
+        c += double(tv.x) * tv.x + double(tv.y) * tv.y + double(tv.z) * tv.z + double(tv.w) * tv.w;
+    }
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; sh[2][warp] = c; }
+    __syncthreads();
+    if (tid == 0) {
+        double x = 0, y = 0, z = 0;
+        for (int i = 0; i < 8; ++i) { x += sh[0][i]; y += sh[1][i]; z += sh[2][i]; }
+        partial[blockIdx.x * 3 + 0] = x;
+        partial[blockIdx.x * 3 + 1] = y;
+        partial[blockIdx.x * 3 + 2] = z;
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && tid == 0) {
+        __threadfence();
+        double x = 0, y = 0, z = 0;
+        for (unsigned i = 0; i < gridDim.x; ++i) {
+            x += __ldcg(partial + i * 3 + 0);
+            y += __ldcg(partial + i * 3 + 1);
+            z += __ldcg(partial + i * 3 + 2);
+        }
+        const double mse = relative ? (z - y * y / x) / double(n) : (x - 2.0 * y + z) / double(n);
+        sums[0] = x; sums[1] = y; sums[2] = z;
+        sums[3] = -10.0 * log10(mse);
+        *ticket = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// incremental path
+// ---------------------------------------------------------------------------
+struct DeltaArgs {
+    float2* U; float* I; const float* T; int8_t* state; const float2* h;
+    double* sums;                  // [E][4]
+    const int32_t* envs;           // [n_tasks] or nullptr (then env_fixed)
+    const long long* actions;      // device
+    const long long* offset_ptr;   // speculative DBS: actions[*offset_ptr + k]; nullptr otherwise
+    long long n_total;             // valid entries of actions
+    int env_fixed;
+    int n_tasks, N, P, F, G, Fg, tiles, rows_per_tile, relative, rule;
+    double2* partials;             // [n_tasks][tiles]
+    unsigned* tickets;             // [n_tasks]
+    Result* results;               // [n_tasks]
+};
+
+struct Decoded {
+    int env, f, g, r, c; float sgn; bool active;
+};
+
+// decode (env.py:158-161) and read the sign of the flip from the resident state
+__device__ __forceinline__ Decoded decode_action(const DeltaArgs& a, int k, long long act) {
+    Decoded d;
+    d.env = a.envs ? a.envs[k] : a.env_fixed;
+    d.f = d.g = d.r = d.c = 0; d.sgn = 0.f;
+    d.active = act >= 0;
+    if (!d.active) return d;
+    const int n2 = a.N * a.N;
+    d.f = int(act / n2);
+    const int pix = int(act - (long long)d.f * n2);
+    d.r = pix / a.N;
+    d.c = pix - d.r * a.N;
+    d.g = d.f / a.Fg;
+    d.sgn = 1.f - 2.f * float(a.state[(size_t(d.env) * a.F + d.f) * n2 + pix]);
+    return d;
+}
+
+// per-pixel delta:  dI = (2 s Re(conj(U) h) + |h|^2) / Fg
+__device__ __forceinline__ float delta_px(float ur, float ui, float hr, float hi, float s2,
+                                          float invFg) {
+    const float a = fmaf(ur, hr, ui * hi);
+    const float m = fmaf(hr, hr, hi * hi);
+    return fmaf(s2, a, m * invFg);
+}
+
+// k_eval: one work item = (task k, tile of rows_per_tile image rows).  Persistent
+// CTAs stride over the items.  Streams U (8 B/px), I, T (4 B/px each) once and
+// the shifted impulse response (8 B/px, L2 resident): 16 N^2 algorithmic HBM
+// bytes per candidate.  The last CTA of a task folds its partials in tile order
+// (deterministic) and writes the PSNR and the accept decision.
+__global__ void __launch_bounds__(256)
+k_eval(const DeltaArgs a) {
+    __shared__ double sh[2][8];
+    __shared__ unsigned s_ticket;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = a.N, P = a.P, nq = N >> 2;
+    const int total = a.n_tasks * a.tiles;
+    const float invFg = 1.f / float(a.Fg);
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int k = item / a.tiles, tile = item - k * a.tiles;
+        long long idx = k;
+        if (a.offset_ptr) idx += *a.offset_ptr;
+        const long long act = (idx < a.n_total) ? a.actions[idx] : -1;
+        const Decoded d = decode_action(a, k, act);
+        if (!d.active) {
+            if (tile == 0 && tid == 0) {
+                Result r; r.psnr_after = 0.0; r.d_sii = 0.0; r.d_sit = 0.0;
+                r.action = -1; r.accept = 0; r.sgn = 0;
+                a.results[k] = r;
+            }
+            continue;
+        }
+        const size_t n2 = size_t(N) * N;
+        const float2* U = a.U + (size_t(d.env) * a.F + d.f) * n2;
+        const float* I = a.I + (size_t(d.env) * a.G + d.g) * n2;
+        const float* T = a.T + (size_t(d.env) * a.G + d.g) * n2;
+        const float2* h = a.h + size_t(d.g) * P * P;
+        const float s2 = 2.f * d.sgn * invFg;
+        float accII = 0.f, accIT = 0.f;
+        const int yend = min(N, (tile + 1) * a.rows_per_tile);
+        for (int y = tile * a.rows_per_tile + warp; y < yend; y += 8) {
+            int hy = y - d.r; if (hy < 0) hy += P;
+            const float2* hrow = h + size_t(hy) * P;
+            const float4* Urow = reinterpret_cast<const float4*>(U + size_t(y) * N);
+            const float4* Irow = reinterpret_cast<const float4*>(I + size_t(y) * N);
+            const float4* Trow = reinterpret_cast<const float4*>(T + size_t(y) * N);
+#pragma unroll 2
+            for (int xq = lane; xq < nq; xq += 32) {
+                const float4 ua = __ldg(Urow + 2 * xq), ub = __ldg(Urow + 2 * xq + 1);
+                const float4 iv = __ldg(Irow + xq), tv = __ldg(Trow + xq);
+                int hx = 4 * xq - d.c; if (hx < 0) hx += P;
+                int hx1 = hx + 1; if (hx1 >= P) hx1 -= P;
+                int hx2 = hx1 + 1; if (hx2 >= P) hx2 -= P;
+                int hx3 = hx2 + 1; if (hx3 >= P) hx3 -= P;
+                const float2 h0 = __ldg(hrow + hx), h1 = __ldg(hrow + hx1);
+                const float2 h2 = __ldg(hrow + hx2), h3 = __ldg(hrow + hx3);
+                const float d0 = delta_px(ua.x, ua.y, h0.x, h0.y, s2, invFg);
+                const float d1 = delta_px(ua.z, ua.w, h1.x, h1.y, s2, invFg);
+                const float d2 = delta_px(ub.x, ub.y, h2.x, h2.y, s2, invFg);
+                const float d3 = delta_px(ub.z, ub.w, h3.x, h3.y, s2, invFg);
+                accII = fmaf(d0, fmaf(2.f, iv.x, d0), accII);
+                accII = fmaf(d1, fmaf(2.f, iv.y, d1), accII);
+                accII = fmaf(d2, fmaf(2.f, iv.z, d2), accII);
+                accII = fmaf(d3, fmaf(2.f, iv.w, d3), accII);
+                accIT = fmaf(d0, tv.x, accIT);
+                accIT = fmaf(d1, tv.y, accIT);
+                accIT = fmaf(d2, tv.z, accIT);
+                accIT = fmaf(d3, tv.w, accIT);
+            }
+        }
+        const double wII = warp_sum(double(accII)), wIT = warp_sum(double(accIT));
+        if (lane == 0) { sh[0][warp] = wII; sh[1][warp] = wIT; }
+        __syncthreads();
+        if (tid == 0) {
+            double x = 0, y = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { x += sh[0][i]; y += sh[1][i]; }
+            a.partials[size_t(k) * a.tiles + tile] = make_double2(x, y);
+            __threadfence();
+            s_ticket = atomicAdd(a.tickets + k, 1u);
+        }
+        __syncthreads();
+        if (s_ticket == unsigned(a.tiles - 1)) {          // last tile of task k
+            __threadfence();
+            // fixed-order fold: thread i takes tiles i, i+256, ...; then a tree
+            double x = 0, y = 0;
+            for (int i = tid; i < a.tiles; i += 256) {
+                const double2 p = __ldcg(a.partials + size_t(k) * a.tiles + i);
+                x += p.x; y += p.y;
+            }
+            x = warp_sum(x); y = warp_sum(y);
+            __syncthreads();
+            if (lane == 0) { sh[0][warp] = x; sh[1][warp] = y; }
+            __syncthreads();
+            if (tid == 0) {
+                double dII = 0, dIT = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { dII += sh[0][i]; dIT += sh[1][i]; }
+                const double* S = a.sums + size_t(d.env) * 4;
+                const double sii = S[0] + dII, sit = S[1] + dIT, stt = S[2];
+                const double n = double(a.G) * double(n2);
+                const double mse = a.relative ? (stt - sit * sit / sii) / n
+                                              : (sii - 2.0 * sit + stt) / n;
+                const double psnr = -10.0 * log10(mse);
+                const double prev = S[3];
+                int acc = 0;
+                if (a.rule == RULE_ENV) acc = !(psnr - prev < 0.0);     // env.py:191
+                else if (a.rule == RULE_DBS) acc = (psnr > prev);       // DBS.py:273
+                Result r; r.psnr_after = psnr; r.d_sii = dII; r.d_sit = dIT;
+                r.action = act; r.accept = acc; r.sgn = int(d.sgn);
+                a.results[k] = r;
+                a.tickets[k] = 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// k_commit: applies every accepted task: U_f += s*shift(h), I_g += dI, flips the
+// state byte and advances the running sums.  24 N^2 algorithmic HBM bytes per
+// accepted flip.  Tasks of one launch must target distinct environments.
+__global__ void __launch_bounds__(256)
+k_commit(const DeltaArgs a) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = a.N, P = a.P, nq = N >> 2;
+    const int total = a.n_tasks * a.tiles;
+    const float invFg = 1.f / float(a.Fg);
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int k = item / a.tiles, tile = item - k * a.tiles;
+        const Result res = a.results[k];
+        if (!res.accept) continue;
+        Decoded d = decode_action(a, k, res.action);
+        d.sgn = float(res.sgn);            // the state byte may already be flipped
+        const size_t n2 = size_t(N) * N;
+        float2* U = a.U + (size_t(d.env) * a.F + d.f) * n2;
+        float* I = a.I + (size_t(d.env) * a.G + d.g) * n2;
+        const float2* h = a.h + size_t(d.g) * P * P;
+        const float s2 = 2.f * d.sgn * invFg;
+        const int yend = min(N, (tile + 1) * a.rows_per_tile);
+        for (int y = tile * a.rows_per_tile + warp; y < yend; y += 8) {
+            int hy = y - d.r; if (hy < 0) hy += P;
+            const float2* hrow = h + size_t(hy) * P;
+            float4* Urow = reinterpret_cast<float4*>(U + size_t(y) * N);
+            float4* Irow = reinterpret_cast<float4*>(I + size_t(y) * N);
+#pragma unroll 2
+            for (int xq = lane; xq < nq; xq += 32) {
+                float4 ua = Urow[2 * xq], ub = Urow[2 * xq + 1];
+                float4 iv = Irow[xq];
+                int hx = 4 * xq - d.c; if (hx < 0) hx += P;
+                int hx1 = hx + 1; if (hx1 >= P) hx1 -= P;
+                int hx2 = hx1 + 1; if (hx2 >= P) hx2 -= P;
+                int hx3 = hx2 + 1; if (hx3 >= P) hx3 -= P;
+                const float2 h0 = __ldg(hrow + hx), h1 = __ldg(hrow + hx1);
+                const float2 h2 = __ldg(hrow + hx2), h3 = __ldg(hrow + hx3);
+                iv.x += delta_px(ua.x, ua.y, h0.x, h0.y, s2, invFg);
+                iv.y += delta_px(ua.z, ua.w, h1.x, h1.y, s2, invFg);
+                iv.z += delta_px(ub.x, ub.y, h2.x, h2.y, s2, invFg);
+                iv.w += delta_px(ub.z, ub.w, h3.x, h3.y, s2, invFg);
+                ua.x = fmaf(d.sgn, h0.x, ua.x); ua.y = fmaf(d.sgn, h0.y, ua.y);
+                ua.z = fmaf(d.sgn, h1.x, ua.z); ua.w = fmaf(d.sgn, h1.y, ua.w);
+                ub.x = fmaf(d.sgn, h2.x, ub.x); ub.y = fmaf(d.sgn, h2.y, ub.y);
+                ub.z = fmaf(d.sgn, h3.x, ub.z); ub.w = fmaf(d.sgn, h3.y, ub.w);
+                Urow[2 * xq] = ua; Urow[2 * xq + 1] = ub;
+                Irow[xq] = iv;
+            }
+        }
+        if (tile == 0 && tid == 0) {
+            int8_t* st = a.state + (size_t(d.env) * a.F + d.f) * n2 + size_t(d.r) * N + d.c;
+            *st = int8_t(1 - *st);
+            double* S = a.sums + size_t(d.env) * 4;
+            S[0] += res.d_sii;
+            S[1] += res.d_sit;
+            S[3] = res.psnr_after;
+        }
+    }
+}
+
+// k_recon_candidate: out_g += dI of one (uncommitted) candidate flip; used to
+// materialise obs["recon_image"] of a rejected step (env.py:176-181, appendix B-2).
+__global__ void __launch_bounds__(256)
+k_recon_candidate(const float2* __restrict__ U, const float2* __restrict__ h,
+                  float* __restrict__ out_g, int N, int P, int r, int c, float sgn, int Fg) {
+    const float invFg = 1.f / float(Fg), s2 = 2.f * sgn * invFg;
+    const size_t n2 = size_t(N) * N;
+    for (size_t p = size_t(blockIdx.x) * blockDim.x + threadIdx.x; p < n2;
+         p += size_t(gridDim.x) * blockDim.x) {
+        const int y = int(p / N), x = int(p - size_t(y) * N);
+        int hy = y - r; if (hy < 0) hy += P;
+        int hx = x - c; if (hx < 0) hx += P;
+        const float2 u = U[p], hv = __ldg(h + size_t(hy) * P + hx);
+        out_g[p] += delta_px(u.x, u.y, hv.x, hv.y, s2, invFg);
+    }
+}
+
+// speculative greedy DBS: among the K results of one batch (all evaluated
+// against the same state) keep the first accepted one, cancel the rest, log
+// the decisions and advance the cursor (DBS.py:247-294 order is preserved:
+// candidates after the first accept are re-evaluated by the next batch).
+__global__ void k_dbs_select(Result* results, int K, long long* offset_ptr, long long n_total,
+                             uint8_t* accepted_out, double* trace_out, long long* n_accepted) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long off = *offset_ptr;
+    long long cnt = n_total - off;
+    if (cnt <= 0) return;
+    if (cnt > K) cnt = K;
+    int first = -1;
+    for (int k = 0; k < cnt; ++k)
+        if (results[k].accept) { first = k; break; }
+    const int used = first >= 0 ? first + 1 : int(cnt);
+    for (int k = 0; k < used; ++k) {
+        accepted_out[off + k] = (k == first) ? 1 : 0;
+        if (trace_out) trace_out[off + k] = results[k].psnr_after;
+    }
+    for (int k = 0; k < K; ++k)
+        if (k != first) results[k].accept = 0;
+    if (first >= 0) *n_accepted += 1;
+    *offset_ptr = off + used;
+}
+
+}  // namespace bh

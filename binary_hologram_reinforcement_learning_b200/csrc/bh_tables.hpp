@@ -1,0 +1,152 @@
+// Host-side (double precision) construction of the per-wavelength tables:
+//   H  angular-spectrum transfer function on the P x P FFT grid
+//   h  = ifft2(H), the field of a unit pixel (the impulse the delta kernel shifts)
+//   tw forward twiddles exp(-2 pi i m / P)
+// Restates what tt.simulate multiplies by (reference call sites env.py:127,172;
+// SURVEY.md 8c).  The phase 2 pi z sqrt(1/wl^2 - f^2) is ~2.4e4 rad, so it is
+// formed and reduced in double and only then rounded to float.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <tuple>
+#include <vector>
+
+namespace bh {
+
+using cd = std::complex<double>;
+
+template <typename Fn>
+inline void parallel_for(int n, Fn fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = int(std::min<unsigned>(hw ? hw : 1u, 32u));
+    nt = std::min(nt, n);
+    if (nt <= 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([=]() { for (int i = t; i < n; i += nt) fn(i); });
+    for (auto& x : th) x.join();
+}
+
+// recursive decimation-in-time FFT for any n (O(n * sum of prime factors)).
+// roots[i] = exp(sign * 2 pi i * i / N0); rs = N0 / n.
+inline void fft_rec(const cd* in, cd* out, int n, int stride, const cd* roots, int N0, int rs) {
+    if (n == 1) { out[0] = in[0]; return; }
+    int p = 2;
+    while (n % p) ++p;
+    const int m = n / p;
+    for (int q = 0; q < p; ++q) fft_rec(in + size_t(q) * stride, out + size_t(q) * m, m, stride * p, roots, N0, rs * p);
+    cd tbuf[32], xbuf[32];
+    std::vector<cd> tvec, xvec;
+    cd *t = tbuf, *x = xbuf;
+    if (p > 32) { tvec.resize(p); xvec.resize(p); t = tvec.data(); x = xvec.data(); }
+    for (int k = 0; k < m; ++k) {
+        for (int q = 0; q < p; ++q)
+            t[q] = out[size_t(q) * m + k] * roots[(int64_t(q) * k * rs) % N0];
+        for (int j = 0; j < p; ++j) {
+            cd acc = t[0];
+            for (int q = 1; q < p; ++q) acc += t[q] * roots[(int64_t(q) * j * m * rs) % N0];
+            x[j] = acc;
+        }
+        for (int j = 0; j < p; ++j) out[size_t(k) + size_t(m) * j] = x[j];
+    }
+}
+
+// in-place unnormalised 2-D transform of a P x P array, sign = -1 forward, +1 inverse
+inline void fft2_host(std::vector<cd>& a, int P, int sign) {
+    std::vector<cd> roots(P);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int i = 0; i < P; ++i) roots[i] = cd(std::cos(two_pi * i / P), sign * std::sin(two_pi * i / P));
+    parallel_for(P, [&](int y) {
+        std::vector<cd> tmp(P);
+        fft_rec(&a[size_t(y) * P], tmp.data(), P, 1, roots.data(), P, 1);
+        std::copy(tmp.begin(), tmp.end(), a.begin() + size_t(y) * P);
+    });
+    parallel_for(P, [&](int x) {
+        std::vector<cd> col(P), tmp(P);
+        for (int y = 0; y < P; ++y) col[y] = a[size_t(y) * P + x];
+        fft_rec(col.data(), tmp.data(), P, 1, roots.data(), P, 1);
+        for (int y = 0; y < P; ++y) a[size_t(y) * P + x] = tmp[y];
+    });
+}
+
+struct HostTables {
+    int P = 0;
+    std::vector<float> H;   // interleaved complex, pre-scaled by 1/P^2
+    std::vector<float> h;   // interleaved complex
+};
+
+inline double fft_freq(int i, int P, double dx) {
+    const int k = (i < (P + 1) / 2) ? i : i - P;       // numpy.fft.fftfreq ordering
+    return double(k) / (double(P) * dx);
+}
+
+inline std::shared_ptr<HostTables> build_tables(int P, double wl, double dx, double z, int method) {
+    auto t = std::make_shared<HostTables>();
+    t->P = P;
+    std::vector<cd> Hd(size_t(P) * P);
+    const double two_pi = 6.283185307179586476925286766559;
+    const double pi = 3.1415926535897932384626433832795;
+    parallel_for(P, [&](int y) {
+        const double fy = fft_freq(y, P, dx);
+        for (int x = 0; x < P; ++x) {
+            const double fx = fft_freq(x, P, dx);
+            cd v(0.0, 0.0);
+            if (method == 0) {
+                const double rad = 1.0 / (wl * wl) - fx * fx - fy * fy;
+                if (rad > 0.0) {
+                    const double ph = two_pi * z * std::sqrt(rad);
+                    v = cd(std::cos(ph), std::sin(ph));
+                }
+            } else {
+                const double ph = two_pi * z / wl - pi * wl * z * (fx * fx + fy * fy);
+                v = cd(std::cos(ph), std::sin(ph));
+            }
+            Hd[size_t(y) * P + x] = v;
+        }
+    });
+    const double inv = 1.0 / (double(P) * double(P));
+    t->H.resize(size_t(P) * P * 2);
+    for (size_t i = 0; i < size_t(P) * P; ++i) {
+        t->H[2 * i] = float(Hd[i].real() * inv);
+        t->H[2 * i + 1] = float(Hd[i].imag() * inv);
+    }
+    fft2_host(Hd, P, +1);
+    t->h.resize(size_t(P) * P * 2);
+    for (size_t i = 0; i < size_t(P) * P; ++i) {
+        t->h[2 * i] = float(Hd[i].real() * inv);
+        t->h[2 * i + 1] = float(Hd[i].imag() * inv);
+    }
+    return t;
+}
+
+// process-wide cache: contexts of the same geometry share the host tables
+inline std::shared_ptr<HostTables> get_tables(int P, double wl, double dx, double z, int method) {
+    using Key = std::tuple<int, double, double, double, int>;
+    static std::mutex mu;
+    static std::map<Key, std::shared_ptr<HostTables>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    const Key key(P, wl, dx, z, method);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    auto t = build_tables(P, wl, dx, z, method);
+    cache[key] = t;
+    return t;
+}
+
+inline std::vector<float> build_twiddles(int P) {
+    std::vector<float> tw(size_t(P) * 2);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int i = 0; i < P; ++i) {
+        tw[2 * i] = float(std::cos(two_pi * i / P));
+        tw[2 * i + 1] = float(-std::sin(two_pi * i / P));
+    }
+    return tw;
+}
+
+}  // namespace bh

@@ -1,0 +1,685 @@
+// C ABI of the B200 hologram reward / DBS engine (see include/bholo.h).
+// Host logic only: context, table upload, launch sequencing.  Kernels live in
+// bh_kernels.cuh / bh_fft.cuh.  Built with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/bholo.h"
+#include "bh_kernels.cuh"
+#include "bh_tables.hpp"
+
+using namespace bh;
+
+static_assert(sizeof(Result) == sizeof(bh_result), "Result must mirror bh_result");
+static_assert(sizeof(bh_result) == 40, "bh_result layout");
+
+static thread_local std::string g_err;
+
+struct bh_ctx {
+    int device = 0, E = 0, N = 0, F = 0, G = 0, Fg = 0, P = 0, pad = 1, relative = 1, method = 0;
+    double dx = 0, z = 0;
+    std::vector<double> wl;
+    cudaStream_t stream = nullptr;
+    size_t n2 = 0;
+    float2 *dH = nullptr, *dh = nullptr, *dtw = nullptr, *dU = nullptr, *dscratch = nullptr;
+    float *dI = nullptr, *dT = nullptr, *drecon = nullptr;
+    int8_t* dstate = nullptr;
+    double* dsums = nullptr;
+    double* dloss_partial = nullptr;
+    unsigned* dloss_ticket = nullptr;
+    int max_tasks = 0, tiles = 0, rows_per_tile = 8, grid_cap = 0;
+    int32_t* d_envs = nullptr;
+    long long* d_actions = nullptr;
+    Result* d_results = nullptr;
+    double2* d_partials = nullptr;
+    unsigned* d_tickets = nullptr;
+    long long* d_scalars = nullptr;      // [0] dbs cursor, [1] accepted count
+    int32_t* h_envs = nullptr;           // pinned staging
+    long long* h_actions = nullptr;
+    Result* h_results = nullptr;
+    long long* h_scalars = nullptr;
+    double* h_sums = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    std::string err;
+};
+
+#define BH_FAIL(ctx, code, ...)                                   \
+    do {                                                          \
+        char _b[512];                                             \
+        snprintf(_b, sizeof _b, __VA_ARGS__);                     \
+        if (ctx) (ctx)->err = _b;                                 \
+        g_err = _b;                                               \
+        return (code);                                            \
+    } while (0)
+
+#define BH_CUDA(ctx, expr)                                                                  \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            BH_FAIL(ctx, -2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define BH_CHECK_CTX(ctx)                       \
+    do {                                        \
+        if (!(ctx)) BH_FAIL((bh_ctx*)nullptr, -1, "null context"); \
+        cudaError_t _e = cudaSetDevice((ctx)->device);             \
+        if (_e != cudaSuccess) BH_FAIL(ctx, -2, "cudaSetDevice: %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+#define BH_CHECK_ENV(ctx, env) \
+    do { if ((env) < 0 || (env) >= (ctx)->E) BH_FAIL(ctx, -3, "env %d out of range [0,%d)", (env), (ctx)->E); } while (0)
+
+extern "C" int bh_abi_version(void) { return 1; }
+
+extern "C" const char* bh_last_error(const bh_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_err.c_str();
+}
+
+// ---------------------------------------------------------------------------
+// propagation dispatch over the supported FFT sides
+// ---------------------------------------------------------------------------
+template <int P, int PAD, typename InT, bool CPLX>
+static cudaError_t launch_prop(const InT* in, float2* buf, float2* U, float* I, const float2* H,
+                               const float2* tw, int frames, int groups, int Fg, bool write_I,
+                               cudaStream_t st) {
+    constexpr int N = P / PAD;
+    constexpr int T = FftCfg<P>::T;
+    const size_t smem = FftCfg<P>::smem;
+    auto kA = k_rows_fwd<P, PAD, InT, CPLX>;
+    auto kB = k_cols<P, PAD>;
+    auto kC1 = k_rows_inv<P, PAD, true>;
+    auto kC0 = k_rows_inv<P, PAD, false>;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return e;
+    if ((e = cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return e;
+    if ((e = cudaFuncSetAttribute(kC1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return e;
+    if ((e = cudaFuncSetAttribute(kC0, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return e;
+    kA<<<dim3(P / TILE_W, frames), T, smem, st>>>(in, buf, tw);
+    kB<<<dim3(P / TILE_W, frames), T, smem, st>>>(buf, H, tw, Fg);
+    if (write_I) kC1<<<dim3(N / TILE_W, groups), T, smem, st>>>(buf, U, I, tw, Fg);
+    else kC0<<<dim3(N / TILE_W, groups), T, smem, st>>>(buf, U, I, tw, Fg);
+    return cudaGetLastError();
+}
+
+template <typename InT, bool CPLX>
+static cudaError_t dispatch_prop(int P, int pad, const InT* in, float2* buf, float2* U, float* I,
+                                 const float2* H, const float2* tw, int frames, int groups, int Fg,
+                                 bool write_I, cudaStream_t st, bool* supported) {
+    *supported = true;
+#define BH_CASE(PP, PD) \
+    if (P == PP && pad == PD) return launch_prop<PP, PD, InT, CPLX>(in, buf, U, I, H, tw, frames, groups, Fg, write_I, st);
+    BH_CASE(32, 1) BH_CASE(64, 1) BH_CASE(128, 1) BH_CASE(256, 1) BH_CASE(512, 1)
+    BH_CASE(896, 1) BH_CASE(1024, 1)
+    BH_CASE(64, 2) BH_CASE(128, 2) BH_CASE(256, 2) BH_CASE(512, 2) BH_CASE(1792, 2) BH_CASE(2048, 2)
+#undef BH_CASE
+    *supported = false;
+    return cudaSuccess;
+}
+
+static bool fft_side_supported(int P, int pad) {
+    static const int p1[] = {32, 64, 128, 256, 512, 896, 1024};
+    static const int p2[] = {64, 128, 256, 512, 1792, 2048};
+    if (pad == 1) { for (int v : p1) if (v == P) return true; }
+    if (pad == 2) { for (int v : p2) if (v == P) return true; }
+    return false;
+}
+
+static int propagate_env(bh_ctx* c, int env) {
+    const size_t n2 = c->n2;
+    const int8_t* st = c->dstate + size_t(env) * c->F * n2;
+    float2* U = c->dU + size_t(env) * c->F * n2;
+    float* I = c->dI + size_t(env) * c->G * n2;
+    const float* T = c->dT + size_t(env) * c->G * n2;
+    float2* buf = (c->pad == 1) ? U : c->dscratch;
+    bool ok = false;
+    BH_CUDA(c, (dispatch_prop<int8_t, false>(c->P, c->pad, st, buf, U, I, c->dH, c->dtw, c->F, c->G,
+                                             c->Fg, true, c->stream, &ok)));
+    if (!ok) BH_FAIL(c, -4, "unsupported FFT side P=%d pad=%d", c->P, c->pad);
+    k_loss_sums<<<LOSS_BLOCKS, 256, 0, c->stream>>>(I, T, size_t(c->G) * n2, c->dloss_partial,
+                                                    c->dloss_ticket, c->dsums + size_t(env) * 4,
+                                                    c->relative);
+    BH_CUDA(c, cudaGetLastError());
+    c->launches += 4;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" int bh_destroy(bh_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream); else cudaDeviceSynchronize();
+    cudaFree(c->dH); cudaFree(c->dh); cudaFree(c->dtw); cudaFree(c->dU); cudaFree(c->dscratch);
+    cudaFree(c->dI); cudaFree(c->dT); cudaFree(c->drecon); cudaFree(c->dstate); cudaFree(c->dsums);
+    cudaFree(c->dloss_partial); cudaFree(c->dloss_ticket);
+    cudaFree(c->d_envs); cudaFree(c->d_actions); cudaFree(c->d_results); cudaFree(c->d_partials);
+    cudaFree(c->d_tickets); cudaFree(c->d_scalars);
+    cudaFreeHost(c->h_envs); cudaFreeHost(c->h_actions); cudaFreeHost(c->h_results);
+    cudaFreeHost(c->h_scalars); cudaFreeHost(c->h_sums);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+    return 0;
+}
+
+extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int G, const double* wl,
+                         double dx, double z, int pad, int relative, int method) {
+    bh_ctx* nul = nullptr;
+    if (!out) BH_FAIL(nul, -1, "out is null");
+    *out = nullptr;
+    if (n_env < 1 || N < 8 || F < 1 || G < 1 || !wl) BH_FAIL(nul, -1, "bad shape arguments");
+    if (F % G) BH_FAIL(nul, -1, "F=%d is not a multiple of G=%d", F, G);
+    if (N % 8) BH_FAIL(nul, -1, "N=%d must be a multiple of 8", N);
+    if (pad != 1 && pad != 2) BH_FAIL(nul, -1, "pad must be 1 or 2");
+    if (method != BH_METHOD_ASM && method != BH_METHOD_FRESNEL) BH_FAIL(nul, -1, "bad method");
+    if (!fft_side_supported(N * pad, pad))
+        BH_FAIL(nul, -4, "unsupported FFT side P=%d (pad=%d); supported: pad 1 {32,64,128,256,512,896,1024}, pad 2 {64,128,256,512,1792,2048}", N * pad, pad);
+    int ndev = 0;
+    BH_CUDA(nul, cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) BH_FAIL(nul, -1, "device %d not present (%d devices)", device, ndev);
+    BH_CUDA(nul, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BH_CUDA(nul, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) BH_FAIL(nul, -5, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+    bh_ctx* c = new bh_ctx;
+    c->device = device; c->E = n_env; c->N = N; c->F = F; c->G = G; c->Fg = F / G;
+    c->P = N * pad; c->pad = pad; c->relative = relative ? 1 : 0; c->method = method;
+    c->dx = dx; c->z = z; c->wl.assign(wl, wl + G);
+    c->n2 = size_t(N) * N;
+    const size_t n2 = c->n2, p2 = size_t(c->P) * c->P;
+    int rc = 0;
+#define BH_TRY(expr)                                                                   \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess && rc == 0) {                                            \
+            char _b[256];                                                              \
+            snprintf(_b, sizeof _b, "%s failed: %s", #expr, cudaGetErrorString(_e));   \
+            g_err = _b; rc = -2;                                                       \
+        }                                                                              \
+    } while (0)
+    BH_TRY(cudaMalloc(&c->dH, size_t(G) * p2 * sizeof(float2)));
+    BH_TRY(cudaMalloc(&c->dh, size_t(G) * p2 * sizeof(float2)));
+    BH_TRY(cudaMalloc(&c->dtw, size_t(c->P) * sizeof(float2)));
+    BH_TRY(cudaMalloc(&c->dU, size_t(n_env) * F * n2 * sizeof(float2)));
+    if (pad == 2) BH_TRY(cudaMalloc(&c->dscratch, size_t(F) * p2 * sizeof(float2)));
+    BH_TRY(cudaMalloc(&c->dI, size_t(n_env) * G * n2 * sizeof(float)));
+    BH_TRY(cudaMalloc(&c->dT, size_t(n_env) * G * n2 * sizeof(float)));
+    BH_TRY(cudaMalloc(&c->drecon, size_t(G) * n2 * sizeof(float)));
+    BH_TRY(cudaMalloc(&c->dstate, size_t(n_env) * F * n2));
+    BH_TRY(cudaMalloc(&c->dsums, size_t(n_env) * 4 * sizeof(double)));
+    BH_TRY(cudaMalloc(&c->dloss_partial, LOSS_BLOCKS * 3 * sizeof(double)));
+    BH_TRY(cudaMalloc(&c->dloss_ticket, sizeof(unsigned)));
+    c->rows_per_tile = 8;
+    c->tiles = (N + c->rows_per_tile - 1) / c->rows_per_tile;
+    c->max_tasks = std::max(4096, n_env);
+    BH_TRY(cudaMalloc(&c->d_envs, size_t(c->max_tasks) * sizeof(int32_t)));
+    BH_TRY(cudaMalloc(&c->d_actions, size_t(c->max_tasks) * sizeof(long long)));
+    BH_TRY(cudaMalloc(&c->d_results, size_t(c->max_tasks) * sizeof(Result)));
+    BH_TRY(cudaMalloc(&c->d_partials, size_t(c->max_tasks) * c->tiles * sizeof(double2)));
+    BH_TRY(cudaMalloc(&c->d_tickets, size_t(c->max_tasks) * sizeof(unsigned)));
+    BH_TRY(cudaMalloc(&c->d_scalars, 4 * sizeof(long long)));
+    BH_TRY(cudaMallocHost(&c->h_envs, size_t(c->max_tasks) * sizeof(int32_t)));
+    BH_TRY(cudaMallocHost(&c->h_actions, size_t(c->max_tasks) * sizeof(long long)));
+    BH_TRY(cudaMallocHost(&c->h_results, size_t(c->max_tasks) * sizeof(Result)));
+    BH_TRY(cudaMallocHost(&c->h_scalars, 4 * sizeof(long long)));
+    BH_TRY(cudaMallocHost(&c->h_sums, size_t(n_env) * 4 * sizeof(double)));
+    BH_TRY(cudaEventCreate(&c->ev0));
+    BH_TRY(cudaEventCreate(&c->ev1));
+    if (rc == 0) {
+        BH_TRY(cudaMemset(c->dloss_ticket, 0, sizeof(unsigned)));
+        BH_TRY(cudaMemset(c->d_tickets, 0, size_t(c->max_tasks) * sizeof(unsigned)));
+        BH_TRY(cudaMemset(c->dsums, 0, size_t(n_env) * 4 * sizeof(double)));
+        BH_TRY(cudaMemset(c->dT, 0, size_t(n_env) * G * n2 * sizeof(float)));
+        BH_TRY(cudaMemset(c->dstate, 0, size_t(n_env) * F * n2));
+        BH_TRY(cudaMemset(c->dU, 0, size_t(n_env) * F * n2 * sizeof(float2)));
+        BH_TRY(cudaMemset(c->dI, 0, size_t(n_env) * G * n2 * sizeof(float)));
+        for (int g = 0; g < G && rc == 0; ++g) {
+            auto t = get_tables(c->P, wl[g], dx, z, method);
+            BH_TRY(cudaMemcpy(c->dH + size_t(g) * p2, t->H.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
+            BH_TRY(cudaMemcpy(c->dh + size_t(g) * p2, t->h.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
+        }
+        auto tw = build_twiddles(c->P);
+        BH_TRY(cudaMemcpy(c->dtw, tw.data(), size_t(c->P) * sizeof(float2), cudaMemcpyHostToDevice));
+        int nb = 0;
+        BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eval, 256, 0));
+        c->grid_cap = std::max(1, nb) * prop.multiProcessorCount;
+    }
+#undef BH_TRY
+    if (rc) { std::string keep = g_err; bh_destroy(c); g_err = keep; return rc; }
+    *out = c;
+    return 0;
+}
+
+extern "C" int bh_set_stream(bh_ctx* c, void* s) {
+    BH_CHECK_CTX(c);
+    c->stream = reinterpret_cast<cudaStream_t>(s);
+    return 0;
+}
+
+extern "C" int bh_max_tasks(const bh_ctx* c) { return c ? c->max_tasks : 0; }
+extern "C" int64_t bh_launch_count(const bh_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" void* bh_device_ptr(bh_ctx* c, int which) {
+    if (!c) return nullptr;
+    switch (which) {
+        case 0: return c->dU; case 1: return c->dI; case 2: return c->dT; case 3: return c->dstate;
+        case 4: return c->dsums; case 5: return c->dh; case 6: return c->dH;
+    }
+    return nullptr;
+}
+
+extern "C" int bh_set_target(bh_ctx* c, int env, const float* T, int on_host) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    if (!T) BH_FAIL(c, -1, "target is null");
+    const size_t bytes = size_t(c->G) * c->n2 * sizeof(float);
+    BH_CUDA(c, cudaMemcpyAsync(c->dT + size_t(env) * c->G * c->n2, T, bytes,
+                               on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
+    if (on_host) BH_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int bh_load_state(bh_ctx* c, int env, const int8_t* state, int on_host) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    if (!state) BH_FAIL(c, -1, "state is null");
+    const size_t bytes = size_t(c->F) * c->n2;
+    BH_CUDA(c, cudaMemcpyAsync(c->dstate + size_t(env) * bytes, state, bytes,
+                               on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
+    int rc = propagate_env(c, env);
+    if (rc) return rc;
+    if (on_host) BH_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int bh_resync(bh_ctx* c, int env) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    return propagate_env(c, env);
+}
+
+extern "C" int bh_get_metrics(bh_ctx* c, int env, double* psnr, double* mse, double* sums3) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    double* hs = c->h_sums + size_t(env) * 4;
+    BH_CUDA(c, cudaMemcpyAsync(hs, c->dsums + size_t(env) * 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA(c, cudaStreamSynchronize(c->stream));
+    const double n = double(c->G) * double(c->n2);
+    const double m = c->relative ? (hs[2] - hs[1] * hs[1] / hs[0]) / n : (hs[0] - 2.0 * hs[1] + hs[2]) / n;
+    if (psnr) *psnr = hs[3];
+    if (mse) *mse = m;
+    if (sums3) { sums3[0] = hs[0]; sums3[1] = hs[1]; sums3[2] = hs[2]; }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// incremental path
+// ---------------------------------------------------------------------------
+static DeltaArgs make_args(bh_ctx* c, int n, int env_fixed, const int32_t* d_envs,
+                           const long long* d_actions, int rule, Result* d_results) {
+    DeltaArgs a;
+    a.U = c->dU; a.I = c->dI; a.T = c->dT; a.state = c->dstate; a.h = c->dh; a.sums = c->dsums;
+    a.envs = d_envs; a.actions = d_actions; a.offset_ptr = nullptr; a.n_total = n;
+    a.env_fixed = env_fixed;
+    a.n_tasks = n; a.N = c->N; a.P = c->P; a.F = c->F; a.G = c->G; a.Fg = c->Fg;
+    a.tiles = c->tiles; a.rows_per_tile = c->rows_per_tile; a.relative = c->relative; a.rule = rule;
+    a.partials = c->d_partials; a.tickets = c->d_tickets; a.results = d_results;
+    return a;
+}
+
+static inline int delta_grid(const bh_ctx* c, int n) {
+    const long long total = (long long)n * c->tiles;
+    return int(std::min<long long>(total, c->grid_cap));
+}
+
+static int launch_eval(bh_ctx* c, const DeltaArgs& a) {
+    k_eval<<<delta_grid(c, a.n_tasks), 256, 0, c->stream>>>(a);
+    c->launches += 1;
+    return 0;
+}
+static int launch_commit(bh_ctx* c, const DeltaArgs& a) {
+    k_commit<<<delta_grid(c, a.n_tasks), 256, 0, c->stream>>>(a);
+    c->launches += 1;
+    return 0;
+}
+
+static int check_actions(bh_ctx* c, const int64_t* actions, int64_t n) {
+    const int64_t lim = int64_t(c->F) * int64_t(c->n2);
+    for (int64_t i = 0; i < n; ++i)
+        if (actions[i] < 0 || actions[i] >= lim)
+            BH_FAIL(c, -3, "action[%lld]=%lld out of range [0,%lld)", (long long)i, (long long)actions[i], (long long)lim);
+    return 0;
+}
+
+extern "C" int bh_eval_flips_device(bh_ctx* c, int env, int n, const int32_t* d_env_ids,
+                                    const int64_t* d_actions, bh_result* d_results) {
+    BH_CHECK_CTX(c);
+    if (n < 0 || n > c->max_tasks) BH_FAIL(c, -3, "n=%d exceeds max_tasks=%d", n, c->max_tasks);
+    if (n == 0) return 0;
+    if (!d_env_ids) BH_CHECK_ENV(c, env);
+    DeltaArgs a = make_args(c, n, env, d_env_ids, reinterpret_cast<const long long*>(d_actions),
+                            RULE_NEVER, reinterpret_cast<Result*>(d_results));
+    launch_eval(c, a);
+    BH_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bh_eval_flips(bh_ctx* c, int env, int64_t n, const int32_t* env_ids,
+                             const int64_t* actions, double* psnr_after) {
+    BH_CHECK_CTX(c);
+    if (n < 0 || !actions || !psnr_after) BH_FAIL(c, -1, "bad arguments");
+    if (!env_ids) BH_CHECK_ENV(c, env);
+    if (int rc = check_actions(c, actions, n)) return rc;
+    if (env_ids)
+        for (int64_t i = 0; i < n; ++i) BH_CHECK_ENV(c, env_ids[i]);
+    std::vector<int> perm;
+    for (int64_t base = 0; base < n; base += c->max_tasks) {
+        const int m = int(std::min<int64_t>(c->max_tasks, n - base));
+        // order the chunk by (env, action): consecutive tasks then share a frame,
+        // so its U / I / T stream from L2 instead of HBM
+        perm.resize(m);
+        std::iota(perm.begin(), perm.end(), 0);
+        std::sort(perm.begin(), perm.end(), [&](int x, int y) {
+            const int ex = env_ids ? env_ids[base + x] : 0, ey = env_ids ? env_ids[base + y] : 0;
+            if (ex != ey) return ex < ey;
+            if (actions[base + x] != actions[base + y]) return actions[base + x] < actions[base + y];
+            return x < y;
+        });
+        for (int i = 0; i < m; ++i) {
+            c->h_actions[i] = actions[base + perm[i]];
+            if (env_ids) c->h_envs[i] = env_ids[base + perm[i]];
+        }
+        BH_CUDA(c, cudaMemcpyAsync(c->d_actions, c->h_actions, size_t(m) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+        if (env_ids)
+            BH_CUDA(c, cudaMemcpyAsync(c->d_envs, c->h_envs, size_t(m) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        DeltaArgs a = make_args(c, m, env, env_ids ? c->d_envs : nullptr, c->d_actions, RULE_NEVER, c->d_results);
+        launch_eval(c, a);
+        BH_CUDA(c, cudaGetLastError());
+        BH_CUDA(c, cudaMemcpyAsync(c->h_results, c->d_results, size_t(m) * sizeof(Result), cudaMemcpyDeviceToHost, c->stream));
+        BH_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < m; ++i) psnr_after[base + perm[i]] = c->h_results[i].psnr_after;
+    }
+    return 0;
+}
+
+extern "C" int bh_step_batch_device(bh_ctx* c, int n, const int32_t* d_env_ids, const int64_t* d_actions,
+                                    int rule, bh_result* d_results) {
+    BH_CHECK_CTX(c);
+    if (n < 0 || n > c->max_tasks) BH_FAIL(c, -3, "n=%d exceeds max_tasks=%d", n, c->max_tasks);
+    if (rule < 0 || rule > 2) BH_FAIL(c, -1, "bad rule %d", rule);
+    if (n == 0) return 0;
+    if (!d_env_ids && n > 1) BH_FAIL(c, -1, "a batch step needs one distinct env per task");
+    DeltaArgs a = make_args(c, n, 0, d_env_ids, reinterpret_cast<const long long*>(d_actions), rule,
+                            reinterpret_cast<Result*>(d_results));
+    launch_eval(c, a);
+    if (rule != RULE_NEVER) launch_commit(c, a);
+    BH_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bh_step_batch(bh_ctx* c, int n, const int32_t* env_ids, const int64_t* actions, int rule,
+                             bh_result* results) {
+    BH_CHECK_CTX(c);
+    if (n < 0 || n > c->max_tasks || !actions || !results) BH_FAIL(c, -1, "bad arguments");
+    if (rule < 0 || rule > 2) BH_FAIL(c, -1, "bad rule %d", rule);
+    if (n == 0) return 0;
+    if (int rc = check_actions(c, actions, n)) return rc;
+    if (n > c->E) BH_FAIL(c, -3, "n=%d tasks but only %d environments", n, c->E);
+    // distinct environments: a launch commits at most one flip per env
+    std::vector<char> seen(c->E, 0);
+    for (int i = 0; i < n; ++i) {
+        const int e = env_ids ? env_ids[i] : i;
+        BH_CHECK_ENV(c, e);
+        if (seen[e]) BH_FAIL(c, -3, "environment %d appears twice in one batch step", e);
+        seen[e] = 1;
+        c->h_envs[i] = e;
+        c->h_actions[i] = actions[i];
+    }
+    BH_CUDA(c, cudaMemcpyAsync(c->d_actions, c->h_actions, size_t(n) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    BH_CUDA(c, cudaMemcpyAsync(c->d_envs, c->h_envs, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    DeltaArgs a = make_args(c, n, 0, c->d_envs, c->d_actions, rule, c->d_results);
+    launch_eval(c, a);
+    if (rule != RULE_NEVER) launch_commit(c, a);
+    BH_CUDA(c, cudaGetLastError());
+    BH_CUDA(c, cudaMemcpyAsync(c->h_results, c->d_results, size_t(n) * sizeof(Result), cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(results, c->h_results, size_t(n) * sizeof(Result));
+    return 0;
+}
+
+extern "C" int bh_commit_flip(bh_ctx* c, int env, int64_t action) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    if (int rc = check_actions(c, &action, 1)) return rc;
+    c->h_actions[0] = action;
+    BH_CUDA(c, cudaMemcpyAsync(c->d_actions, c->h_actions, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    DeltaArgs a = make_args(c, 1, env, nullptr, c->d_actions, RULE_NEVER, c->d_results);
+    launch_eval(c, a);
+    // force the decision, then apply
+    Result r;
+    BH_CUDA(c, cudaMemcpyAsync(c->h_results, c->d_results, sizeof(Result), cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA(c, cudaStreamSynchronize(c->stream));
+    r = c->h_results[0];
+    r.accept = 1;
+    c->h_results[0] = r;
+    BH_CUDA(c, cudaMemcpyAsync(c->d_results, c->h_results, sizeof(Result), cudaMemcpyHostToDevice, c->stream));
+    launch_commit(c, a);
+    BH_CUDA(c, cudaGetLastError());
+    BH_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, int k_spec,
+                          int64_t resync_every, uint8_t* accepted, double* psnr_trace,
+                          int64_t* n_accepted, double* final_psnr) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    if (n < 0 || (n > 0 && (!order || !accepted))) BH_FAIL(c, -1, "bad arguments");
+    if (int rc = check_actions(c, order, n)) return rc;
+    long long* d_order = nullptr; uint8_t* d_acc = nullptr; double* d_trace = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() { cudaFree(d_order); cudaFree(d_acc); cudaFree(d_trace); };
+#define BH_DBS(expr)                                                                       \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            cleanup();                                                                     \
+            BH_FAIL(c, -2, "%s failed: %s", #expr, cudaGetErrorString(_e));                \
+        }                                                                                  \
+    } while (0)
+    if (n > 0) {
+        BH_DBS(cudaMalloc(&d_order, size_t(n) * sizeof(long long)));
+        BH_DBS(cudaMalloc(&d_acc, size_t(n)));
+        if (psnr_trace) BH_DBS(cudaMalloc(&d_trace, size_t(n) * sizeof(double)));
+        BH_DBS(cudaMemcpyAsync(d_order, order, size_t(n) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+        BH_DBS(cudaMemsetAsync(d_acc, 0, size_t(n), c->stream));
+        BH_DBS(cudaMemsetAsync(c->d_scalars, 0, 4 * sizeof(long long), c->stream));
+        const int kmax = std::min(64, c->max_tasks);
+        int K = k_spec > 0 ? std::min(k_spec, c->max_tasks) : 2;
+        const int iters_per_sync = 32;
+        long long cursor = 0, nacc = 0, last_resync = 0;
+        while (cursor < n) {
+            DeltaArgs a = make_args(c, K, env, nullptr, d_order, RULE_DBS, c->d_results);
+            a.offset_ptr = c->d_scalars;
+            a.n_total = n;
+            for (int it = 0; it < iters_per_sync; ++it) {
+                launch_eval(c, a);
+                k_dbs_select<<<1, 32, 0, c->stream>>>(c->d_results, K, c->d_scalars, n, d_acc, d_trace, c->d_scalars + 1);
+                launch_commit(c, a);
+                c->launches += 1;
+            }
+            BH_DBS(cudaGetLastError());
+            BH_DBS(cudaMemcpyAsync(c->h_scalars, c->d_scalars, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+            BH_DBS(cudaStreamSynchronize(c->stream));
+            const long long consumed = c->h_scalars[0] - cursor;
+            cursor = c->h_scalars[0];
+            nacc = c->h_scalars[1];
+            if (k_spec <= 0) {      // adapt the speculation depth to the accept rate
+                const double per_iter = double(consumed) / iters_per_sync;
+                if (per_iter > 0.75 * K && K < kmax) K = std::min(kmax, K * 2);
+                else if (per_iter < 0.30 * K && K > 1) K = std::max(1, K / 2);
+            }
+            if (resync_every > 0 && nacc - last_resync >= resync_every && cursor < n) {
+                rc = propagate_env(c, env);
+                if (rc) { cleanup(); return rc; }
+                last_resync = nacc;
+            }
+        }
+        BH_DBS(cudaMemcpyAsync(accepted, d_acc, size_t(n), cudaMemcpyDeviceToHost, c->stream));
+        if (psnr_trace)
+            BH_DBS(cudaMemcpyAsync(psnr_trace, d_trace, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        BH_DBS(cudaStreamSynchronize(c->stream));
+        if (n_accepted) *n_accepted = nacc;
+    } else if (n_accepted) {
+        *n_accepted = 0;
+    }
+#undef BH_DBS
+    cleanup();
+    if (final_psnr) return bh_get_metrics(c, env, final_psnr, nullptr, nullptr);
+    return 0;
+}
+
+extern "C" int bh_get_recon(bh_ctx* c, int env, float* out, int on_host, int64_t cand) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    if (!out) BH_FAIL(c, -1, "out is null");
+    const size_t n2 = c->n2, bytes = size_t(c->G) * n2 * sizeof(float);
+    const float* I = c->dI + size_t(env) * c->G * n2;
+    float* dst = on_host ? c->drecon : out;
+    BH_CUDA(c, cudaMemcpyAsync(dst, I, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (cand >= 0) {
+        if (int rc = check_actions(c, &cand, 1)) return rc;
+        const int f = int(cand / (long long)n2);
+        const int pix = int(cand - (long long)f * (long long)n2);
+        const int r = pix / c->N, col = pix % c->N, g = f / c->Fg;
+        int8_t sb = 0;
+        BH_CUDA(c, cudaMemcpyAsync(&sb, c->dstate + (size_t(env) * c->F + f) * n2 + pix, 1, cudaMemcpyDeviceToHost, c->stream));
+        BH_CUDA(c, cudaStreamSynchronize(c->stream));
+        const float sgn = 1.f - 2.f * float(sb);
+        k_recon_candidate<<<std::min<size_t>((n2 + 255) / 256, 148 * 8), 256, 0, c->stream>>>(
+            c->dU + (size_t(env) * c->F + f) * n2, c->dh + size_t(g) * c->P * c->P, dst + size_t(g) * n2,
+            c->N, c->P, r, col, sgn, c->Fg);
+        BH_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+    }
+    if (on_host) {
+        BH_CUDA(c, cudaMemcpyAsync(out, c->drecon, bytes, cudaMemcpyDeviceToHost, c->stream));
+        BH_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+extern "C" int bh_get_state(bh_ctx* c, int env, int8_t* out, int on_host) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    if (!out) BH_FAIL(c, -1, "out is null");
+    const size_t bytes = size_t(c->F) * c->n2;
+    BH_CUDA(c, cudaMemcpyAsync(out, c->dstate + size_t(env) * bytes, bytes,
+                               on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
+    if (on_host) BH_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int bh_get_field(bh_ctx* c, int env, int frame, float* out, int on_host) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    if (!out || frame < 0 || frame >= c->F) BH_FAIL(c, -1, "bad arguments");
+    const size_t bytes = c->n2 * sizeof(float2);
+    BH_CUDA(c, cudaMemcpyAsync(out, c->dU + (size_t(env) * c->F + frame) * c->n2, bytes,
+                               on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
+    if (on_host) BH_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// stand-alone tt.simulate operator
+// ---------------------------------------------------------------------------
+__global__ void k_real_to_complex(const float* __restrict__ in, float2* __restrict__ out, size_t n) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+        out[i] = make_float2(in[i], 0.f);
+}
+
+extern "C" int bh_simulate(int device, void* stream_, const float* in, int is_complex, int C, int N,
+                           double wl, double dx, double z, int pad, int method, float* out, int on_host) {
+    bh_ctx* nul = nullptr;
+    if (!in || !out || C < 1 || N < 8) BH_FAIL(nul, -1, "bad arguments");
+    if (pad != 1 && pad != 2) BH_FAIL(nul, -1, "pad must be 1 or 2");
+    const int P = N * pad;
+    if (!fft_side_supported(P, pad)) BH_FAIL(nul, -4, "unsupported FFT side P=%d (pad=%d)", P, pad);
+    BH_CUDA(nul, cudaSetDevice(device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+    const size_t n2 = size_t(N) * N, p2 = size_t(P) * P, cnt = size_t(C) * n2;
+    float2 *dH = nullptr, *dtw = nullptr, *din = nullptr, *dbuf = nullptr, *dout = nullptr;
+    float* draw = nullptr;
+    auto cleanup = [&]() { cudaFree(dH); cudaFree(dtw); cudaFree(din); cudaFree(dbuf); cudaFree(dout); cudaFree(draw); };
+#define BH_SIM(expr)                                                          \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) {                                              \
+            cleanup();                                                        \
+            BH_FAIL(nul, -2, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+        }                                                                     \
+    } while (0)
+    auto t = get_tables(P, wl, dx, z, method);
+    auto tw = build_twiddles(P);
+    BH_SIM(cudaMalloc(&dH, p2 * sizeof(float2)));
+    BH_SIM(cudaMalloc(&dtw, size_t(P) * sizeof(float2)));
+    BH_SIM(cudaMalloc(&din, cnt * sizeof(float2)));
+    BH_SIM(cudaMemcpyAsync(dH, t->H.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice, st));
+    BH_SIM(cudaMemcpyAsync(dtw, tw.data(), size_t(P) * sizeof(float2), cudaMemcpyHostToDevice, st));
+    const cudaMemcpyKind kin = on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (is_complex) {
+        BH_SIM(cudaMemcpyAsync(din, in, cnt * sizeof(float2), kin, st));
+    } else {
+        BH_SIM(cudaMalloc(&draw, cnt * sizeof(float)));
+        BH_SIM(cudaMemcpyAsync(draw, in, cnt * sizeof(float), kin, st));
+        k_real_to_complex<<<std::min<size_t>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(draw, din, cnt);
+    }
+    float2* U = reinterpret_cast<float2*>(out);
+    if (on_host) { BH_SIM(cudaMalloc(&dout, cnt * sizeof(float2))); U = dout; }
+    float2* buf = U;
+    if (pad == 2) { BH_SIM(cudaMalloc(&dbuf, size_t(C) * p2 * sizeof(float2))); buf = dbuf; }
+    bool ok = false;
+    BH_SIM((dispatch_prop<float2, true>(P, pad, din, buf, U, nullptr, dH, dtw, C, 1, C, false, st, &ok)));
+    if (on_host) BH_SIM(cudaMemcpyAsync(out, dout, cnt * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    BH_SIM(cudaStreamSynchronize(st));
+#undef BH_SIM
+    cleanup();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// timing hooks (CUDA events on the context stream)
+// ---------------------------------------------------------------------------
+extern "C" int bh_time_eval(bh_ctx* c, int n, const int32_t* d_env_ids, const int64_t* d_actions,
+                            int reps, float* ms_per_launch) {
+    BH_CHECK_CTX(c);
+    if (n < 1 || n > c->max_tasks || reps < 1 || !ms_per_launch) BH_FAIL(c, -1, "bad arguments");
+    DeltaArgs a = make_args(c, n, 0, d_env_ids, reinterpret_cast<const long long*>(d_actions), RULE_NEVER, c->d_results);
+    launch_eval(c, a);          // warm
+    BH_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i) launch_eval(c, a);
+    BH_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    BH_CUDA(c, cudaEventSynchronize(c->ev1));
+    BH_CUDA(c, cudaGetLastError());
+    float ms = 0.f;
+    BH_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *ms_per_launch = ms / float(reps);
+    return 0;
+}
+
+extern "C" int bh_time_propagate(bh_ctx* c, int env, int reps, float* ms_per_launch) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    if (reps < 1 || !ms_per_launch) BH_FAIL(c, -1, "bad arguments");
+    if (int rc = propagate_env(c, env)) return rc;
+    BH_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i)
+        if (int rc = propagate_env(c, env)) return rc;
+    BH_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    BH_CUDA(c, cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    BH_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *ms_per_launch = ms / float(reps);
+    return 0;
+}

@@ -1,0 +1,305 @@
+"""Direct binary search drivers on the CUDA engine.
+
+``optimize_with_random_pixel_flips`` keeps the reference's two call shapes:
+
+* ``(env, z=2e-3[, pixel_pitch])`` -- greedy DBS (DBS.py:202-307,
+  DBS_1024_24.py:206-469): visit every pixel once in a random order, keep a flip
+  iff the PSNR strictly improves.
+* ``(target_function, trainloader, z, pixel_pitch, crop_margin)`` -- the
+  score-and-revert sweep (dbs-1024-1024-24-6464.py:194-478, range.py:195-421):
+  every candidate is scored against the fixed base state and binned by the
+  decile of the pre-model output.
+
+The reference re-simulates a colour group per candidate on the host loop; here
+the loop runs on the device (speculative batches through ``bh_dbs_run``) or as
+batched ``bh_eval_flips`` launches.  Both return their results (the reference
+only prints); the printed blocks keep the reference's format.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Callable, Iterable, List, Optional
+
+import numpy as np
+
+from .engine import HoloEngine
+from .envs import BinaryHologramEnv, WL_MONO, WL_RGB, _to_numpy
+
+OUTPUT_BINS = np.round(np.linspace(0, 1.0, 11), decimals=10)   # dbs-...-6464.py:197
+
+
+def decile_index(pre_values: np.ndarray) -> np.ndarray:
+    """Half-open deciles, last one closed (dbs-...-6464.py:377-391); -1 = outside [0,1]."""
+    v = np.asarray(pre_values, dtype=np.float64)
+    idx = np.searchsorted(OUTPUT_BINS, v, side="right") - 1
+    idx[v == OUTPUT_BINS[-1]] = len(OUTPUT_BINS) - 2
+    idx[(v < OUTPUT_BINS[0]) | (v > OUTPUT_BINS[-1])] = -1
+    return idx
+
+
+def _file_stem(name) -> str:
+    if isinstance(name, (list, tuple)):
+        name = name[0]
+    return os.path.splitext(os.path.basename(str(name)))[0]
+
+
+def _permutation(n: int, rng) -> np.ndarray:
+    """np.arange + np.random.shuffle (DBS.py:243-244); a Generator can be injected."""
+    order = np.arange(n, dtype=np.int64)
+    (rng if rng is not None else np.random).shuffle(order)
+    return order
+
+
+def _print_bins(bin_counts, improved, gains, attempted=None):
+    total_improved = int(np.sum(improved))
+    for i in range(len(OUTPUT_BINS) - 1):
+        tc, ic = int(bin_counts[i]), int(improved[i])
+        ratio_in = ic / tc if tc > 0 else 0
+        ratio_tot = ic / total_improved if total_improved > 0 else 0
+        tot = float(gains[i]) if ic > 0 else 0
+        avg = tot / ic if ic > 0 else 0
+        mid = ""
+        if attempted is not None:
+            ac = int(attempted[i])
+            mid = f"Attempted Pixels = {ac}, Improvement Ratio = {(ic / ac if ac > 0 else 0):.6f}, "
+        print(f"Range {OUTPUT_BINS[i]:.1f}-{OUTPUT_BINS[i + 1]:.1f}: "
+              f"Total Pixels = {tc}, Improved Pixels = {ic}, {mid}"
+              f"Improvement Ratio (in range) = {ratio_in:.6f}, "
+              f"Improvement Ratio (to total improved) = {ratio_tot:.6f}, "
+              f"Total PSNR Improvement = {tot:.6f}, "
+              f"Average PSNR Improvement = {avg:.8f}")
+
+
+def bin_population(pre_model: np.ndarray) -> np.ndarray:
+    """Pixels per decile of the pre-model output (DBS_1024_24.py:290-301)."""
+    idx = decile_index(pre_model.ravel())
+    return np.bincount(idx[idx >= 0], minlength=len(OUTPUT_BINS) - 1)
+
+
+# ---------------------------------------------------------------------------
+# greedy DBS
+# ---------------------------------------------------------------------------
+def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_datasets=None,
+                   order: Optional[np.ndarray] = None, rng=None, k_spec: int = 0,
+                   resync_every: int = 1024, segment: int = 1 << 20, verbose: bool = True,
+                   max_candidates: Optional[int] = None, save_dir: Optional[str] = None) -> List[dict]:
+    """DBS.py:202-307 / DBS_1024_24.py:206-469 on the device-resident engine."""
+    results = []
+    db_num = 0
+    if max_datasets is None:
+        max_datasets = 800 if env.G == 1 else 10          # DBS.py:205, DBS_1024_24.py:208
+    while db_num <= max_datasets:                         # DBS.py:208 (runs max+1 images)
+        try:
+            obs, info = env.reset(z=z, pixel_pitch=pixel_pitch)
+            db_num += 1
+        except Exception as e:                            # DBS.py:212-214
+            print(f"An error occurred during reset: {e}")
+            break
+        t0 = time.time()
+        eng, e = env.engine, env._e
+        initial_psnr = env.initial_psnr
+        file_name = _file_stem(env.current_file)
+        pre = env._crop(env.observation[0])
+        bin_counts = bin_population(pre)
+        if save_dir:                                      # DBS_1024_24.py:282-287
+            os.makedirs(save_dir, exist_ok=True)
+            np.save(os.path.join(save_dir, f"episode_{file_name}png_rgb_before.npy"),
+                    eng.recon(e)[None])
+        if verbose:
+            print(f"Starting pixel flip optimization for file {file_name}.png with initial PSNR: {initial_psnr:.6f}")
+        n = eng.num_pixels
+        perm = _permutation(n, rng) if order is None else np.asarray(order, dtype=np.int64)
+        if max_candidates is not None:
+            perm = perm[:max_candidates]
+        accepted = np.zeros(perm.shape[0], dtype=np.uint8)
+        trace = np.zeros(perm.shape[0], dtype=np.float64)
+        step_gain = 0.5 if env.G == 1 else 0.1            # DBS.py:226, DBS_1024_24.py:304
+        thresholds = [initial_psnr + i * step_gain for i in range(1, 21 if env.G == 1 else 101)]
+        previous = initial_psnr
+        flip_count = 0
+        for lo in range(0, perm.shape[0], segment):
+            hi = min(perm.shape[0], lo + segment)
+            acc, tr, nacc, psnr_now = eng.dbs_run(perm[lo:hi], env=e, k_spec=k_spec,
+                                                  resync_every=resync_every, trace=True)
+            accepted[lo:hi], trace[lo:hi] = acc, tr
+            flip_count += nacc
+            if verbose and nacc:
+                hit = np.flatnonzero(acc) + lo
+                for j in hit:
+                    while thresholds and trace[j] >= thresholds[0]:
+                        thresholds.pop(0)
+                        pa = trace[j]
+                        prev_acc = hit[hit < j]
+                        pb = trace[prev_acc[-1]] if prev_acc.size else previous
+                        print(f"Step: {j + 1}"
+                              f"\nPSNR Before: {pb:.6f} | PSNR After: {pa:.6f} | Change: {pa - pb:.6f} | Diff: {pa - initial_psnr:.6f}"
+                              f"\nSuccess Ratio: {np.count_nonzero(accepted[:j + 1]) / (j + 1):.6f} | Flip Count: {np.count_nonzero(accepted[:j + 1])}"
+                              f"\nTime taken for this data: {time.time() - t0:.2f} seconds")
+                previous = trace[hit[-1]]
+        # host mirrors follow the device state
+        new_state = eng.state(e)
+        env._crop(env.state[0])[...] = new_state
+        final_psnr, _, _ = eng.metrics(e)
+        env.previous_psnr = final_psnr
+        # decile statistics of the accepted flips (DBS_1024_24.py:390-416)
+        acc_idx = np.flatnonzero(accepted)
+        improved = np.zeros(len(OUTPUT_BINS) - 1, dtype=np.int64)
+        gains = np.zeros(len(OUTPUT_BINS) - 1)
+        if acc_idx.size:
+            prev_psnr = np.concatenate([[initial_psnr], trace[acc_idx[:-1]]])
+            d = decile_index(pre.ravel()[perm[acc_idx]])
+            ok = d >= 0
+            improved = np.bincount(d[ok], minlength=improved.size)
+            gains = np.bincount(d[ok], weights=(trace[acc_idx] - prev_psnr)[ok], minlength=gains.size)
+        steps = int(perm.shape[0])
+        dt = time.time() - t0
+        out = dict(file=file_name, initial_psnr=initial_psnr, final_psnr=final_psnr, steps=steps,
+                   flip_count=int(flip_count), accepted=accepted, psnr_trace=trace, order=perm,
+                   seconds=dt, bin_counts=bin_counts + improved, improved_bin_counts=improved,
+                   psnr_improvements=gains, state=new_state)
+        results.append(out)
+        if save_dir:                                      # DBS_1024_24.py:446-451 (+ the hologram itself)
+            np.save(os.path.join(save_dir, f"episode_{file_name}_rgb_after.npy"), eng.recon(e)[None])
+            np.save(os.path.join(save_dir, f"episode_{file_name}_state_after.npy"), new_state)
+        if verbose:
+            last = trace[-1] if steps else initial_psnr
+            print(f"Step: {steps}"
+                  f"\nPSNR Before: {final_psnr:.6f} | PSNR After: {last:.6f} | Change: {last - initial_psnr:.6f}"
+                  f"\nSuccess Ratio: {(flip_count / steps if steps else 0):.6f} | Flip Count: {flip_count}"
+                  f"\nTime taken for this data: {dt:.2f} seconds")
+            print(f"{file_name}.png Optimization completed. Final PSNR improvement: {last - initial_psnr:.6f}")
+            print(f"Time taken for this data: {dt:.2f} seconds\n")
+            if env.G > 1:
+                print("Pre-model output range statistics:")
+                _print_bins(out["bin_counts"], improved, gains)
+                print("\n")
+    return results
+
+
+# ---------------------------------------------------------------------------
+# score-and-revert sweep
+# ---------------------------------------------------------------------------
+def sweep_engine(eng: HoloEngine, env_index: int, pre_model: np.ndarray, order: np.ndarray,
+                 initial_psnr: float):
+    """Score ``order`` against the fixed state of one env; decile statistics.
+
+    Returns dict(psnr_after, attempted, improved, gains, flip_count).
+    """
+    order = np.asarray(order, dtype=np.int64)
+    psnr_after = eng.eval_flips(order, env=env_index)
+    better = psnr_after > initial_psnr                    # dbs-...-6464.py:381,393
+    d = decile_index(pre_model.ravel()[order])
+    ok = d >= 0
+    nb = len(OUTPUT_BINS) - 1
+    attempted = np.bincount(d[ok], minlength=nb)
+    improved = np.bincount(d[ok & better], minlength=nb)
+    gains = np.bincount(d[ok & better], weights=(psnr_after - initial_psnr)[ok & better], minlength=nb)
+    return dict(psnr_after=psnr_after, attempted=attempted, improved=improved, gains=gains,
+                flip_count=int(np.count_nonzero(better)))
+
+
+def dbs_sweep(target_function: Callable, trainloader: Iterable, z=2e-3, pixel_pitch=7.56e-6,
+              crop_margin=64, *, CH=24, wl=WL_RGB, max_datasets=1, order: Optional[np.ndarray] = None,
+              rng=None, device=0, pad=1, relative=True, verbose=True,
+              max_candidates: Optional[int] = None, chunk: int = 1 << 18,
+              shard: Optional[tuple] = None) -> List[dict]:
+    """dbs-1024-1024-24-6464.py:194-478: crop, then score every flip and always revert.
+
+    ``shard=(rank, world)`` scores only this rank's contiguous slice of the
+    (globally defined) candidate order -- the multi-GPU partition of SURVEY 8e.
+    """
+    results = []
+    data_iter = iter(trainloader)
+    db_num = 0
+    eng = None
+    if verbose:
+        print(OUTPUT_BINS)
+    while db_num <= max_datasets:                         # ...6464.py:202
+        try:
+            target_image, current_file = next(data_iter)
+            db_num += 1
+        except Exception as e:
+            print(f"An error occurred during reset: {e}")
+            break
+        t0 = time.time()
+        tgt_in = target_image
+        if hasattr(tgt_in, "cuda"):
+            try:
+                tgt_in = tgt_in.cuda(device)
+            except Exception:
+                pass
+        target_np = np.ascontiguousarray(_to_numpy(tgt_in), dtype=np.float32)
+        observation = np.ascontiguousarray(_to_numpy(target_function(tgt_in)), dtype=np.float32)
+        state = (observation >= 0.5).astype(np.int8)     # ...6464.py:217
+        m = int(crop_margin)
+        crop = (lambda a: a[..., m:-m, m:-m]) if m > 0 else (lambda a: a)
+        cstate, ctarget, cpre = crop(state[0]), crop(target_np[0]), crop(observation[0])
+        N = cstate.shape[-1]
+        if eng is None or eng.N != N or eng.z != float(z) or eng.dx != float(pixel_pitch):
+            if eng is not None:
+                eng.close()
+            eng = HoloEngine(N, cstate.shape[0], wl, n_env=1, device=device, dx=pixel_pitch, z=z,
+                             pad=pad, relative=relative)
+        eng.set_target(0, ctarget)
+        eng.load_state(0, cstate)
+        initial_psnr, _, _ = eng.metrics(0)
+        file_name = _file_stem(current_file)
+        bin_counts = bin_population(cpre)
+        if verbose:
+            print(f"Starting pixel flip optimization for file {file_name}.png with initial PSNR: {initial_psnr:.6f}")
+        n = eng.num_pixels
+        perm = _permutation(n, rng) if order is None else np.asarray(order, dtype=np.int64)
+        if max_candidates is not None:
+            perm = perm[:max_candidates]
+        lo_all, hi_all = 0, perm.shape[0]
+        if shard is not None:
+            rank, world = shard
+            per = (perm.shape[0] + world - 1) // world
+            lo_all, hi_all = min(perm.shape[0], rank * per), min(perm.shape[0], (rank + 1) * per)
+        nb = len(OUTPUT_BINS) - 1
+        attempted = np.zeros(nb, dtype=np.int64)
+        improved = np.zeros(nb, dtype=np.int64)
+        gains = np.zeros(nb)
+        psnr_all = np.empty(hi_all - lo_all, dtype=np.float64)
+        flip_count = 0
+        for lo in range(lo_all, hi_all, chunk):
+            hi = min(hi_all, lo + chunk)
+            r = sweep_engine(eng, 0, cpre, perm[lo:hi], initial_psnr)
+            psnr_all[lo - lo_all:hi - lo_all] = r["psnr_after"]
+            attempted += r["attempted"]; improved += r["improved"]; gains += r["gains"]
+            flip_count += r["flip_count"]
+            if verbose:                                   # ...6464.py:396-431 (every 5000 steps there)
+                steps = hi - lo_all
+                print(f"Step: {steps}"
+                      f"\nPSNR Before: {initial_psnr:.6f} | PSNR After: {psnr_all[hi - lo_all - 1]:.6f} | Change: {psnr_all[hi - lo_all - 1] - initial_psnr:.6f}"
+                      f"\nSuccess Ratio: {flip_count / steps:.6f} | Flip Count: {flip_count}"
+                      f"\nTime taken for this data: {time.time() - t0:.2f} seconds")
+                _print_bins(bin_counts, improved, gains, attempted)
+        dt = time.time() - t0
+        results.append(dict(file=file_name, initial_psnr=initial_psnr, psnr_after=psnr_all,
+                            order=perm[lo_all:hi_all], attempted=attempted, improved=improved,
+                            gains=gains, bin_counts=bin_counts, flip_count=flip_count,
+                            steps=int(hi_all - lo_all), seconds=dt))
+        if verbose:
+            print(f"{file_name}.png Optimization completed.")
+            print(f"Time taken for this data: {dt:.2f} seconds\n")
+            print("Pre-model output range statistics:")
+            _print_bins(bin_counts, improved, gains)
+            print("\n")
+    if eng is not None:
+        eng.close()
+    return results
+
+
+def optimize_with_random_pixel_flips(first, *args, **kw):
+    """Reference entry point (DBS.py:202; dbs-1024-1024-24-6464.py:194).
+
+    ``first`` is an env -> greedy DBS; ``first`` is a callable ``target_function``
+    (followed by the trainloader) -> score-and-revert sweep.
+    """
+    if isinstance(first, BinaryHologramEnv):
+        return dbs_greedy_env(first, *args, **kw)
+    if callable(first):
+        return dbs_sweep(first, *args, **kw)
+    raise TypeError("expected a BinaryHologramEnv or a target_function")

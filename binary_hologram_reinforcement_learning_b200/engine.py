@@ -1,0 +1,274 @@
+"""ctypes binding of the C ABI in ``include/bholo.h`` (libbholo_b200.so).
+
+There is no CPU fallback: if the CUDA library is missing, cannot be loaded, or
+no sm_100 device is present, constructing a :class:`HoloEngine` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _build
+
+RULE_ENV, RULE_DBS, RULE_NEVER = 0, 1, 2
+METHOD_ASM, METHOD_FRESNEL = 0, 1
+
+# every symbol include/bholo.h declares
+ABI_SYMBOLS = (
+    "bh_abi_version", "bh_last_error", "bh_create", "bh_destroy", "bh_set_stream",
+    "bh_set_target", "bh_load_state", "bh_resync", "bh_get_metrics", "bh_eval_flips",
+    "bh_step_batch", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
+    "bh_commit_flip", "bh_dbs_run", "bh_get_recon", "bh_get_state", "bh_get_field",
+    "bh_device_ptr", "bh_simulate", "bh_time_eval", "bh_time_propagate", "bh_launch_count",
+)
+
+
+class BhResult(C.Structure):
+    """Mirror of ``bh_result`` (40 bytes)."""
+    _fields_ = [("psnr_after", C.c_double), ("d_sii", C.c_double), ("d_sit", C.c_double),
+                ("action", C.c_int64), ("accept", C.c_int32), ("sgn", C.c_int32)]
+
+
+RESULT_DTYPE = np.dtype([("psnr_after", "<f8"), ("d_sii", "<f8"), ("d_sit", "<f8"),
+                         ("action", "<i8"), ("accept", "<i4"), ("sgn", "<i4")])
+assert RESULT_DTYPE.itemsize == C.sizeof(BhResult) == 40
+
+
+class HoloError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def library_path() -> str:
+    return os.environ.get("BHOLO_LIB", _build.LIB_PATH)
+
+
+def load_library(build_if_missing: bool = True):
+    """dlopen libbholo_b200.so and declare the signatures.  Raises if unavailable."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise HoloError(f"{path} is missing; run python -m binary_hologram_reinforcement_learning_b200._build")
+        _build.build()
+    lib = C.CDLL(path)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    P = C.POINTER
+    sig = {
+        "bh_abi_version": (i32, []),
+        "bh_last_error": (C.c_char_p, [vp]),
+        "bh_create": (i32, [P(vp), i32, i32, i32, i32, i32, P(dbl), dbl, dbl, i32, i32, i32]),
+        "bh_destroy": (i32, [vp]),
+        "bh_set_stream": (i32, [vp, vp]),
+        "bh_set_target": (i32, [vp, i32, vp, i32]),
+        "bh_load_state": (i32, [vp, i32, vp, i32]),
+        "bh_resync": (i32, [vp, i32]),
+        "bh_get_metrics": (i32, [vp, i32, P(dbl), P(dbl), P(dbl)]),
+        "bh_eval_flips": (i32, [vp, i32, i64, vp, vp, vp]),
+        "bh_step_batch": (i32, [vp, i32, vp, vp, i32, vp]),
+        "bh_step_batch_device": (i32, [vp, i32, vp, vp, i32, vp]),
+        "bh_eval_flips_device": (i32, [vp, i32, i32, vp, vp, vp]),
+        "bh_max_tasks": (i32, [vp]),
+        "bh_commit_flip": (i32, [vp, i32, i64]),
+        "bh_dbs_run": (i32, [vp, i32, vp, i64, i32, i64, vp, vp, P(i64), P(dbl)]),
+        "bh_get_recon": (i32, [vp, i32, vp, i32, i64]),
+        "bh_get_state": (i32, [vp, i32, vp, i32]),
+        "bh_get_field": (i32, [vp, i32, i32, vp, i32]),
+        "bh_device_ptr": (vp, [vp, i32]),
+        "bh_simulate": (i32, [i32, vp, vp, i32, i32, i32, dbl, dbl, dbl, i32, i32, vp, i32]),
+        "bh_time_eval": (i32, [vp, i32, vp, vp, i32, P(C.c_float)]),
+        "bh_time_propagate": (i32, [vp, i32, i32, P(C.c_float)]),
+        "bh_launch_count": (i64, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class HoloEngine:
+    """Device-resident state of ``n_env`` hologram environments.
+
+    Owns U (fields), I (reconstruction), T (target), the binary state and the
+    running loss sums on one GPU; all arithmetic of the reward / DBS path runs in
+    the CUDA kernels behind the C ABI.
+    """
+
+    def __init__(self, N: int, F: int, wl: Sequence[float], n_env: int = 1, device: int = 0,
+                 dx: float = 7.56e-6, z: float = 2e-3, pad: int = 1, relative: bool = True,
+                 method: str = "asm", stream: Optional[int] = None):
+        self._h = C.c_void_p()
+        self.lib = load_library()
+        self.N, self.F, self.G = int(N), int(F), len(wl)
+        self.n_env, self.device = int(n_env), int(device)
+        self.wl, self.dx, self.z = tuple(float(w) for w in wl), float(dx), float(z)
+        self.pad, self.relative, self.method = int(pad), bool(relative), method
+        self.Fg = self.F // self.G
+        self.num_pixels = self.F * self.N * self.N
+        wl_arr = (C.c_double * self.G)(*self.wl)
+        rc = self.lib.bh_create(C.byref(self._h), self.device, self.n_env, self.N, self.F, self.G,
+                                wl_arr, self.dx, self.z, self.pad, int(self.relative),
+                                METHOD_ASM if method == "asm" else METHOD_FRESNEL)
+        if rc != 0:
+            msg = self.lib.bh_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise HoloError(f"bh_create failed ({rc}): {msg}")
+        if stream is not None:
+            self.set_stream(stream)
+
+    # -- plumbing ---------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise HoloError(f"{what} failed ({rc}): {self.lib.bh_last_error(self._h).decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.bh_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.bh_set_stream(self._h, C.c_void_p(int(cuda_stream))), "bh_set_stream")
+
+    @property
+    def max_tasks(self) -> int:
+        return self.lib.bh_max_tasks(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.bh_launch_count(self._h))
+
+    def device_ptr(self, which: str) -> int:
+        idx = {"U": 0, "I": 1, "T": 2, "state": 3, "sums": 4, "h": 5, "H": 6}[which]
+        return int(self.lib.bh_device_ptr(self._h, idx) or 0)
+
+    # -- reset path -------------------------------------------------------
+    def set_target(self, env: int, target: np.ndarray):
+        t = np.ascontiguousarray(target, dtype=np.float32).reshape(self.G, self.N, self.N)
+        self._check(self.lib.bh_set_target(self._h, env, _ptr(t), 1), "bh_set_target")
+
+    def load_state(self, env: int, state: np.ndarray):
+        s = np.ascontiguousarray(state, dtype=np.int8).reshape(self.F, self.N, self.N)
+        self._check(self.lib.bh_load_state(self._h, env, _ptr(s), 1), "bh_load_state")
+
+    def resync(self, env: int):
+        self._check(self.lib.bh_resync(self._h, env), "bh_resync")
+
+    def metrics(self, env: int):
+        """(psnr, mse, (sum I^2, sum I*T, sum T^2))."""
+        p, m = C.c_double(), C.c_double()
+        s3 = (C.c_double * 3)()
+        self._check(self.lib.bh_get_metrics(self._h, env, C.byref(p), C.byref(m), s3), "bh_get_metrics")
+        return p.value, m.value, (s3[0], s3[1], s3[2])
+
+    # -- incremental path -------------------------------------------------
+    def eval_flips(self, actions: np.ndarray, env: int = 0,
+                   env_ids: Optional[np.ndarray] = None) -> np.ndarray:
+        a = np.ascontiguousarray(actions, dtype=np.int64).ravel()
+        e = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32).ravel()
+        out = np.empty(a.shape[0], dtype=np.float64)
+        self._check(self.lib.bh_eval_flips(self._h, env, a.shape[0], _ptr(e), _ptr(a), _ptr(out)),
+                    "bh_eval_flips")
+        return out
+
+    def step_batch(self, actions: np.ndarray, env_ids: Optional[np.ndarray] = None,
+                   rule: int = RULE_ENV, out: Optional[np.ndarray] = None) -> np.ndarray:
+        a = np.ascontiguousarray(actions, dtype=np.int64).ravel()
+        e = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32).ravel()
+        if out is None:
+            out = np.empty(a.shape[0], dtype=RESULT_DTYPE)
+        self._check(self.lib.bh_step_batch(self._h, a.shape[0], _ptr(e), _ptr(a), rule, _ptr(out)),
+                    "bh_step_batch")
+        return out
+
+    def step_batch_device(self, n: int, d_env_ids: int, d_actions: int, rule: int, d_results: int):
+        self._check(self.lib.bh_step_batch_device(self._h, n, C.c_void_p(d_env_ids),
+                                                  C.c_void_p(d_actions), rule, C.c_void_p(d_results)),
+                    "bh_step_batch_device")
+
+    def eval_flips_device(self, n: int, d_env_ids: int, d_actions: int, d_results: int, env: int = 0):
+        self._check(self.lib.bh_eval_flips_device(self._h, env, n, C.c_void_p(d_env_ids or None),
+                                                  C.c_void_p(d_actions), C.c_void_p(d_results)),
+                    "bh_eval_flips_device")
+
+    def commit_flip(self, env: int, action: int):
+        self._check(self.lib.bh_commit_flip(self._h, env, int(action)), "bh_commit_flip")
+
+    def dbs_run(self, order: np.ndarray, env: int = 0, k_spec: int = 0, resync_every: int = 0,
+                trace: bool = False):
+        """Greedy DBS over ``order``.  Returns (accepted uint8[n], psnr_trace|None, n_acc, psnr)."""
+        o = np.ascontiguousarray(order, dtype=np.int64).ravel()
+        n = o.shape[0]
+        acc = np.zeros(n, dtype=np.uint8)
+        tr = np.zeros(n, dtype=np.float64) if trace else None
+        nacc, fin = C.c_int64(0), C.c_double(0.0)
+        self._check(self.lib.bh_dbs_run(self._h, env, _ptr(o), n, k_spec, resync_every, _ptr(acc),
+                                        _ptr(tr), C.byref(nacc), C.byref(fin)), "bh_dbs_run")
+        return acc, tr, int(nacc.value), fin.value
+
+    # -- read-back --------------------------------------------------------
+    def recon(self, env: int = 0, candidate_action: int = -1,
+              out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.G, self.N, self.N), dtype=np.float32)
+        self._check(self.lib.bh_get_recon(self._h, env, _ptr(out), 1, int(candidate_action)),
+                    "bh_get_recon")
+        return out
+
+    def state(self, env: int = 0) -> np.ndarray:
+        out = np.empty((self.F, self.N, self.N), dtype=np.int8)
+        self._check(self.lib.bh_get_state(self._h, env, _ptr(out), 1), "bh_get_state")
+        return out
+
+    def field(self, env: int, frame: int) -> np.ndarray:
+        out = np.empty((self.N, self.N), dtype=np.complex64)
+        self._check(self.lib.bh_get_field(self._h, env, frame, _ptr(out), 1), "bh_get_field")
+        return out
+
+    # -- timing hooks -----------------------------------------------------
+    def time_eval(self, n: int, d_env_ids: int, d_actions: int, reps: int) -> float:
+        ms = C.c_float(0.0)
+        self._check(self.lib.bh_time_eval(self._h, n, C.c_void_p(d_env_ids or None),
+                                          C.c_void_p(d_actions), reps, C.byref(ms)), "bh_time_eval")
+        return float(ms.value)
+
+    def time_propagate(self, env: int, reps: int) -> float:
+        ms = C.c_float(0.0)
+        self._check(self.lib.bh_time_propagate(self._h, env, reps, C.byref(ms)), "bh_time_propagate")
+        return float(ms.value)
+
+
+def simulate(field: np.ndarray, wl: float, z: float = 2e-3, dx: float = 7.56e-6, pad: int = 1,
+             method: str = "asm", device: int = 0) -> np.ndarray:
+    """``tt.simulate`` on host arrays: (..., N, N) real or complex -> complex64."""
+    lib = load_library()
+    x = np.asarray(field)
+    N = x.shape[-1]
+    lead = x.shape[:-2]
+    cplx = np.iscomplexobj(x)
+    xin = np.ascontiguousarray(x, dtype=np.complex64 if cplx else np.float32).reshape(-1, N, N)
+    out = np.empty(xin.shape, dtype=np.complex64)
+    rc = lib.bh_simulate(device, None, _ptr(xin), int(cplx), xin.shape[0], N, float(wl), float(dx),
+                         float(z), int(pad), METHOD_ASM if method == "asm" else METHOD_FRESNEL,
+                         _ptr(out), 1)
+    if rc != 0:
+        raise HoloError(f"bh_simulate failed ({rc}): {lib.bh_last_error(None).decode()}")
+    return out.reshape(lead + (N, N))

@@ -1,0 +1,145 @@
+/* bholo.h -- C ABI of the B200 hologram reward / direct-binary-search engine.
+ *
+ * The reference (songyb111-gachon/binary-hologram-reinforcement-learning) has no
+ * FFI of its own: its de-facto operator interface for this path is five calls
+ * into the absent third-party package torchOptics plus the host loops around
+ * them.  Every entry point below cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - return 0 on success, < 0 on error; bh_last_error() gives the message.
+ *     Nothing throws or aborts.
+ *   - pointers are HOST pointers unless the parameter is named d_* or an
+ *     on_host flag says otherwise.  Outputs are caller-allocated.
+ *   - a context owns all device memory of its E environments; it is not
+ *     thread-safe, distinct contexts are independent.
+ *   - work is enqueued on the stream given to bh_set_stream (default: the
+ *     legacy default stream); functions with host outputs synchronise that
+ *     stream only.
+ *   - an action is the flat index  frame * N*N + row * N + col  of the
+ *     reference (env.py:158-161).
+ */
+#ifndef BHOLO_H
+#define BHOLO_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bh_ctx bh_ctx;
+
+/* accept rules */
+#define BH_RULE_ENV   0   /* keep iff psnr_after - previous >= 0   (env.py:191)   */
+#define BH_RULE_DBS   1   /* keep iff psnr_after > previous        (DBS.py:273)   */
+#define BH_RULE_NEVER 2   /* score and revert    (dbs-1024-1024-24-6464.py:371)   */
+
+/* propagation method */
+#define BH_METHOD_ASM     0
+#define BH_METHOD_FRESNEL 1
+
+typedef struct bh_result {      /* one evaluated flip; 40 bytes */
+    double  psnr_after;         /* PSNR with the flip applied                     */
+    double  d_sii;              /* change of sum(I^2)                             */
+    double  d_sit;              /* change of sum(I*T)                             */
+    int64_t action;             /* the evaluated action, -1 when the slot is idle */
+    int32_t accept;             /* decision under the rule                        */
+    int32_t sgn;                /* +1: pixel 0 -> 1, -1: 1 -> 0                   */
+} bh_result;
+
+int bh_abi_version(void);
+
+/* Last error of ctx (or of the calling thread when ctx is NULL). */
+const char* bh_last_error(const bh_ctx* ctx);
+
+/* Create a context for n_env environments of F frames of N x N pixels in G
+ * colour groups of F/G frames, wavelength wl[g] per group.
+ * Replaces the constants baked into the reference envs (env.py:27-28,124;
+ * env_1024_24.py:29-30,135-147).  pad: 1 = circular (FFT side P = N),
+ * 2 = linear (P = 2N); relative: 1 = scale-invariant loss of tt.relativeLoss. */
+int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int G,
+              const double* wl, double dx, double z, int pad, int relative, int method);
+int bh_destroy(bh_ctx* ctx);
+int bh_set_stream(bh_ctx* ctx, void* cuda_stream);
+
+/* Target image of one env, float [G][N][N]  (env.py:106-107 target.cuda()). */
+int bh_set_target(bh_ctx* ctx, int env, const float* target, int on_host);
+
+/* Upload a binary stack int8 [F][N][N] and run the full propagation:
+ * tt.Tensor + tt.simulate + abs()**2 + mean(dim=1) + relativeLoss
+ * (env.py:123-132; env_1024_24.py:140-166).  Fills U, I and the loss sums. */
+int bh_load_state(bh_ctx* ctx, int env, const int8_t* state, int on_host);
+
+/* Re-propagate from the device-resident state (bounds fp32 drift of the
+ * incremental updates); same arithmetic as bh_load_state. */
+int bh_resync(bh_ctx* ctx, int env);
+
+/* Current PSNR / MSE (env.py:131-132) and, optionally, the three sums
+ * (sum I^2, sum I*T, sum T^2). */
+int bh_get_metrics(bh_ctx* ctx, int env, double* psnr, double* mse, double* sums3);
+
+/* Score n single-pixel flips against the CURRENT state without changing it
+ * (env_group.py:96-119; dbs-1024-1024-24-6464.py:337-371; range.py:294-335).
+ * env_ids may be NULL: every candidate then targets `env`. */
+int bh_eval_flips(bh_ctx* ctx, int env, int64_t n, const int32_t* env_ids,
+                  const int64_t* actions, double* psnr_after);
+
+/* One environment step for n distinct environments: score the flip, keep or
+ * revert it under `rule` (env.py:154-196 / DBS_1024_24.py:313-422 body).
+ * results: n records. */
+int bh_step_batch(bh_ctx* ctx, int n, const int32_t* env_ids, const int64_t* actions,
+                  int rule, bh_result* results);
+
+/* Same with DEVICE pointers and no synchronisation (inputs resident in HBM). */
+int bh_step_batch_device(bh_ctx* ctx, int n, const int32_t* d_env_ids,
+                         const int64_t* d_actions, int rule, bh_result* d_results);
+
+/* Score only, DEVICE pointers, no synchronisation; n <= bh_max_tasks(). */
+int bh_eval_flips_device(bh_ctx* ctx, int env, int n, const int32_t* d_env_ids,
+                         const int64_t* d_actions, bh_result* d_results);
+int bh_max_tasks(const bh_ctx* ctx);
+
+/* Unconditionally apply one flip (DBS "keep" branch, DBS.py:273-291). */
+int bh_commit_flip(bh_ctx* ctx, int env, int64_t action);
+
+/* Greedy direct binary search over `order` (DBS.py:247-294,
+ * DBS_1024_24.py:313-422): visit candidates in order, keep a flip iff the PSNR
+ * strictly improves.  Runs on the device in speculative batches of up to
+ * k_spec candidates (<= 0: adaptive); the decision sequence is that of the
+ * sequential loop.  accepted: n bytes; psnr_trace (nullable): n doubles, PSNR
+ * of every evaluated candidate; resync_every (<= 0: never): re-propagate after
+ * that many accepted flips. */
+int bh_dbs_run(bh_ctx* ctx, int env, const int64_t* order, int64_t n, int k_spec,
+               int64_t resync_every, uint8_t* accepted, double* psnr_trace,
+               int64_t* n_accepted, double* final_psnr);
+
+/* Reconstruction float [G][N][N].  candidate_action >= 0 adds the intensity
+ * change of that (uncommitted) flip -- obs["recon_image"] of a rejected step
+ * (env.py:176-181). */
+int bh_get_recon(bh_ctx* ctx, int env, float* out, int on_host, int64_t candidate_action);
+int bh_get_state(bh_ctx* ctx, int env, int8_t* out, int on_host);
+/* Field of one frame, complex64 [N][N] as interleaved floats (test hook). */
+int bh_get_field(bh_ctx* ctx, int env, int frame, float* out, int on_host);
+
+/* Device pointers of the resident arrays (for zero-copy views): which =
+ * 0 U, 1 I, 2 T, 3 state, 4 sums, 5 h, 6 H. */
+void* bh_device_ptr(bh_ctx* ctx, int which);
+
+/* Stand-alone operator: tt.simulate(field, z) for C frames of N x N
+ * (env.py:127).  in: float [C][N][N] (is_complex = 0) or interleaved complex;
+ * out: interleaved complex64 [C][N][N].  Pointers are device pointers when
+ * on_host = 0. */
+int bh_simulate(int device, void* cuda_stream, const float* in, int is_complex, int C, int N,
+                double wl, double dx, double z, int pad, int method, float* out, int on_host);
+
+/* Timing hooks for bench.py: launch the delta-eval (or commit, or propagation)
+ * kernel `reps` times on the context stream between two CUDA events and return
+ * the average milliseconds per launch.  n tasks from d_actions / d_env_ids. */
+int bh_time_eval(bh_ctx* ctx, int n, const int32_t* d_env_ids, const int64_t* d_actions,
+                 int reps, float* ms_per_launch);
+int bh_time_propagate(bh_ctx* ctx, int env, int reps, float* ms_per_launch);
+/* Kernels launched by this context since creation (for "gpu_launches"). */
+int64_t bh_launch_count(const bh_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BHOLO_H */

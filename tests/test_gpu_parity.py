@@ -1,0 +1,330 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): PSNR within 1e-3 dB, per-step reward within
+1e-5 relative (of the reward scale of the step, with an absolute floor for the
+fp32 fields), accept/reject sequences identical except documented near-ties.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import binary_hologram_reinforcement_learning_b200 as bh
+from binary_hologram_reinforcement_learning_b200.engine import RULE_DBS, RULE_ENV, RULE_NEVER
+from oracle import hologram_oracle as O
+from tests.golden import make_golden as MG
+
+PSNR_TOL = 1e-3          # dB, north_star
+NEAR_TIE = 2e-6          # |dPSNR| (dB) below which fp32 fields may flip a decision
+
+
+def _problem(N, F, wl, seed):
+    pre, tgt = bh.synthetic_problem(N, F, len(wl), seed)
+    return pre, tgt, (pre >= 0.5).astype(np.int8)
+
+
+def _engine(N, F, wl, pad=1, relative=True, n_env=1):
+    return bh.HoloEngine(N, F, wl, n_env=n_env, pad=pad, relative=relative)
+
+
+# ---------------------------------------------------------------------------
+# propagation: tt.simulate + abs**2 + mean + relativeLoss
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("N,F,wl,pad", [
+    (32, 4, O.WL_MONO, 1), (64, 8, O.WL_MONO, 1), (128, 6, O.WL_RGB, 1), (256, 8, O.WL_MONO, 1),
+    (512, 3, O.WL_RGB, 1), (896, 3, O.WL_RGB, 1), (1024, 3, O.WL_RGB, 1),
+    (32, 4, O.WL_MONO, 2), (64, 6, O.WL_RGB, 2), (128, 2, O.WL_MONO, 2), (256, 2, O.WL_MONO, 2),
+    (896, 1, O.WL_MONO, 2), (1024, 1, O.WL_MONO, 2),
+])
+def test_propagation_matches_oracle(N, F, wl, pad):
+    pre, tgt, st = _problem(N, F, wl, seed=N + F)
+    cfg = O.HoloConfig(N=N, F=F, wl=wl, pad=pad)
+    eng = _engine(N, F, wl, pad)
+    eng.set_target(0, tgt)
+    eng.load_state(0, st)
+    recon_ref = O.reconstruct(cfg, st)
+    psnr_ref, mse_ref = O.score(cfg, recon_ref, tgt)
+    psnr, mse, sums = eng.metrics(0)
+    assert abs(psnr - psnr_ref) < 1e-4, (psnr, psnr_ref)
+    np.testing.assert_allclose(sums, O.loss_sums(recon_ref, tgt), rtol=2e-6)
+    np.testing.assert_allclose(eng.recon(0), recon_ref, rtol=0, atol=2e-5 * recon_ref.max())
+    for f in sorted({0, F - 1}):
+        g = cfg.group_of(f)
+        U_ref = O.propagate_group(cfg, st[g * cfg.Fg:(g + 1) * cfg.Fg], g)[f - g * cfg.Fg]
+        U = eng.field(0, f)
+        assert np.abs(U - U_ref).max() < 1e-5 * np.abs(U_ref).max()
+    assert np.array_equal(eng.state(0), st)
+    eng.close()
+
+
+def test_simulate_operator_matches_oracle():
+    rng = np.random.default_rng(0)
+    for N, pad in [(64, 1), (256, 1), (64, 2)]:
+        x = rng.random((3, N, N)).astype(np.float32)
+        H = O.transfer_function(N * pad, O.PIXEL_PITCH, 515e-9, O.Z_DEFAULT)
+        ref = O.simulate(x.astype(np.float64), H, pad)
+        got = bh.simulate(x, 515e-9, pad=pad)
+        assert np.abs(got - ref).max() < 1e-5 * np.abs(ref).max()
+        xc = (x + 1j * rng.random((3, N, N))).astype(np.complex64)
+        refc = O.simulate(xc.astype(np.complex128), H, pad)
+        assert np.abs(bh.simulate(xc, 515e-9, pad=pad) - refc).max() < 1e-5 * np.abs(refc).max()
+
+
+def test_unsupported_shapes_fail_loudly():
+    with pytest.raises(bh.HoloError):
+        bh.HoloEngine(96, 8, bh.WL_MONO)          # FFT side 96 not in the plan table
+    with pytest.raises(bh.HoloError):
+        bh.HoloEngine(64, 7, bh.WL_RGB)           # F not a multiple of G
+    eng = _engine(32, 4, O.WL_MONO)
+    with pytest.raises(bh.HoloError):
+        eng.eval_flips(np.array([4 * 32 * 32]))   # action out of range
+    with pytest.raises(bh.HoloError):
+        eng.step_batch(np.array([0, 1]), np.array([0, 0]))   # same env twice
+    eng.close()
+
+
+# ---------------------------------------------------------------------------
+# candidate scoring (env_group.py:96-119, dbs-...-6464.py:337-371)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("N,F,wl,pad,relative", [
+    (64, 8, O.WL_MONO, 1, True), (64, 6, O.WL_RGB, 1, True), (32, 4, O.WL_MONO, 2, True),
+    (64, 8, O.WL_MONO, 1, False), (128, 6, O.WL_RGB, 1, True),
+])
+def test_eval_flips_matches_full_resimulation(N, F, wl, pad, relative):
+    pre, tgt, st = _problem(N, F, wl, seed=7)
+    cfg = O.HoloConfig(N=N, F=F, wl=wl, pad=pad, relative=relative)
+    eng = _engine(N, F, wl, pad, relative)
+    eng.set_target(0, tgt)
+    eng.load_state(0, st)
+    rng = np.random.default_rng(3)
+    actions = np.concatenate([rng.integers(0, F * N * N, size=60),
+                              [0, N - 1, N * N - 1, F * N * N - 1, (F - 1) * N * N + N * (N - 1)]])
+    got = eng.eval_flips(actions)
+    ref, p0, *_ = O.sweep(cfg, st, tgt, pre, actions)
+    psnr0 = eng.metrics(0)[0]
+    assert np.abs(got - ref).max() < 1e-4
+    d_got, d_ref = got - psnr0, ref - p0
+    np.testing.assert_allclose(d_got, d_ref, rtol=1e-4, atol=1e-7)
+    assert np.array_equal(eng.state(0), st)                      # score-and-revert: state untouched
+    assert abs(eng.metrics(0)[0] - psnr0) == 0
+    eng.close()
+
+
+# ---------------------------------------------------------------------------
+# golden fixtures (tests/golden/*.npz, made by the float64 oracle)
+# ---------------------------------------------------------------------------
+def _decisions_equal_up_to_near_ties(acc, acc_ref, delta_ref):
+    bad = np.flatnonzero(np.asarray(acc, bool) != np.asarray(acc_ref, bool))
+    return all(abs(delta_ref[i]) < NEAR_TIE for i in bad), bad
+
+
+@pytest.mark.parametrize("name", list(MG.CASES))
+def test_golden_env_trajectory(name, golden_dir):
+    """env.py:154-260 semantics through BinaryHologramEnv.step on the CUDA engine."""
+    N, F, wl, pad, relative, seed = MG.CASES[name]
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    ld = bh.SyntheticLoader(N, F, len(wl), seeds=(seed,))
+    env = bh.BinaryHologramEnv(ld.target_function, ld, max_steps=MG.N_STEPS - 10, T_PSNR_DIFF=1e9,
+                               IPS=N, CH=F, wl=wl, pad=pad, relative=relative, verbose=False)
+    obs, info = env.reset()
+    assert abs(env.initial_psnr - float(g["initial_psnr"])) < 1e-4
+    assert obs["recon_image"].shape == (1, len(wl), N, N) and obs["state"].dtype == np.int8
+    prev = float(g["initial_psnr"])
+    for i, a in enumerate(g["env_actions"]):
+        flips_before = env.flip_count
+        obs, r, term, trunc, _ = env.step(int(a))
+        acc_ref = bool(g["env_accepted"][i])
+        d_ref = float(g["env_psnr"][i]) - prev
+        assert isinstance(r, float) and isinstance(term, bool) and isinstance(trunc, bool)
+        got_acc = env.flip_count == flips_before + 1      # kept flips count (env.py:167,194)
+        if got_acc != acc_ref:
+            assert abs(d_ref) < NEAR_TIE, (i, d_ref)
+            pytest.skip("near-tie divergence: trajectories legitimately differ from here")
+        r_ref = float(g["env_rewards"][i])
+        assert abs(r - r_ref) <= 1e-5 * abs(r_ref) + 800 * 2e-7, (i, r, r_ref)
+        assert term == bool(g["env_terminated"][i])
+        if acc_ref:
+            prev = float(g["env_psnr"][i])
+    assert int(env.state.sum()) == int(g["env_final_state_sum"])
+    assert np.array_equal(env.engine.state(0), env.state[0])
+    env.close()
+
+
+@pytest.mark.parametrize("name", list(MG.CASES))
+@pytest.mark.parametrize("k_spec", [1, 0, 16])
+def test_golden_dbs_greedy(name, k_spec, golden_dir):
+    """DBS.py:247-294: the device loop reproduces the sequential accept sequence for any batch depth."""
+    N, F, wl, pad, relative, seed = MG.CASES[name]
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    pre, tgt, st = _problem(N, F, wl, seed)
+    eng = _engine(N, F, wl, pad, relative)
+    eng.set_target(0, tgt)
+    eng.load_state(0, st)
+    acc, trace, nacc, final = eng.dbs_run(g["dbs_order"], k_spec=k_spec, trace=True)
+    ref_acc, ref_trace = g["dbs_accepted"], g["dbs_trace"]
+    prev = np.concatenate([[float(g["initial_psnr"])], ref_trace[:-1]])
+    running = np.maximum.accumulate(np.concatenate([[float(g["initial_psnr"])], np.where(ref_acc, ref_trace, -np.inf)]))[:-1]
+    ok, bad = _decisions_equal_up_to_near_ties(acc, ref_acc, ref_trace - running)
+    assert ok, bad
+    if bad.size == 0:
+        np.testing.assert_allclose(trace, ref_trace, rtol=0, atol=1e-4)
+        assert nacc == int(ref_acc.sum())
+        assert int(eng.state(0).sum()) == int(g["dbs_final_state_sum"])
+        assert abs(final - ref_trace[ref_acc][-1]) < 1e-4
+    eng.close()
+
+
+@pytest.mark.parametrize("name", list(MG.CASES))
+def test_golden_sweep(name, golden_dir):
+    N, F, wl, pad, relative, seed = MG.CASES[name]
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    pre, tgt, st = _problem(N, F, wl, seed)
+    eng = _engine(N, F, wl, pad, relative)
+    eng.set_target(0, tgt)
+    eng.load_state(0, st)
+    r = bh.sweep_engine(eng, 0, pre, g["sweep_order"], eng.metrics(0)[0])
+    np.testing.assert_allclose(r["psnr_after"], g["sweep_psnr"], rtol=0, atol=1e-4)
+    assert np.array_equal(r["attempted"], g["sweep_attempted"])
+    d_ref = g["sweep_psnr"] - float(g["initial_psnr"])
+    if np.all(np.abs(d_ref) > NEAR_TIE):
+        assert np.array_equal(r["improved"], g["sweep_improved"])
+        np.testing.assert_allclose(r["gains"], g["sweep_gain"], rtol=1e-4, atol=1e-7)
+    eng.close()
+
+
+# ---------------------------------------------------------------------------
+# vectorised envs, group reward, cropped env
+# ---------------------------------------------------------------------------
+def test_vec_env_matches_independent_oracle_envs():
+    N, F, wl, E = 64, 6, O.WL_RGB, 4
+    loaders = [bh.SyntheticLoader(N, F, 3, seeds=(100 + i,)) for i in range(E)]
+    tf = lambda t: next(l for l in loaders if t[0, 0, :4].tobytes() in l._pre).target_function(t)
+    vec = bh.HologramVecEnv(E, tf, loaders, max_steps=10 ** 6, T_PSNR_DIFF=1e9, IPS=N, CH=F, wl=wl)
+    vec.reset()
+    cfg = O.HoloConfig(N=N, F=F, wl=wl)
+    refs = []
+    for i in range(E):
+        pre, tgt = bh.synthetic_problem(N, F, 3, 100 + i)
+        e = O.OracleEnv(cfg, max_steps=10 ** 6, T_PSNR_DIFF=1e9)
+        e.reset(pre, tgt)
+        refs.append(e)
+        assert abs(vec.envs[i].initial_psnr - e.initial_psnr) < 1e-4
+    rng = np.random.default_rng(5)
+    for step in range(40):
+        acts = rng.integers(0, F * N * N, size=E)
+        obs, rewards, dones, infos = vec.step(acts)
+        for i in range(E):
+            r, term, trunc, p, acc = refs[i].step(int(acts[i]))
+            assert abs(rewards[i] - r) <= 1e-5 * abs(r) + 800 * 2e-7
+            assert not dones[i]
+    for i in range(E):
+        assert np.array_equal(vec.envs[i].state[0], refs[i].state)
+        assert np.array_equal(vec.engine.state(i), refs[i].state)
+        rec = vec.envs[i].refresh_recon()[0]
+        np.testing.assert_allclose(rec, refs[i].recon, atol=3e-5 * refs[i].recon.max())
+    vec.close()
+
+
+def test_group_env_importance_table():
+    N, F = 64, 8
+    ld = bh.SyntheticLoader(N, F, 1, seeds=(31,))
+    env = bh.BinaryHologramEnvGroup(ld.target_function, ld, IPS=N, CH=F, verbose=False,
+                                    num_samples=300, rng=np.random.default_rng(9))
+    env.reset()
+    cfg = O.HoloConfig(N=N, F=F)
+    pre, tgt = bh.synthetic_problem(N, F, 1, 31)
+    ch, ranks, pos = O.pixel_importance(cfg, (pre >= 0.5).astype(np.int8), tgt, env.initial_psnr,
+                                        None, 300, actions=env.importance_actions)
+    np.testing.assert_allclose(env.psnr_change_list, ch, rtol=1e-4, atol=1e-7)
+    assert abs(env.T_PSNR_DIFF - pos / 4) < 1e-5 * pos
+    if np.min(np.abs(np.diff(np.sort(ch)))) > 1e-7:
+        np.testing.assert_allclose(env.importance_ranks, ranks, atol=1e-9)
+    obs, r, term, trunc, _ = env.step(int(env.importance_actions[0]))
+    assert -0.6 < r < 1.1                                           # a table value (env_group.py:255)
+    env.close()
+
+
+def test_cropped_env_simulates_the_window_only():
+    """env_1024_24_128.py:139-181 at a small shape: crop 8 of 64 -> 48^2 simulated."""
+    N, F, m = 64, 6, 8
+    ld = bh.SyntheticLoader(N, F, 3, seeds=(41,))
+    env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, wl=O.WL_RGB, crop_margin=m,
+                               verbose=False, T_PSNR_DIFF=1e9)
+    with pytest.raises(bh.HoloError):
+        env.reset()                                                 # 48 is not a supported FFT side
+    env.close()
+    N, m = 80, 8                                                    # 80 - 16 = 64
+    ld = bh.SyntheticLoader(N, F, 3, seeds=(41,))
+    env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, wl=O.WL_RGB, crop_margin=m,
+                               verbose=False, T_PSNR_DIFF=1e9)
+    obs, _ = env.reset()
+    pre, tgt = bh.synthetic_problem(N, F, 3, 41)
+    cfg = O.HoloConfig(N=N - 2 * m, F=F, wl=O.WL_RGB)
+    st = (pre >= 0.5).astype(np.int8)[:, m:-m, m:-m]
+    p_ref, _ = O.score(cfg, O.reconstruct(cfg, st), tgt[:, m:-m, m:-m])
+    assert abs(env.initial_psnr - p_ref) < 1e-4
+    obs, r, *_ = env.step(0)                                        # outside the window: no change
+    assert r == 0.0 and obs["state"][0, 0, 0, 0] != (pre[0, 0, 0] >= 0.5)
+    env.close()
+
+
+# ---------------------------------------------------------------------------
+# size-independent properties at the full BASELINE shape (1024^2 x 24, 3 colours)
+# ---------------------------------------------------------------------------
+def test_full_size_properties():
+    N, F, wl = 1024, 24, O.WL_RGB
+    pre, tgt, st = _problem(N, F, wl, seed=0)
+    eng = _engine(N, F, wl, n_env=2)
+    for e in range(2):
+        eng.set_target(e, tgt)
+        eng.load_state(e, st)
+    p0, mse0, sums0 = eng.metrics(0)
+    assert eng.metrics(1)[0] == p0                                  # same inputs -> same bits
+    # one colour group against the oracle (full 24-frame oracle run is too slow for a unit test)
+    cfg = O.HoloConfig(N=N, F=8, wl=(wl[1],), dtype="float64")
+    rec_g = O.reconstruct(cfg, st[8:16])[0]
+    np.testing.assert_allclose(eng.recon(0)[1], rec_g, atol=2e-5 * rec_g.max())
+    rng = np.random.default_rng(1)
+    acts = rng.integers(0, F * N * N, size=64)
+    # (1) scoring does not depend on batch composition or order
+    a = eng.eval_flips(acts)
+    b = eng.eval_flips(acts[::-1])[::-1]
+    assert np.array_equal(a, b)
+    c = np.array([eng.eval_flips(acts[i:i + 1])[0] for i in range(8)])
+    assert np.array_equal(a[:8], c)
+    # (2) delta evaluation == full re-propagation of the flipped state
+    for i in range(3):
+        st2 = st.copy().reshape(-1); st2[acts[i]] = 1 - st2[acts[i]]
+        eng.load_state(1, st2.reshape(F, N, N))
+        assert abs(eng.metrics(1)[0] - a[i]) < 2e-6, (eng.metrics(1)[0], a[i])
+    eng.load_state(1, st)
+    # (3) commit + commit of the same pixel is the identity (up to fp32 rounding of U)
+    eng.commit_flip(0, int(acts[0]))
+    assert abs(eng.metrics(0)[0] - a[0]) < 1e-9
+    assert eng.state(0).reshape(-1)[acts[0]] != st.reshape(-1)[acts[0]]
+    eng.commit_flip(0, int(acts[0]))
+    assert abs(eng.metrics(0)[0] - p0) < 1e-7
+    assert np.array_equal(eng.state(0), st)
+    # (4) a batch step over both envs == two single steps; accepted flips stick, rejected revert
+    res = eng.step_batch(acts[:2], np.array([0, 1]), RULE_ENV)
+    for e in range(2):
+        flipped = eng.state(e).reshape(-1)[acts[e]] != st.reshape(-1)[acts[e]]
+        assert flipped == bool(res["accept"][e])
+        assert bool(res["accept"][e]) == (res["psnr_after"][e] - p0 >= 0)
+        if res["accept"][e]:
+            assert eng.metrics(e)[0] == res["psnr_after"][e]
+    # (5) resync after incremental updates agrees with the running sums
+    order = rng.permutation(F * N * N)[:400]
+    acc, tr, nacc, fin = eng.dbs_run(order, env=0, k_spec=0, trace=True)
+    assert nacc == int(acc.sum()) and nacc > 50
+    before = eng.metrics(0)
+    eng.resync(0)
+    after = eng.metrics(0)
+    assert abs(before[0] - after[0]) < 5e-6
+    np.testing.assert_allclose(before[2], after[2], rtol=1e-6)
+    # accepted candidates strictly increase the PSNR trace
+    inc = tr[acc.astype(bool)]
+    assert np.all(np.diff(inc) > 0)
+    eng.close()

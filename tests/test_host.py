@@ -1,0 +1,147 @@
+"""CPU: host logic, the C-ABI library surface and the native FFT check (no GPU needed)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+import binary_hologram_reinforcement_learning_b200 as bh
+from binary_hologram_reinforcement_learning_b200 import dbs, dist, engine, envs, spaces, _build
+from oracle import hologram_oracle as O
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    path = _build.build()
+    assert os.path.exists(path)
+    lib = engine.load_library()
+    header = open(os.path.join(ROOT, "include", "bholo.h")).read()
+    declared = set(re.findall(r"\b(bh_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(engine.ABI_SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None, name
+    assert lib.bh_abi_version() == 1
+    assert ctypes.sizeof(engine.BhResult) == 40
+
+
+def test_sass_is_sm100a():
+    out = subprocess.run(["cuobjdump", "-lelf", _build.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(bh.HoloError):
+        bh.HoloEngine(64, 8, bh.WL_MONO)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "binary_hologram_reinforcement_learning_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f
+
+
+def test_native_fft_passes_on_host(tmp_path):
+    """The exact __host__ __device__ pass functions the kernels run, executed on the CPU."""
+    exe = str(tmp_path / "host_check")
+    src = os.path.join(ROOT, "tests", "native", "host_check.cu")
+    subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, src], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0 and "HOST_CHECK_OK" in res.stdout, res.stdout
+
+
+def test_decile_index_matches_oracle():
+    v = np.concatenate([np.linspace(0, 1, 101), [0.1, 0.2, 0.30000000001, 1.0, 0.0]])
+    got = dbs.decile_index(v)
+    exp = np.array([O.decile_of(float(x)) for x in v])
+    assert np.array_equal(got, exp)
+
+
+def test_importance_table_matches_oracle():
+    rng = np.random.default_rng(0)
+    ch = list(rng.normal(size=500) * 1e-4)
+    np.testing.assert_allclose(envs.importance_reward_table(ch), O.importance_reward_table(ch),
+                               rtol=1e-12, atol=1e-12)
+
+
+def test_goal_bonus_constants():
+    assert abs(envs.goal_bonus(1.0, -595.2) - 300.04) < 1e-9      # env.py:227-235
+    assert abs(envs.goal_bonus(0.5, -595.24) - O.goal_bonus(0.5, -595.24)) < 1e-12
+
+
+def test_synthetic_inputs_match_oracle_copy():
+    a = bh.synthetic_problem(32, 6, 3, 7)
+    b = O.synthetic_problem(32, 6, 3, 7)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    ld = bh.SyntheticLoader(32, 6, 3, seeds=(7,))
+    tgt, name = next(iter(ld))
+    assert tgt.shape == (1, 3, 32, 32) and np.array_equal(ld.target_function(tgt)[0], a[0])
+
+
+def test_spaces_and_action_mapping():
+    ld = bh.SyntheticLoader(32, 6, 3, seeds=(1,))
+    env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=32, CH=6, wl=bh.WL_RGB, crop_margin=4,
+                               verbose=False)
+    assert env.action_space.n == 6 * 32 * 32
+    assert env.observation_space["state"].shape == (1, 6, 32, 32)
+    assert env.observation_space["recon_image"].shape == (1, 3, 24, 24)
+    a = np.array([0, 4 * 32 + 4, 32 * 32 + 5 * 32 + 27, 6 * 32 * 32 - 1])
+    sim, inside = env._map_actions(a)
+    assert list(inside) == [False, True, True, False]
+    assert sim[1] == 0 and sim[2] == 24 * 24 + 1 * 24 + 23
+
+
+def test_shard_helpers():
+    n = 19267584
+    cover = []
+    for r in range(8):
+        lo, hi = dist.shard_range(n, r, 8)
+        cover.append((lo, hi))
+    assert cover[0][0] == 0 and cover[-1][1] == n
+    assert all(cover[i][1] == cover[i + 1][0] for i in range(7))
+    assert np.array_equal(np.sort(np.concatenate([dist.shard_indices(13, r, 4) for r in range(4)])),
+                          np.arange(13))
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+from binary_hologram_reinforcement_learning_b200 import dist
+dist.init_process_group("gloo")
+rank, world, _ = dist.env_info()
+rows = np.arange((rank + 1) * 5, dtype=np.float64).reshape(rank + 1, 5) + 100 * rank
+allr = dist.gather_episode_stats(rows)
+assert allr.shape == (3, 5), allr.shape
+assert allr[0, 0] == 0 and allr[1, 0] == 100 and allr[2, 0] == 105
+h, = dist.reduce_histograms(np.array([1, 2, 3]) * (rank + 1))
+assert list(h) == [3, 6, 9]
+assert dist.max_over_ranks(float(rank)) == 1.0
+lo, hi = dist.shard_range(10, rank, world)
+assert (lo, hi) == ((0, 5) if rank == 0 else (5, 10))
+dist.barrier()
+print("GLOO_OK", rank)
+"""
+
+
+def test_two_rank_gloo_stats_gather(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT="29641")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"GLOO_OK {r}" in o, o
