@@ -653,13 +653,16 @@ extern "C" int bh_simulate(int device, void* stream_, const float* in, int is_co
 // timing hooks (CUDA events on the context stream)
 // ---------------------------------------------------------------------------
 extern "C" int bh_time_eval(bh_ctx* c, int n, const int32_t* d_env_ids, const int64_t* d_actions,
-                            int reps, float* ms_per_launch) {
+                            int n_sets, int reps, float* ms_per_launch) {
     BH_CHECK_CTX(c);
-    if (n < 1 || n > c->max_tasks || reps < 1 || !ms_per_launch) BH_FAIL(c, -1, "bad arguments");
+    if (n < 1 || n > c->max_tasks || reps < 1 || n_sets < 1 || !ms_per_launch) BH_FAIL(c, -1, "bad arguments");
     DeltaArgs a = make_args(c, n, 0, d_env_ids, reinterpret_cast<const long long*>(d_actions), RULE_NEVER, c->d_results);
-    launch_eval(c, a);          // warm
+    for (int i = 0; i < 3; ++i) launch_eval(c, a);          // warm
     BH_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    for (int i = 0; i < reps; ++i) launch_eval(c, a);
+    for (int i = 0; i < reps; ++i) {
+        a.actions = reinterpret_cast<const long long*>(d_actions) + size_t(i % n_sets) * n;
+        launch_eval(c, a);
+    }
     BH_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     BH_CUDA(c, cudaEventSynchronize(c->ev1));
     BH_CUDA(c, cudaGetLastError());

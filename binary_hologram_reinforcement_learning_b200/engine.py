@@ -83,7 +83,7 @@ def load_library(build_if_missing: bool = True):
         "bh_get_field": (i32, [vp, i32, i32, vp, i32]),
         "bh_device_ptr": (vp, [vp, i32]),
         "bh_simulate": (i32, [i32, vp, vp, i32, i32, i32, dbl, dbl, dbl, i32, i32, vp, i32]),
-        "bh_time_eval": (i32, [vp, i32, vp, vp, i32, P(C.c_float)]),
+        "bh_time_eval": (i32, [vp, i32, vp, vp, i32, i32, P(C.c_float)]),
         "bh_time_propagate": (i32, [vp, i32, i32, P(C.c_float)]),
         "bh_launch_count": (i64, [vp]),
     }
@@ -244,10 +244,11 @@ class HoloEngine:
         return out
 
     # -- timing hooks -----------------------------------------------------
-    def time_eval(self, n: int, d_env_ids: int, d_actions: int, reps: int) -> float:
+    def time_eval(self, n: int, d_env_ids: int, d_actions: int, n_sets: int, reps: int) -> float:
         ms = C.c_float(0.0)
         self._check(self.lib.bh_time_eval(self._h, n, C.c_void_p(d_env_ids or None),
-                                          C.c_void_p(d_actions), reps, C.byref(ms)), "bh_time_eval")
+                                          C.c_void_p(d_actions), n_sets, reps, C.byref(ms)),
+                    "bh_time_eval")
         return float(ms.value)
 
     def time_propagate(self, env: int, reps: int) -> float:

@@ -130,11 +130,13 @@ void* bh_device_ptr(bh_ctx* ctx, int which);
 int bh_simulate(int device, void* cuda_stream, const float* in, int is_complex, int C, int N,
                 double wl, double dx, double z, int pad, int method, float* out, int on_host);
 
-/* Timing hooks for bench.py: launch the delta-eval (or commit, or propagation)
- * kernel `reps` times on the context stream between two CUDA events and return
- * the average milliseconds per launch.  n tasks from d_actions / d_env_ids. */
+/* Timing hooks for bench.py: launch the delta-eval kernel (or the propagation
+ * passes) `reps` times on the context stream between two CUDA events and return
+ * the average milliseconds per launch.  Launch i scores the n tasks
+ * d_actions[(i % n_sets) * n ...] of environments d_env_ids[0..n), so that
+ * consecutive launches stream different frames (working set >> L2). */
 int bh_time_eval(bh_ctx* ctx, int n, const int32_t* d_env_ids, const int64_t* d_actions,
-                 int reps, float* ms_per_launch);
+                 int n_sets, int reps, float* ms_per_launch);
 int bh_time_propagate(bh_ctx* ctx, int env, int reps, float* ms_per_launch);
 /* Kernels launched by this context since creation (for "gpu_launches"). */
 int64_t bh_launch_count(const bh_ctx* ctx);

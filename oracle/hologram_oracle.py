@@ -105,6 +105,8 @@ def simulate(x: np.ndarray, H: np.ndarray, pad: int = 1, workers=None) -> np.nda
     assert P == pad * N and x.shape[-2] == N
     cdt = H.dtype
     rdt = np.float32 if cdt == np.complex64 else np.float64
+    if np.iscomplexobj(x):
+        rdt = cdt
     if pad == 1:
         X = _fft2(x.astype(rdt, copy=False), workers=workers)
         return _ifft2(X * H, workers=workers).astype(cdt, copy=False)

@@ -200,7 +200,7 @@ def test_golden_sweep(name, golden_dir):
 def test_vec_env_matches_independent_oracle_envs():
     N, F, wl, E = 64, 6, O.WL_RGB, 4
     loaders = [bh.SyntheticLoader(N, F, 3, seeds=(100 + i,)) for i in range(E)]
-    tf = lambda t: next(l for l in loaders if t[0, 0, :4].tobytes() in l._pre).target_function(t)
+    tf = lambda t: next(l for l in loaders if np.ascontiguousarray(t[0, 0, 0, :4]).tobytes() in l._pre).target_function(t)
     vec = bh.HologramVecEnv(E, tf, loaders, max_steps=10 ** 6, T_PSNR_DIFF=1e9, IPS=N, CH=F, wl=wl)
     vec.reset()
     cfg = O.HoloConfig(N=N, F=F, wl=wl)
@@ -235,8 +235,11 @@ def test_group_env_importance_table():
     env.reset()
     cfg = O.HoloConfig(N=N, F=F)
     pre, tgt = bh.synthetic_problem(N, F, 1, 31)
-    ch, ranks, pos = O.pixel_importance(cfg, (pre >= 0.5).astype(np.int8), tgt, env.initial_psnr,
-                                        None, 300, actions=env.importance_actions)
+    st = (pre >= 0.5).astype(np.int8)
+    p0_ref, _ = O.score(cfg, O.reconstruct(cfg, st), tgt)
+    assert abs(env.initial_psnr - p0_ref) < 1e-4
+    ch, ranks, pos = O.pixel_importance(cfg, st, tgt, p0_ref, None, 300,
+                                        actions=env.importance_actions)
     np.testing.assert_allclose(env.psnr_change_list, ch, rtol=1e-4, atol=1e-7)
     assert abs(env.T_PSNR_DIFF - pos / 4) < 1e-5 * pos
     if np.min(np.abs(np.diff(np.sort(ch)))) > 1e-7:

@@ -102,3 +102,22 @@ def test_env_reject_semantics():
 def test_decile_bins():
     assert O.decile_of(0.0) == 0 and O.decile_of(0.0999) == 0 and O.decile_of(0.1) == 1
     assert O.decile_of(1.0) == 9 and O.decile_of(0.95) == 9 and O.decile_of(1.5) == -1
+
+
+def test_torch_reference_path_matches_numpy_oracle():
+    """The timed CPU baseline (oracle/torch_path.py, fp32 torch) follows the float64 oracle."""
+    from oracle.torch_path import TorchRefEnv
+    for (N, F, wl, pad) in [(64, 6, O.WL_RGB, 1), (32, 4, O.WL_MONO, 2)]:
+        pre, tgt = O.synthetic_problem(N, F, len(wl), 17)
+        ref = O.OracleEnv(O.HoloConfig(N=N, F=F, wl=wl, pad=pad), max_steps=10 ** 9, T_PSNR_DIFF=1e9)
+        ref.reset(pre, tgt)
+        te = TorchRefEnv(N, F, wl, pad=pad)
+        assert abs(te.reset(pre, tgt) - ref.initial_psnr) < 1e-4
+        for a in np.random.default_rng(2).integers(0, F * N * N, size=25):
+            r, term, trunc, p, acc = ref.step(int(a))
+            r2, p2, acc2 = te.step(int(a))
+            assert abs(p - p2) < 1e-4
+            if abs(r) > 800 * 2e-5:
+                assert acc == acc2 and abs(r - r2) < 0.05 * abs(r) + 800 * 2e-5
+            if acc != acc2:
+                break
