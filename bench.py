@@ -309,6 +309,7 @@ def run_b200(args):
     clocks = sampler.stop(windows)
 
     # ---- the one collective: all-gather of per-env episode statistics ----
+    vec.sync_envs()
     stats = np.array([[vec._ep_reward[i], vec.envs[i].steps, vec.envs[i].flip_count, psnr0[i],
                        vec.envs[i].previous_psnr] for i in range(E)])
     all_stats = bdist.gather_episode_stats(stats)

@@ -229,6 +229,22 @@ k_loss_sums(const float* __restrict__ I, const float* __restrict__ T, size_t n,
 // ---------------------------------------------------------------------------
 // incremental path
 // ---------------------------------------------------------------------------
+// Work decomposition.  A "unit" is UNIT_PX = 1024 consecutive pixels of one
+// candidate's N x N image (one pass of a 256-thread CTA at 4 px per thread).
+// The n_tasks * units_per_task units of a launch are split into gridDim.x
+// contiguous, balanced ranges (CTA b owns [b*total/grid, (b+1)*total/grid)), so
+// every resident CTA streams the same number of bytes (+-1 unit) and a CTA
+// crosses at most a few task boundaries.
+//
+// Reduction.  Per-thread fp32 partials of one quad are converted to 2^-40
+// fixed point and summed as 64-bit integers (registers -> warp shuffles ->
+// shared -> one global atomic per CTA and task).  Integer addition is
+// associative, so sum(dI*(2I+dI)) and sum(dI*T) are bit-identical for every
+// grid size, batch composition, speculation depth and GPU count.
+constexpr int UNIT_PX = 1024;
+constexpr float FIX_SCALE = 1099511627776.0f;          // 2^40
+constexpr double FIX_INV = 1.0 / 1099511627776.0;
+
 struct DeltaArgs {
     float2* U; float* I; const float* T; int8_t* state; const float2* h;
     double* sums;                  // [E][4]
@@ -237,11 +253,20 @@ struct DeltaArgs {
     const long long* offset_ptr;   // speculative DBS: actions[*offset_ptr + k]; nullptr otherwise
     long long n_total;             // valid entries of actions
     int env_fixed;
-    int n_tasks, N, P, F, G, Fg, tiles, rows_per_tile, relative, rule;
-    double2* partials;             // [n_tasks][tiles]
+    int n_tasks, N, P, F, G, Fg, relative, rule;
+    int units_per_task;            // N*N / UNIT_PX
+    int unit_dy, unit_dx;          // UNIT_PX / N, UNIT_PX % N
+    unsigned long long* acc;       // [n_tasks][2] fixed-point accumulators (zero between launches)
     unsigned* tickets;             // [n_tasks]
     Result* results;               // [n_tasks]
+    Result* results_host;          // optional mapped pinned mirror written by the finaliser
+    // small batches (one env step of <= INLINE_MAX envs) carry their tasks in the
+    // kernel parameters: no host-to-device copy on the step path
+    int n_inline;
+    long long inl_actions[32];
+    int inl_envs[32];
 };
+constexpr int INLINE_MAX = 32;
 
 struct Decoded {
     int env, f, g, r, c; float sgn; bool active;
@@ -250,7 +275,7 @@ struct Decoded {
 // decode (env.py:158-161) and read the sign of the flip from the resident state
 __device__ __forceinline__ Decoded decode_action(const DeltaArgs& a, int k, long long act) {
     Decoded d;
-    d.env = a.envs ? a.envs[k] : a.env_fixed;
+    d.env = a.n_inline ? a.inl_envs[k] : (a.envs ? a.envs[k] : a.env_fixed);
     d.f = d.g = d.r = d.c = 0; d.sgn = 0.f;
     d.active = act >= 0;
     if (!d.active) return d;
@@ -272,99 +297,168 @@ __device__ __forceinline__ float delta_px(float ur, float ui, float hr, float hi
     return fmaf(s2, a, m * invFg);
 }
 
-// k_eval: one work item = (task k, tile of rows_per_tile image rows).  Persistent
-// CTAs stride over the items.  Streams U (8 B/px), I, T (4 B/px each) once and
-// the shifted impulse response (8 B/px, L2 resident): 16 N^2 algorithmic HBM
-// bytes per candidate.  The last CTA of a task folds its partials in tile order
-// (deterministic) and writes the PSNR and the accept decision.
-__global__ void __launch_bounds__(256)
+// L2 cache-policy loads: the streamed operands (U, I, T) are read once per
+// candidate and marked evict-first; the impulse response is re-read by every
+// candidate and marked evict-last so it stays L2 resident (25 MB for 3 colours).
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ float4 ld_stream4(const float4* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float2 ld_keep2(const float2* p, uint64_t pol) {
+    float2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
+                 : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+
+struct Quad {                      // operands of 4 consecutive pixels
+    float4 ua, ub, iv, tv;
+    float2 h0, h1, h2, h3;
+};
+
+// position of the thread's quad inside the image, advanced unit by unit
+struct Cursor {
+    int y, x;
+    __device__ __forceinline__ void init(int unit, int tid, int N) {
+        const int p = unit * UNIT_PX + tid * 4;
+        y = p / N; x = p - y * N;
+    }
+    __device__ __forceinline__ void next(const DeltaArgs& a) {
+        y += a.unit_dy; x += a.unit_dx;
+        if (x >= a.N) { x -= a.N; ++y; }
+    }
+};
+
+template <bool WITH_T>
+__device__ __forceinline__ void load_quad(Quad& q, const float2* U, const float* I, const float* T,
+                                          const float2* h, const Cursor& cu, int N, int P, int r, int c,
+                                          uint64_t pf, uint64_t pl) {
+    const size_t p = size_t(cu.y) * N + cu.x;
+    const float4* Up = reinterpret_cast<const float4*>(U + p);
+    q.ua = ld_stream4(Up, pf);
+    q.ub = ld_stream4(Up + 1, pf);
+    q.iv = ld_stream4(reinterpret_cast<const float4*>(I + p), pf);
+    if (WITH_T) q.tv = ld_stream4(reinterpret_cast<const float4*>(T + p), pf);
+    int hy = cu.y - r; if (hy < 0) hy += P;
+    int hx = cu.x - c; if (hx < 0) hx += P;
+    const float2* hrow = h + size_t(hy) * P;
+    int hx1 = hx + 1; if (hx1 >= P) hx1 -= P;
+    int hx2 = hx1 + 1; if (hx2 >= P) hx2 -= P;
+    int hx3 = hx2 + 1; if (hx3 >= P) hx3 -= P;
+    q.h0 = ld_keep2(hrow + hx, pl); q.h1 = ld_keep2(hrow + hx1, pl);
+    q.h2 = ld_keep2(hrow + hx2, pl); q.h3 = ld_keep2(hrow + hx3, pl);
+}
+
+__device__ __forceinline__ void eval_quad(const Quad& q, float s2, float invFg, long long& aII,
+                                          long long& aIT) {
+    const float d0 = delta_px(q.ua.x, q.ua.y, q.h0.x, q.h0.y, s2, invFg);
+    const float d1 = delta_px(q.ua.z, q.ua.w, q.h1.x, q.h1.y, s2, invFg);
+    const float d2 = delta_px(q.ub.x, q.ub.y, q.h2.x, q.h2.y, s2, invFg);
+    const float d3 = delta_px(q.ub.z, q.ub.w, q.h3.x, q.h3.y, s2, invFg);
+    float ii = d0 * fmaf(2.f, q.iv.x, d0);
+    ii = fmaf(d1, fmaf(2.f, q.iv.y, d1), ii);
+    ii = fmaf(d2, fmaf(2.f, q.iv.z, d2), ii);
+    ii = fmaf(d3, fmaf(2.f, q.iv.w, d3), ii);
+    float it = d0 * q.tv.x;
+    it = fmaf(d1, q.tv.y, it);
+    it = fmaf(d2, q.tv.z, it);
+    it = fmaf(d3, q.tv.w, it);
+    aII += __float2ll_rn(ii * FIX_SCALE);
+    aIT += __float2ll_rn(it * FIX_SCALE);
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// CTA that owns unit u under the balanced partition of `total` units over `grid` CTAs
+__device__ __forceinline__ int cta_of_unit(long long u, long long total, int grid) {
+    return int(((u + 1) * grid - 1) / total);
+}
+
+// k_eval: streams U (8 B/px), I and T (4 B/px each) once per candidate and the
+// shifted impulse response from L2: 16 N^2 algorithmic HBM bytes per candidate.
+// The last CTA to contribute to a task turns the exact sums into the PSNR and
+// the accept decision.
+__global__ void __launch_bounds__(256, 4)
 k_eval(const DeltaArgs a) {
-    __shared__ double sh[2][8];
+    __shared__ long long sh[2][8];
     __shared__ unsigned s_ticket;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int N = a.N, P = a.P, nq = N >> 2;
-    const int total = a.n_tasks * a.tiles;
+    const int N = a.N, P = a.P, upt = a.units_per_task;
+    const long long total = (long long)a.n_tasks * upt;
+    const long long beg = (long long)blockIdx.x * total / gridDim.x;
+    const long long end = (long long)(blockIdx.x + 1) * total / gridDim.x;
     const float invFg = 1.f / float(a.Fg);
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        const int k = item / a.tiles, tile = item - k * a.tiles;
+    const uint64_t pf = policy_evict_first(), pl = policy_evict_last();
+    const size_t n2 = size_t(N) * N;
+    long long u = beg;
+    while (u < end) {
+        const int k = int(u / upt);
+        const long long t_beg = (long long)k * upt;
+        const long long seg_end = (t_beg + upt < end) ? t_beg + upt : end;
         long long idx = k;
         if (a.offset_ptr) idx += *a.offset_ptr;
-        const long long act = (idx < a.n_total) ? a.actions[idx] : -1;
+        const long long act = a.n_inline ? a.inl_actions[k]
+                                         : ((idx < a.n_total) ? a.actions[idx] : -1);
         const Decoded d = decode_action(a, k, act);
         if (!d.active) {
-            if (tile == 0 && tid == 0) {
+            if (u == t_beg && tid == 0) {
                 Result r; r.psnr_after = 0.0; r.d_sii = 0.0; r.d_sit = 0.0;
                 r.action = -1; r.accept = 0; r.sgn = 0;
                 a.results[k] = r;
             }
+            u = seg_end;
             continue;
         }
-        const size_t n2 = size_t(N) * N;
         const float2* U = a.U + (size_t(d.env) * a.F + d.f) * n2;
         const float* I = a.I + (size_t(d.env) * a.G + d.g) * n2;
         const float* T = a.T + (size_t(d.env) * a.G + d.g) * n2;
         const float2* h = a.h + size_t(d.g) * P * P;
         const float s2 = 2.f * d.sgn * invFg;
-        float accII = 0.f, accIT = 0.f;
-        const int yend = min(N, (tile + 1) * a.rows_per_tile);
-        for (int y = tile * a.rows_per_tile + warp; y < yend; y += 8) {
-            int hy = y - d.r; if (hy < 0) hy += P;
-            const float2* hrow = h + size_t(hy) * P;
-            const float4* Urow = reinterpret_cast<const float4*>(U + size_t(y) * N);
-            const float4* Irow = reinterpret_cast<const float4*>(I + size_t(y) * N);
-            const float4* Trow = reinterpret_cast<const float4*>(T + size_t(y) * N);
-#pragma unroll 2
-            for (int xq = lane; xq < nq; xq += 32) {
-                const float4 ua = __ldg(Urow + 2 * xq), ub = __ldg(Urow + 2 * xq + 1);
-                const float4 iv = __ldg(Irow + xq), tv = __ldg(Trow + xq);
-                int hx = 4 * xq - d.c; if (hx < 0) hx += P;
-                int hx1 = hx + 1; if (hx1 >= P) hx1 -= P;
-                int hx2 = hx1 + 1; if (hx2 >= P) hx2 -= P;
-                int hx3 = hx2 + 1; if (hx3 >= P) hx3 -= P;
-                const float2 h0 = __ldg(hrow + hx), h1 = __ldg(hrow + hx1);
-                const float2 h2 = __ldg(hrow + hx2), h3 = __ldg(hrow + hx3);
-                const float d0 = delta_px(ua.x, ua.y, h0.x, h0.y, s2, invFg);
-                const float d1 = delta_px(ua.z, ua.w, h1.x, h1.y, s2, invFg);
-                const float d2 = delta_px(ub.x, ub.y, h2.x, h2.y, s2, invFg);
-                const float d3 = delta_px(ub.z, ub.w, h3.x, h3.y, s2, invFg);
-                accII = fmaf(d0, fmaf(2.f, iv.x, d0), accII);
-                accII = fmaf(d1, fmaf(2.f, iv.y, d1), accII);
-                accII = fmaf(d2, fmaf(2.f, iv.z, d2), accII);
-                accII = fmaf(d3, fmaf(2.f, iv.w, d3), accII);
-                accIT = fmaf(d0, tv.x, accIT);
-                accIT = fmaf(d1, tv.y, accIT);
-                accIT = fmaf(d2, tv.z, accIT);
-                accIT = fmaf(d3, tv.w, accIT);
-            }
+        long long aII = 0, aIT = 0;
+        Cursor cu; cu.init(int(u - t_beg), tid, N);
+        long long v = u;
+        for (; v + 1 < seg_end; v += 2) {            // two units in flight per thread
+            Quad q0, q1;
+            load_quad<true>(q0, U, I, T, h, cu, N, P, d.r, d.c, pf, pl); cu.next(a);
+            load_quad<true>(q1, U, I, T, h, cu, N, P, d.r, d.c, pf, pl); cu.next(a);
+            eval_quad(q0, s2, invFg, aII, aIT);
+            eval_quad(q1, s2, invFg, aII, aIT);
         }
-        const double wII = warp_sum(double(accII)), wIT = warp_sum(double(accIT));
-        if (lane == 0) { sh[0][warp] = wII; sh[1][warp] = wIT; }
+        if (v < seg_end) {
+            Quad q0;
+            load_quad<true>(q0, U, I, T, h, cu, N, P, d.r, d.c, pf, pl);
+            eval_quad(q0, s2, invFg, aII, aIT);
+        }
+        aII = warp_sum_ll(aII); aIT = warp_sum_ll(aIT);
+        if (lane == 0) { sh[0][warp] = aII; sh[1][warp] = aIT; }
         __syncthreads();
         if (tid == 0) {
-            double x = 0, y = 0;
+            long long x = 0, y = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) { x += sh[0][i]; y += sh[1][i]; }
-            a.partials[size_t(k) * a.tiles + tile] = make_double2(x, y);
+            atomicAdd(a.acc + 2 * k, (unsigned long long)x);
+            atomicAdd(a.acc + 2 * k + 1, (unsigned long long)y);
             __threadfence();
+            const int first = cta_of_unit(t_beg, total, gridDim.x);
+            const int last = cta_of_unit(t_beg + upt - 1, total, gridDim.x);
             s_ticket = atomicAdd(a.tickets + k, 1u);
-        }
-        __syncthreads();
-        if (s_ticket == unsigned(a.tiles - 1)) {          // last tile of task k
-            __threadfence();
-            // fixed-order fold: thread i takes tiles i, i+256, ...; then a tree
-            double x = 0, y = 0;
-            for (int i = tid; i < a.tiles; i += 256) {
-                const double2 p = __ldcg(a.partials + size_t(k) * a.tiles + i);
-                x += p.x; y += p.y;
-            }
-            x = warp_sum(x); y = warp_sum(y);
-            __syncthreads();
-            if (lane == 0) { sh[0][warp] = x; sh[1][warp] = y; }
-            __syncthreads();
-            if (tid == 0) {
-                double dII = 0, dIT = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { dII += sh[0][i]; dIT += sh[1][i]; }
+            if (s_ticket == unsigned(last - first)) {        // every contribution has landed
+                __threadfence();
+                const long long sII = (long long)__ldcg(a.acc + 2 * k);
+                const long long sIT = (long long)__ldcg(a.acc + 2 * k + 1);
+                const double dII = double(sII) * FIX_INV, dIT = double(sIT) * FIX_INV;
                 const double* S = a.sums + size_t(d.env) * 4;
                 const double sii = S[0] + dII, sit = S[1] + dIT, stt = S[2];
                 const double n = double(a.G) * double(n2);
@@ -378,62 +472,77 @@ k_eval(const DeltaArgs a) {
                 Result r; r.psnr_after = psnr; r.d_sii = dII; r.d_sit = dIT;
                 r.action = act; r.accept = acc; r.sgn = int(d.sgn);
                 a.results[k] = r;
+                if (a.results_host) a.results_host[k] = r;
+                a.acc[2 * k] = 0ull; a.acc[2 * k + 1] = 0ull;
                 a.tickets[k] = 0;
             }
         }
         __syncthreads();
+        u = seg_end;
     }
 }
 
 // k_commit: applies every accepted task: U_f += s*shift(h), I_g += dI, flips the
 // state byte and advances the running sums.  24 N^2 algorithmic HBM bytes per
-// accepted flip.  Tasks of one launch must target distinct environments.
+// accepted flip.  Tasks of one launch must target distinct environments
+// (n_tasks <= COMMIT_MAX_TASKS).  Every CTA first compacts the accepted tasks,
+// then the balanced unit partition runs over the accepted ones only, so a
+// launch with one accepted flip out of K still uses the whole chip.
+constexpr int COMMIT_MAX_TASKS = 256;
 __global__ void __launch_bounds__(256)
 k_commit(const DeltaArgs a) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int N = a.N, P = a.P, nq = N >> 2;
-    const int total = a.n_tasks * a.tiles;
+    __shared__ int s_list[COMMIT_MAX_TASKS];
+    __shared__ int s_cnt;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        int n = 0;
+        for (int k = 0; k < a.n_tasks; ++k)
+            if (a.results[k].accept) s_list[n++] = k;
+        s_cnt = n;
+    }
+    __syncthreads();
+    const int n_acc = s_cnt;
+    if (n_acc == 0) return;
+    const int N = a.N, P = a.P, upt = a.units_per_task;
+    const long long total = (long long)n_acc * upt;
+    const long long beg = (long long)blockIdx.x * total / gridDim.x;
+    const long long end = (long long)(blockIdx.x + 1) * total / gridDim.x;
     const float invFg = 1.f / float(a.Fg);
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        const int k = item / a.tiles, tile = item - k * a.tiles;
+    const uint64_t pf = policy_evict_first(), pl = policy_evict_last();
+    const size_t n2 = size_t(N) * N;
+    long long u = beg;
+    while (u < end) {
+        const int slot = int(u / upt);
+        const int k = s_list[slot];
+        const long long t_beg = (long long)slot * upt;
+        const long long seg_end = (t_beg + upt < end) ? t_beg + upt : end;
         const Result res = a.results[k];
-        if (!res.accept) continue;
         Decoded d = decode_action(a, k, res.action);
         d.sgn = float(res.sgn);            // the state byte may already be flipped
-        const size_t n2 = size_t(N) * N;
         float2* U = a.U + (size_t(d.env) * a.F + d.f) * n2;
         float* I = a.I + (size_t(d.env) * a.G + d.g) * n2;
         const float2* h = a.h + size_t(d.g) * P * P;
-        const float s2 = 2.f * d.sgn * invFg;
-        const int yend = min(N, (tile + 1) * a.rows_per_tile);
-        for (int y = tile * a.rows_per_tile + warp; y < yend; y += 8) {
-            int hy = y - d.r; if (hy < 0) hy += P;
-            const float2* hrow = h + size_t(hy) * P;
-            float4* Urow = reinterpret_cast<float4*>(U + size_t(y) * N);
-            float4* Irow = reinterpret_cast<float4*>(I + size_t(y) * N);
-#pragma unroll 2
-            for (int xq = lane; xq < nq; xq += 32) {
-                float4 ua = Urow[2 * xq], ub = Urow[2 * xq + 1];
-                float4 iv = Irow[xq];
-                int hx = 4 * xq - d.c; if (hx < 0) hx += P;
-                int hx1 = hx + 1; if (hx1 >= P) hx1 -= P;
-                int hx2 = hx1 + 1; if (hx2 >= P) hx2 -= P;
-                int hx3 = hx2 + 1; if (hx3 >= P) hx3 -= P;
-                const float2 h0 = __ldg(hrow + hx), h1 = __ldg(hrow + hx1);
-                const float2 h2 = __ldg(hrow + hx2), h3 = __ldg(hrow + hx3);
-                iv.x += delta_px(ua.x, ua.y, h0.x, h0.y, s2, invFg);
-                iv.y += delta_px(ua.z, ua.w, h1.x, h1.y, s2, invFg);
-                iv.z += delta_px(ub.x, ub.y, h2.x, h2.y, s2, invFg);
-                iv.w += delta_px(ub.z, ub.w, h3.x, h3.y, s2, invFg);
-                ua.x = fmaf(d.sgn, h0.x, ua.x); ua.y = fmaf(d.sgn, h0.y, ua.y);
-                ua.z = fmaf(d.sgn, h1.x, ua.z); ua.w = fmaf(d.sgn, h1.y, ua.w);
-                ub.x = fmaf(d.sgn, h2.x, ub.x); ub.y = fmaf(d.sgn, h2.y, ub.y);
-                ub.z = fmaf(d.sgn, h3.x, ub.z); ub.w = fmaf(d.sgn, h3.y, ub.w);
-                Urow[2 * xq] = ua; Urow[2 * xq + 1] = ub;
-                Irow[xq] = iv;
-            }
+        const float s2 = 2.f * d.sgn * invFg, sg = d.sgn;
+        Cursor cu; cu.init(int(u - t_beg), tid, N);
+        for (long long v = u; v < seg_end; ++v) {
+            Quad q;
+            load_quad<false>(q, U, I, nullptr, h, cu, N, P, d.r, d.c, pf, pl);
+            const size_t p = size_t(cu.y) * N + cu.x;
+            float4 iv = q.iv, ua = q.ua, ub = q.ub;
+            iv.x += delta_px(ua.x, ua.y, q.h0.x, q.h0.y, s2, invFg);
+            iv.y += delta_px(ua.z, ua.w, q.h1.x, q.h1.y, s2, invFg);
+            iv.z += delta_px(ub.x, ub.y, q.h2.x, q.h2.y, s2, invFg);
+            iv.w += delta_px(ub.z, ub.w, q.h3.x, q.h3.y, s2, invFg);
+            ua.x = fmaf(sg, q.h0.x, ua.x); ua.y = fmaf(sg, q.h0.y, ua.y);
+            ua.z = fmaf(sg, q.h1.x, ua.z); ua.w = fmaf(sg, q.h1.y, ua.w);
+            ub.x = fmaf(sg, q.h2.x, ub.x); ub.y = fmaf(sg, q.h2.y, ub.y);
+            ub.z = fmaf(sg, q.h3.x, ub.z); ub.w = fmaf(sg, q.h3.y, ub.w);
+            float4* Up = reinterpret_cast<float4*>(U + p);
+            Up[0] = ua; Up[1] = ub;
+            *reinterpret_cast<float4*>(I + p) = iv;
+            cu.next(a);
         }
-        if (tile == 0 && tid == 0) {
+        if (u == t_beg && tid == 0) {
             int8_t* st = a.state + (size_t(d.env) * a.F + d.f) * n2 + size_t(d.r) * N + d.c;
             *st = int8_t(1 - *st);
             double* S = a.sums + size_t(d.env) * 4;
@@ -441,6 +550,7 @@ k_commit(const DeltaArgs a) {
             S[1] += res.d_sit;
             S[3] = res.psnr_after;
         }
+        u = seg_end;
     }
 }
 

@@ -34,11 +34,11 @@ struct bh_ctx {
     double* dsums = nullptr;
     double* dloss_partial = nullptr;
     unsigned* dloss_ticket = nullptr;
-    int max_tasks = 0, tiles = 0, rows_per_tile = 8, grid_cap = 0;
+    int max_tasks = 0, units_per_task = 0, grid_cap = 0, grid_cap_commit = 0;
     int32_t* d_envs = nullptr;
     long long* d_actions = nullptr;
     Result* d_results = nullptr;
-    double2* d_partials = nullptr;
+    unsigned long long* d_acc = nullptr;
     unsigned* d_tickets = nullptr;
     long long* d_scalars = nullptr;      // [0] dbs cursor, [1] accepted count
     int32_t* h_envs = nullptr;           // pinned staging
@@ -46,7 +46,8 @@ struct bh_ctx {
     Result* h_results = nullptr;
     long long* h_scalars = nullptr;
     double* h_sums = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Result* h_results_dev = nullptr;     // device alias of the mapped h_results
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_eval = nullptr;
     int64_t launches = 0;
     std::string err;
 };
@@ -161,12 +162,13 @@ extern "C" int bh_destroy(bh_ctx* c) {
     cudaFree(c->dH); cudaFree(c->dh); cudaFree(c->dtw); cudaFree(c->dU); cudaFree(c->dscratch);
     cudaFree(c->dI); cudaFree(c->dT); cudaFree(c->drecon); cudaFree(c->dstate); cudaFree(c->dsums);
     cudaFree(c->dloss_partial); cudaFree(c->dloss_ticket);
-    cudaFree(c->d_envs); cudaFree(c->d_actions); cudaFree(c->d_results); cudaFree(c->d_partials);
+    cudaFree(c->d_envs); cudaFree(c->d_actions); cudaFree(c->d_results); cudaFree(c->d_acc);
     cudaFree(c->d_tickets); cudaFree(c->d_scalars);
     cudaFreeHost(c->h_envs); cudaFreeHost(c->h_actions); cudaFreeHost(c->h_results);
     cudaFreeHost(c->h_scalars); cudaFreeHost(c->h_sums);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_eval) cudaEventDestroy(c->ev_eval);
     delete c;
     return 0;
 }
@@ -178,7 +180,7 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
     *out = nullptr;
     if (n_env < 1 || N < 8 || F < 1 || G < 1 || !wl) BH_FAIL(nul, -1, "bad shape arguments");
     if (F % G) BH_FAIL(nul, -1, "F=%d is not a multiple of G=%d", F, G);
-    if (N % 8) BH_FAIL(nul, -1, "N=%d must be a multiple of 8", N);
+    if (N % 32) BH_FAIL(nul, -1, "N=%d must be a multiple of 32", N);
     if (pad != 1 && pad != 2) BH_FAIL(nul, -1, "pad must be 1 or 2");
     if (method != BH_METHOD_ASM && method != BH_METHOD_FRESNEL) BH_FAIL(nul, -1, "bad method");
     if (!fft_side_supported(N * pad, pad))
@@ -219,25 +221,27 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
     BH_TRY(cudaMalloc(&c->dsums, size_t(n_env) * 4 * sizeof(double)));
     BH_TRY(cudaMalloc(&c->dloss_partial, LOSS_BLOCKS * 3 * sizeof(double)));
     BH_TRY(cudaMalloc(&c->dloss_ticket, sizeof(unsigned)));
-    c->rows_per_tile = 8;
-    c->tiles = (N + c->rows_per_tile - 1) / c->rows_per_tile;
+    c->units_per_task = int(n2 / UNIT_PX);
     c->max_tasks = std::max(4096, n_env);
     BH_TRY(cudaMalloc(&c->d_envs, size_t(c->max_tasks) * sizeof(int32_t)));
     BH_TRY(cudaMalloc(&c->d_actions, size_t(c->max_tasks) * sizeof(long long)));
     BH_TRY(cudaMalloc(&c->d_results, size_t(c->max_tasks) * sizeof(Result)));
-    BH_TRY(cudaMalloc(&c->d_partials, size_t(c->max_tasks) * c->tiles * sizeof(double2)));
+    BH_TRY(cudaMalloc(&c->d_acc, size_t(c->max_tasks) * 2 * sizeof(unsigned long long)));
     BH_TRY(cudaMalloc(&c->d_tickets, size_t(c->max_tasks) * sizeof(unsigned)));
     BH_TRY(cudaMalloc(&c->d_scalars, 4 * sizeof(long long)));
     BH_TRY(cudaMallocHost(&c->h_envs, size_t(c->max_tasks) * sizeof(int32_t)));
     BH_TRY(cudaMallocHost(&c->h_actions, size_t(c->max_tasks) * sizeof(long long)));
-    BH_TRY(cudaMallocHost(&c->h_results, size_t(c->max_tasks) * sizeof(Result)));
+    BH_TRY(cudaHostAlloc(&c->h_results, size_t(c->max_tasks) * sizeof(Result), cudaHostAllocMapped));
+    if (rc == 0) BH_TRY(cudaHostGetDevicePointer(&c->h_results_dev, c->h_results, 0));
     BH_TRY(cudaMallocHost(&c->h_scalars, 4 * sizeof(long long)));
     BH_TRY(cudaMallocHost(&c->h_sums, size_t(n_env) * 4 * sizeof(double)));
     BH_TRY(cudaEventCreate(&c->ev0));
     BH_TRY(cudaEventCreate(&c->ev1));
+    BH_TRY(cudaEventCreateWithFlags(&c->ev_eval, cudaEventDisableTiming));
     if (rc == 0) {
         BH_TRY(cudaMemset(c->dloss_ticket, 0, sizeof(unsigned)));
         BH_TRY(cudaMemset(c->d_tickets, 0, size_t(c->max_tasks) * sizeof(unsigned)));
+        BH_TRY(cudaMemset(c->d_acc, 0, size_t(c->max_tasks) * 2 * sizeof(unsigned long long)));
         BH_TRY(cudaMemset(c->dsums, 0, size_t(n_env) * 4 * sizeof(double)));
         BH_TRY(cudaMemset(c->dT, 0, size_t(n_env) * G * n2 * sizeof(float)));
         BH_TRY(cudaMemset(c->dstate, 0, size_t(n_env) * F * n2));
@@ -253,6 +257,8 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
         int nb = 0;
         BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eval, 256, 0));
         c->grid_cap = std::max(1, nb) * prop.multiProcessorCount;
+        BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_commit, 256, 0));
+        c->grid_cap_commit = std::max(1, nb) * prop.multiProcessorCount;
     }
 #undef BH_TRY
     if (rc) { std::string keep = g_err; bh_destroy(c); g_err = keep; return rc; }
@@ -328,13 +334,16 @@ static DeltaArgs make_args(bh_ctx* c, int n, int env_fixed, const int32_t* d_env
     a.envs = d_envs; a.actions = d_actions; a.offset_ptr = nullptr; a.n_total = n;
     a.env_fixed = env_fixed;
     a.n_tasks = n; a.N = c->N; a.P = c->P; a.F = c->F; a.G = c->G; a.Fg = c->Fg;
-    a.tiles = c->tiles; a.rows_per_tile = c->rows_per_tile; a.relative = c->relative; a.rule = rule;
-    a.partials = c->d_partials; a.tickets = c->d_tickets; a.results = d_results;
+    a.relative = c->relative; a.rule = rule;
+    a.units_per_task = c->units_per_task;
+    a.unit_dy = UNIT_PX / c->N; a.unit_dx = UNIT_PX % c->N;
+    a.acc = c->d_acc; a.tickets = c->d_tickets; a.results = d_results;
+    a.results_host = nullptr; a.n_inline = 0;
     return a;
 }
 
 static inline int delta_grid(const bh_ctx* c, int n) {
-    const long long total = (long long)n * c->tiles;
+    const long long total = (long long)n * c->units_per_task;
     return int(std::min<long long>(total, c->grid_cap));
 }
 
@@ -343,9 +352,18 @@ static int launch_eval(bh_ctx* c, const DeltaArgs& a) {
     c->launches += 1;
     return 0;
 }
-static int launch_commit(bh_ctx* c, const DeltaArgs& a) {
-    k_commit<<<delta_grid(c, a.n_tasks), 256, 0, c->stream>>>(a);
-    c->launches += 1;
+// commit launches carry at most COMMIT_MAX_TASKS tasks; larger batches are split
+static int launch_commit(bh_ctx* c, const DeltaArgs& a0) {
+    for (int base = 0; base < a0.n_tasks; base += COMMIT_MAX_TASKS) {
+        DeltaArgs a = a0;
+        a.n_tasks = std::min(COMMIT_MAX_TASKS, a0.n_tasks - base);
+        if (a.envs) a.envs += base;
+        a.results += base;
+        // one accepted task already fills the chip; more only add units
+        const int grid = int(std::min<long long>((long long)a.units_per_task, c->grid_cap_commit));
+        k_commit<<<grid, 256, 0, c->stream>>>(a);
+        c->launches += 1;
+    }
     return 0;
 }
 
@@ -441,14 +459,29 @@ extern "C" int bh_step_batch(bh_ctx* c, int n, const int32_t* env_ids, const int
         c->h_envs[i] = e;
         c->h_actions[i] = actions[i];
     }
-    BH_CUDA(c, cudaMemcpyAsync(c->d_actions, c->h_actions, size_t(n) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-    BH_CUDA(c, cudaMemcpyAsync(c->d_envs, c->h_envs, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     DeltaArgs a = make_args(c, n, 0, c->d_envs, c->d_actions, rule, c->d_results);
-    launch_eval(c, a);
-    if (rule != RULE_NEVER) launch_commit(c, a);
-    BH_CUDA(c, cudaGetLastError());
-    BH_CUDA(c, cudaMemcpyAsync(c->h_results, c->d_results, size_t(n) * sizeof(Result), cudaMemcpyDeviceToHost, c->stream));
-    BH_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n <= INLINE_MAX) {
+        // step path: tasks ride in the kernel parameters, the finaliser mirrors the results
+        // into mapped pinned memory, and the host only waits for the evaluation -- the
+        // commit of the accepted flips overlaps the caller's bookkeeping (stream order
+        // keeps every later call behind it)
+        a.n_inline = n;
+        for (int i = 0; i < n; ++i) { a.inl_actions[i] = c->h_actions[i]; a.inl_envs[i] = c->h_envs[i]; }
+        a.results_host = c->h_results_dev;
+        launch_eval(c, a);
+        BH_CUDA(c, cudaEventRecord(c->ev_eval, c->stream));
+        if (rule != RULE_NEVER) launch_commit(c, a);
+        BH_CUDA(c, cudaGetLastError());
+        BH_CUDA(c, cudaEventSynchronize(c->ev_eval));
+    } else {
+        BH_CUDA(c, cudaMemcpyAsync(c->d_actions, c->h_actions, size_t(n) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+        BH_CUDA(c, cudaMemcpyAsync(c->d_envs, c->h_envs, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        launch_eval(c, a);
+        if (rule != RULE_NEVER) launch_commit(c, a);
+        BH_CUDA(c, cudaGetLastError());
+        BH_CUDA(c, cudaMemcpyAsync(c->h_results, c->d_results, size_t(n) * sizeof(Result), cudaMemcpyDeviceToHost, c->stream));
+        BH_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     std::memcpy(results, c->h_results, size_t(n) * sizeof(Result));
     return 0;
 }

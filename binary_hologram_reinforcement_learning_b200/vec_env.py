@@ -15,7 +15,7 @@ from typing import Callable, Iterable, List, Optional, Sequence
 import numpy as np
 
 from .engine import HoloEngine, RULE_ENV, RESULT_DTYPE
-from .envs import BinaryHologramEnv, WL_MONO
+from .envs import BinaryHologramEnv, WL_MONO, RW, goal_bonus
 
 
 class HologramVecEnv:
@@ -50,6 +50,23 @@ class HologramVecEnv:
         # episode statistics of finished episodes: reward, steps, flips, psnr0, psnr1
         self.episode_stats: List[np.ndarray] = []
         self._ep_reward = np.zeros(self.num_envs)
+        # vectorised bookkeeping (env.py:154-260 evaluated for all envs at once); used when no
+        # per-step printing, cropping or rank-table reward is involved
+        self._fast = (crop_margin == 0 and reward_mode == "psnr" and not verbose
+                      and recon_obs != "eager")
+        E = self.num_envs
+        self._steps = np.zeros(E, dtype=np.int64)
+        self._flips = np.zeros(E, dtype=np.int64)
+        self._prev = np.zeros(E)
+        self._init = np.zeros(E)
+        self._sustained = np.zeros(E, dtype=np.int64)
+        self._ar = np.arange(E)
+        self._state = self._record = None
+        self._last_cand = np.full(E, -1, dtype=np.int64)
+        self._tdiff = np.full(E, float(T_PSNR_DIFF))
+        self._tpsnr = np.full(E, float(T_PSNR))
+        self._maxsteps = np.full(E, int(max_steps), dtype=np.int64)
+        self._obs_cache = [None] * E
 
     # ------------------------------------------------------------------
     def _pack(self, obs_list):
@@ -57,15 +74,103 @@ class HologramVecEnv:
             return obs_list
         return {k: np.stack([o[k] for o in obs_list]) for k in obs_list[0]}
 
+    def _adopt(self, i: int):
+        """Re-home env i's host mirrors in the stacked arrays and load its scalars."""
+        env = self.envs[i]
+        if self._state is None:
+            shape = (self.num_envs,) + env.state.shape
+            self._state = np.zeros(shape, dtype=np.int8)
+            self._record = np.zeros(shape, dtype=np.int8)
+            self._state2d = self._state.reshape(self.num_envs, -1)
+            self._record2d = self._record.reshape(self.num_envs, -1)
+        self._state[i] = env.state
+        self._record[i] = env.state_record
+        env.state, env.state_record = self._state[i], self._record[i]
+        self._steps[i] = env.steps
+        self._flips[i] = env.flip_count
+        self._prev[i] = env.previous_psnr
+        self._init[i] = env.initial_psnr
+        self._sustained[i] = env.psnr_sustained_steps
+        self._last_cand[i] = -1
+        self._tdiff[i], self._tpsnr[i], self._maxsteps[i] = env.T_PSNR_DIFF, env.T_PSNR, env.max_steps
+        self._obs_cache[i] = env._obs()
+
+    def sync_envs(self):
+        """Push the vectorised counters back into the per-env objects."""
+        if not self._fast:
+            return
+        for i, env in enumerate(self.envs):
+            env.steps, env.flip_count = int(self._steps[i]), int(self._flips[i])
+            env.previous_psnr, env.psnr_sustained_steps = float(self._prev[i]), int(self._sustained[i])
+            env._last_candidate = int(self._last_cand[i])
+
+    def refresh_recon(self, i: int) -> np.ndarray:
+        """obs["recon_image"] of env i, the last evaluated flip included (env.py:176-181)."""
+        self.sync_envs()
+        return self.envs[i].refresh_recon()
+
+    def _reset_env(self, i: int):
+        obs = self.envs[i].reset(z=self.z, pixel_pitch=self.pixel_pitch)[0]
+        self._adopt(i)
+        return self.envs[i]._obs()
+
     def reset(self):
-        obs = [e.reset(z=self.z, pixel_pitch=self.pixel_pitch)[0] for e in self.envs]
+        obs = [self._reset_env(i) for i in range(self.num_envs)]
         self._ep_reward[:] = 0
         return self._pack(obs)
+
+    def _step_fast(self):
+        """env.py:154-260 for all envs with numpy; per-env Python only on episode events."""
+        acts, envs, E = self._actions, self.envs, self.num_envs
+        res = self.engine.step_batch(acts, self._eids, RULE_ENV, out=self._res)
+        acc = res["accept"] != 0
+        psnr_after = res["psnr_after"]
+        self._steps += 1
+        self._record2d[self._ar, acts] += 1                          # env.py:165
+        change = psnr_after - self._prev                             # env.py:184-188
+        diff = psnr_after - self._init
+        rewards = change * RW
+        self._state2d[self._ar[acc], acts[acc]] ^= 1                 # env.py:164 / 191-193
+        self._flips += acc
+        self._prev[acc] = psnr_after[acc]                            # env.py:214
+        dones = np.zeros(E, dtype=bool)
+        infos = [{} for _ in range(E)]
+        self._last_cand = np.where(acc, -1, acts)
+        event = acc & ((diff >= self._tdiff) | ((psnr_after >= self._tpsnr) & (diff < 0.1))
+                       | (self._steps >= self._maxsteps))
+        if envs[0].resync_every > 0:
+            for i in np.flatnonzero(acc & (self._flips % envs[0].resync_every == 0)):
+                self.engine.resync(int(i))
+        for i in np.flatnonzero(event):                              # env.py:216-260
+            env = envs[i]
+            ratio = self._flips[i] / self._steps[i]
+            if diff[i] >= env.T_PSNR_DIFF or (psnr_after[i] >= env.T_PSNR and diff[i] < 0.1):
+                self._sustained[i] += 1
+                if self._sustained[i] >= env.T_steps and diff[i] >= env.T_PSNR_DIFF:
+                    rewards[i] += goal_bonus(ratio, -595.2)
+            if self._steps[i] >= env.max_steps:
+                rewards[i] += goal_bonus(ratio, -595.24)
+            term = self._steps[i] >= env.max_steps or self._sustained[i] >= env.T_steps
+            trunc = self._steps[i] >= env.max_steps
+            if term or trunc:
+                dones[i] = True
+                self.sync_envs()
+                infos[i] = {"terminal_observation": {k: np.array(v) for k, v in env._obs().items()},
+                            "TimeLimit.truncated": bool(trunc and not term)}
+                self.episode_stats.append(np.array(
+                    [self._ep_reward[i] + rewards[i], self._steps[i], self._flips[i], self._init[i],
+                     self._prev[i]]))
+                self._ep_reward[i] = -rewards[i]
+                self._reset_env(i)
+        self._ep_reward += rewards
+        return self._pack(self._obs_cache), rewards, dones, infos
 
     def step_async(self, actions):
         self._actions = np.asarray(actions, dtype=np.int64).reshape(self.num_envs)
 
     def step_wait(self):
+        if self._fast:
+            return self._step_fast()
         acts = self._actions
         envs = self.envs
         if envs[0].crop_margin == 0:
@@ -95,12 +200,12 @@ class HologramVecEnv:
             if term or trunc:
                 dones[i] = True
                 info = dict(info)
-                info["terminal_observation"] = obs
+                info["terminal_observation"] = {k: np.array(v) for k, v in obs.items()}
                 info["TimeLimit.truncated"] = bool(trunc and not term)
                 self.episode_stats.append(np.array(
                     [self._ep_reward[i], env.steps, env.flip_count, env.initial_psnr, env.previous_psnr]))
                 self._ep_reward[i] = 0.0
-                obs = env.reset(z=self.z, pixel_pitch=self.pixel_pitch)[0]
+                obs = self._reset_env(i)
             obs_list.append(obs)
             infos.append(info)
         return self._pack(obs_list), rewards, dones, infos

@@ -211,6 +211,7 @@ def test_vec_env_matches_independent_oracle_envs():
         e.reset(pre, tgt)
         refs.append(e)
         assert abs(vec.envs[i].initial_psnr - e.initial_psnr) < 1e-4
+    assert vec._fast
     rng = np.random.default_rng(5)
     for step in range(40):
         acts = rng.integers(0, F * N * N, size=E)
@@ -219,11 +220,51 @@ def test_vec_env_matches_independent_oracle_envs():
             r, term, trunc, p, acc = refs[i].step(int(acts[i]))
             assert abs(rewards[i] - r) <= 1e-5 * abs(r) + 800 * 2e-7
             assert not dones[i]
+    vec.sync_envs()
     for i in range(E):
         assert np.array_equal(vec.envs[i].state[0], refs[i].state)
+        assert np.array_equal(vec.envs[i].state_record[0], refs[i].state_record)
         assert np.array_equal(vec.engine.state(i), refs[i].state)
-        rec = vec.envs[i].refresh_recon()[0]
+        assert vec.envs[i].flip_count == refs[i].flip_count and vec.envs[i].steps == refs[i].steps
+        rec = vec.refresh_recon(i)[0]
         np.testing.assert_allclose(rec, refs[i].recon, atol=3e-5 * refs[i].recon.max())
+    vec.close()
+
+
+@pytest.mark.parametrize("verbose", [False, True])
+def test_vec_env_episode_end_bonus_and_autoreset(verbose, capsys):
+    """max_steps bonus (env.py:237-254), SB3-style auto-reset; fast (numpy) and per-env paths agree."""
+    N, F, wl, E, MAXS = 64, 8, O.WL_MONO, 3, 12
+    loaders = [bh.SyntheticLoader(N, F, 1, seeds=(200 + i,)) for i in range(E)]
+    tf = lambda t: next(l for l in loaders if np.ascontiguousarray(t[0, 0, 0, :4]).tobytes() in l._pre).target_function(t)
+    vec = bh.HologramVecEnv(E, tf, loaders, max_steps=MAXS, T_PSNR_DIFF=1e9, IPS=N, CH=F, wl=wl,
+                            verbose=verbose)
+    assert vec._fast == (not verbose)
+    vec.reset()
+    cfg = O.HoloConfig(N=N, F=F, wl=wl)
+    probs = [bh.synthetic_problem(N, F, 1, 200 + i) for i in range(E)]
+    refs = []
+    for i in range(E):
+        e = O.OracleEnv(cfg, max_steps=MAXS, T_PSNR_DIFF=1e9)
+        e.reset(*probs[i])
+        refs.append(e)
+    rng = np.random.default_rng(8)
+    n_done = 0
+    for step in range(40):
+        acts = rng.integers(0, F * N * N, size=E)
+        obs, rewards, dones, infos = vec.step(acts)
+        for i in range(E):
+            r, term, trunc, p, acc = refs[i].step(int(acts[i]))
+            assert abs(rewards[i] - r) <= 1e-5 * abs(r) + 800 * 2e-7, (step, i, rewards[i], r)
+            assert bool(dones[i]) == bool(term or trunc)
+            if dones[i]:
+                n_done += 1
+                assert "terminal_observation" in infos[i] and infos[i]["TimeLimit.truncated"] is False
+                assert infos[i]["terminal_observation"]["state"].sum() == refs[i].state.sum()
+                refs[i].reset(*probs[i])
+                assert np.array_equal(obs[i]["state"][0], refs[i].state)
+    assert n_done >= E and len(vec.episode_stats) == n_done
+    capsys.readouterr()
     vec.close()
 
 
