@@ -17,7 +17,8 @@ if [ "${NCU:-1}" = "1" ]; then
       --log-file gpurun_out/launches.csv $SMALL > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches rc=$?"
   timeout 600 $SMALL > gpurun_out/bench_small2.json 2> gpurun_out/bench_small2.err &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_eval -s 40 -c 3 \
-      -f -o gpurun_out/prof_k_eval $SMALL > gpurun_out/ncu_full.log 2>&1
+  timeout 1200 ncu --set full --clock-control none --import-source on \
+      -k regex:"k_(eval|commit|rows_fwd|cols|rows_inv|loss_sums)" -s 24 -c 28 \
+      -f -o gpurun_out/prof_hotpath $SMALL > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
 fi

@@ -372,3 +372,40 @@ def test_full_size_properties():
     inc = tr[acc.astype(bool)]
     assert np.all(np.diff(inc) > 0)
     eng.close()
+
+
+# ---------------------------------------------------------------------------
+# drop-in shims: the reference's own call sequence (env.py:123-132) through compat/torchOptics
+# ---------------------------------------------------------------------------
+def test_reference_call_sequence_through_compat_shims():
+    import sys
+    import torch
+    compat = os.path.join(os.path.dirname(bh.__file__), "compat")
+    sys.path.insert(0, compat)
+    try:
+        import torchOptics.optics as tt
+        import torchOptics.metrics as tm
+        import env as ref_env_module
+    finally:
+        sys.path.remove(compat)
+    assert ref_env_module.BinaryHologramEnv is bh.BinaryHologramEnv and ref_env_module.IPS == 256
+    N, F = 256, 8
+    pre, tgt = bh.synthetic_problem(N, F, 1, 5)
+    state = (pre >= 0.5).astype(np.int8)[None]
+    # --- verbatim shape of env.py:123-132 ---
+    binary = torch.tensor(state, dtype=torch.float32).cuda()
+    binary = tt.Tensor(binary, meta={'dx': (7.56e-6, 7.56e-6), 'wl': 515e-9})
+    sim = tt.simulate(binary, 2e-3).abs() ** 2
+    result = torch.mean(sim, dim=1, keepdim=True)
+    target = torch.from_numpy(tgt[None]).cuda()
+    psnr = tt.relativeLoss(result, target, tm.get_PSNR)
+    # ---
+    cfg = O.HoloConfig(N=N, F=F)
+    psnr_ref, _ = O.score(cfg, O.reconstruct(cfg, state[0]), tgt)
+    assert isinstance(psnr, float) and abs(psnr - psnr_ref) < PSNR_TOL
+    # numpy int8 input as in env_1024_24.py:149-151
+    red = tt.Tensor(state[:, :4], meta={'wl': (638e-9), 'dx': (7.56e-6, 7.56e-6)})
+    U = tt.simulate(red, 2e-3)
+    H = O.transfer_function(N, O.PIXEL_PITCH, 638e-9, O.Z_DEFAULT)
+    ref = O.simulate(state[0, :4].astype(np.float64), H, 1)
+    assert np.abs(U.cpu().numpy()[0] - ref).max() < 1e-5 * np.abs(ref).max()
