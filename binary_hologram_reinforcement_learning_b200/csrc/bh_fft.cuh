@@ -1,11 +1,9 @@
 // Shared-memory tile FFT primitives for the hologram propagation kernels (sm_100a).
 //
-// A "tile" is W independent length-N complex sequences interleaved in shared
-// memory: element i of sequence w lives at s[i * WP + w] (WP >= W, WP = W + 1
-// pads the transposing loads of the row passes off the same banks).  Threads
-// are laid out across sequences first (w = tid % W, q = tid / W), so every
-// warp-wide shared access touches consecutive 8-byte words: conflict free by
-// construction for both the row passes and the column pass.
+// A "tile" is W = 8 independent length-N complex sequences in shared memory, in
+// one of two skewed layouts (see "shared-memory layouts" below): sequence-major
+// for the row passes (global rows copy in and out coalesced), interleaved for the
+// column pass (a 64-byte row segment of 8 columns copies in and out directly).
 //
 // One Stockham autosort pass of radix R (Ns = product of the radices already
 // applied) does, for butterfly j in [0, N/R):
@@ -149,59 +147,19 @@ template <int R, bool INV> BH_HD void dft(float2* v) {
 }
 
 // ---------------------------------------------------------------------------
-// one Stockham pass split in two phases around a barrier
+// shared-memory layouts.  Element e of a sequence lives at
+//     s[ (e + (e >> SK)) * ES + base ]
+// i.e. one padding slot after every 2^SK elements (a skew that breaks the
+// power-of-two strides of the Stockham scatter):
+//   row layout     ES = 1, base = w * SEQ      threads along the sequence
+//                  (16 consecutive butterflies per half-warp -> 16 distinct banks)
+//   column layout  ES = W (8 or 16), base = w   threads across the W sequences first
+//                  (W = 8: 8 sequences x 2 butterflies per half-warp, the skew makes the two
+//                   butterflies land 8 float2 apart modulo 16; W = 16: one butterfly per
+//                   half-warp, 16 consecutive float2)
 // ---------------------------------------------------------------------------
-template <int N, int R, int Ns, int Q>
-struct PassShape {
-    static constexpr int NBF = N / R;                 // butterflies per sequence
-    static constexpr int NB = (NBF + Q - 1) / Q;      // butterflies per thread
-};
-
-// phase 1: gather + twiddle + butterfly into registers.
-// s points at sequence w (already offset by w); q is the thread's slot in [0,Q).
-// tw: forward twiddle table exp(-2 pi i m / N), m in [0, N).
-template <int N, int R, int Ns, int Q, int WP, bool INV>
-BH_HD void pass_read(const float2* s, int q, const float2* __restrict__ tw,
-                     float2 (&v)[PassShape<N, R, Ns, Q>::NB][R]) {
-    constexpr int NBF = N / R;
-    constexpr int NB = PassShape<N, R, Ns, Q>::NB;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        const int j = q + b * Q;
-        if ((NBF % Q == 0) || j < NBF) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[b][r] = s[(j + r * NBF) * WP];
-            if (Ns > 1) {
-                const int k = j % Ns;
-                constexpr int step = N / (Ns * R);
-#pragma unroll
-                for (int r = 1; r < R; ++r) {
-                    float2 w = tw[r * k * step];
-                    if (INV) w.y = -w.y;
-                    v[b][r] = cmul(v[b][r], w);
-                }
-            }
-            dft<R, INV>(v[b]);
-        }
-    }
-}
-
-// phase 2: scatter to the autosorted positions.
-template <int N, int R, int Ns, int Q, int WP>
-BH_HD void pass_write(float2* s, int q, const float2 (&v)[PassShape<N, R, Ns, Q>::NB][R]) {
-    constexpr int NBF = N / R;
-    constexpr int NB = PassShape<N, R, Ns, Q>::NB;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        const int j = q + b * Q;
-        if ((NBF % Q == 0) || j < NBF) {
-            const int k = j % Ns;
-            const int j0 = (j / Ns) * Ns * R + k;
-#pragma unroll
-            for (int r = 0; r < R; ++r) s[(j0 + r * Ns) * WP] = v[b][r];
-        }
-    }
-}
+template <int SK> BH_HD int padded(int e) { return e + (e >> SK); }
+template <int N, int SK> struct SeqLen { static constexpr int value = N + (N >> SK) + 1; };
 
 // ---------------------------------------------------------------------------
 // radix plans.  The product of the radices is N; larger radices first keeps the
@@ -218,30 +176,92 @@ template <> struct Plan<1024> { static constexpr int n = 3; static constexpr int
 template <> struct Plan<1792> { static constexpr int n = 3; static constexpr int r[3] = {16, 16, 7}; };
 template <> struct Plan<2048> { static constexpr int n = 3; static constexpr int r[3] = {16, 16, 8}; };
 
-#ifdef __CUDACC__
-#define BH_SYNC() __syncthreads()
-#else
-#define BH_SYNC() ((void)0)
-#endif
+// Twiddle table of a plan: for pass p >= 1 with radix R and Ns = product of the
+// earlier radices, entries tw[off_p + (r - 1) * Ns + k] = exp(-2 pi i r k / (Ns R)),
+// r = 1..R-1, k = 0..Ns-1.  Consecutive k are contiguous, so the threads of a warp
+// (consecutive butterflies) read one or two 128-byte lines per twiddle.
+template <int N> struct TwLayout {
+    using P = Plan<N>;
+    static constexpr int off1 = 0;
+    static constexpr int len1 = (P::r[1] - 1) * P::r[0];
+    static constexpr int off2 = len1;
+    static constexpr int len2 = (P::n == 3) ? (P::r[2] - 1) * P::r[0] * P::r[1] : 0;
+    static constexpr int total = len1 + len2;
+};
+
+// ---------------------------------------------------------------------------
+// one Stockham pass split in two phases around a barrier
+// ---------------------------------------------------------------------------
+template <int N, int R, int Ns, int Q>
+struct PassShape {
+    static constexpr int NBF = N / R;                 // butterflies per sequence
+    static constexpr int NB = (NBF + Q - 1) / Q;      // butterflies per thread
+};
+
+// phase 1: gather + twiddle + butterfly into registers.
+// s points at the sequence base; q is the thread's slot in [0,Q).
+// twp: this pass's twiddle block (see TwLayout), forward sign.
+template <int N, int R, int Ns, int Q, int ES, int SK, bool INV>
+BH_HD void pass_read(const float2* s, int q, const float2* __restrict__ twp,
+                     float2 (&v)[PassShape<N, R, Ns, Q>::NB][R]) {
+    constexpr int NBF = N / R;
+    constexpr int NB = PassShape<N, R, Ns, Q>::NB;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int j = q + b * Q;
+        if ((NBF % Q == 0) || j < NBF) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[b][r] = s[padded<SK>(j + r * NBF) * ES];
+            if (Ns > 1) {
+                const int k = j % Ns;
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    float2 w = twp[(r - 1) * Ns + k];
+                    if (INV) w.y = -w.y;
+                    v[b][r] = cmul(v[b][r], w);
+                }
+            }
+            dft<R, INV>(v[b]);
+        }
+    }
+}
+
+// phase 2: scatter to the autosorted positions.
+template <int N, int R, int Ns, int Q, int ES, int SK>
+BH_HD void pass_write(float2* s, int q, const float2 (&v)[PassShape<N, R, Ns, Q>::NB][R]) {
+    constexpr int NBF = N / R;
+    constexpr int NB = PassShape<N, R, Ns, Q>::NB;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int j = q + b * Q;
+        if ((NBF % Q == 0) || j < NBF) {
+            const int k = j % Ns;
+            const int j0 = (j / Ns) * Ns * R + k;
+#pragma unroll
+            for (int r = 0; r < R; ++r) s[padded<SK>(j0 + r * Ns) * ES] = v[b][r];
+        }
+    }
+}
 
 #ifdef __CUDACC__
 // Full in-place tile FFT executed cooperatively by the CTA (device only).
-template <int N, int Q, int WP, bool INV, int R, int Ns>
-__device__ __forceinline__ void tile_pass(float2* s, int q, const float2* __restrict__ tw) {
+template <int N, int Q, int ES, int SK, bool INV, int R, int Ns>
+__device__ __forceinline__ void tile_pass(float2* s, int q, const float2* __restrict__ twp) {
     float2 v[PassShape<N, R, Ns, Q>::NB][R];
-    pass_read<N, R, Ns, Q, WP, INV>(s, q, tw, v);
+    pass_read<N, R, Ns, Q, ES, SK, INV>(s, q, twp, v);
     __syncthreads();
-    pass_write<N, R, Ns, Q, WP>(s, q, v);
+    pass_write<N, R, Ns, Q, ES, SK>(s, q, v);
     __syncthreads();
 }
 
-template <int N, int Q, int WP, bool INV>
+template <int N, int Q, int ES, int SK, bool INV>
 __device__ __forceinline__ void tile_fft(float2* s, int q, const float2* __restrict__ tw) {
     using P = Plan<N>;
+    using L = TwLayout<N>;
     constexpr int R0 = P::r[0], R1 = P::r[1], R2 = P::r[2];
-    tile_pass<N, Q, WP, INV, R0, 1>(s, q, tw);
-    tile_pass<N, Q, WP, INV, R1, R0>(s, q, tw);
-    if constexpr (P::n == 3) tile_pass<N, Q, WP, INV, R2, R0 * R1>(s, q, tw);
+    tile_pass<N, Q, ES, SK, INV, R0, 1>(s, q, tw);
+    tile_pass<N, Q, ES, SK, INV, R1, R0>(s, q, tw + L::off1);
+    if constexpr (P::n == 3) tile_pass<N, Q, ES, SK, INV, R2, R0 * R1>(s, q, tw + L::off2);
 }
 #endif
 

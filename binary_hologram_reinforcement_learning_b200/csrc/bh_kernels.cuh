@@ -1,6 +1,7 @@
 // CUDA kernels of the hologram reward / DBS hot path (sm_100a).
 //
-//  propagation (reset / re-sync):  k_rows_fwd -> k_cols -> k_rows_inv  (+ k_loss_sums)
+//  propagation (reset / re-sync), per colour group:
+//      k_rows_fwd -> k_cols -> k_rows_inv -> k_intensity ; then k_loss_final
 //      restates tt.simulate + .abs()**2 + mean(dim=1) + tt.relativeLoss
 //      (reference env.py:123-132, env_1024_24.py:149-166)
 //  incremental path (every step / candidate):  k_eval -> k_commit
@@ -36,25 +37,37 @@ struct Result {            // mirrored by bh_result in include/bholo.h (40 bytes
 enum { RULE_ENV = 0, RULE_DBS = 1, RULE_NEVER = 2 };
 
 constexpr int TILE_W = 8;          // sequences per FFT tile
-constexpr int TILE_WP = TILE_W + 1;
 
+constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
+
+// threads per CTA: P/16 threads per sequence (16 complex values in registers per
+// thread and pass) so that two CTAs share an SM at P = 1024
 template <int P> struct FftCfg {
-    static constexpr int T = (P >= 1792) ? 512 : 256;   // threads per CTA
+    static constexpr int T = (P >= 896) ? 512 : 256;    // threads per CTA
     static constexpr int Q = T / TILE_W;                // threads per sequence
-    static constexpr size_t smem = size_t(P) * TILE_WP * sizeof(float2);
+    static constexpr int MINB = (P <= 1024) ? 2 : 1;    // CTAs per SM the compiler must allow
+    static constexpr int SKR = 4;                       // row layout: pad after every 16 elements
+    static constexpr int SKC = ilog2_c(Plan<P>::r[0]);  // column layout: pad after every R0 elements
+    static constexpr int SEQ = SeqLen<P, SKR>::value;   // row layout: stride between sequences
+    static constexpr size_t smem_row = size_t(SEQ) * TILE_W * sizeof(float2);
+    // column pass: 8 columns per tile (64-byte row segments).  16 columns x 1024 threads was
+    // measured equal at best (it spills at the 64-register cap), see profiles/r1_notes.md
+    static constexpr int WC = 8;
+    static constexpr int TC = WC * Q;
+    static constexpr int MINBC = (TC >= 1024) ? 1 : MINB;
+    static constexpr size_t smem_col = size_t(SeqLen<P, SKC>::value) * WC * sizeof(float2);
 };
 
-__device__ __forceinline__ float ld_real(const int8_t* p, size_t i) { return float(p[i]); }
-__device__ __forceinline__ float ld_real(const float* p, size_t i) { return p[i]; }
-
 // ---------------------------------------------------------------------------
-// pass A: FFT along x of W canvas rows.  in: [frames][N][N] real (int8/float)
-// or complex (float2, IS_CPLX); out: buf [frames][P][P].
+// pass A: FFT along x of W canvas rows.  in: [frames][N][N] int8 state (or
+// complex float2 for the stand-alone operator); out: buf [frames][P][P].
+// Row layout: thread (w = tid / Q, q = tid % Q).
 // ---------------------------------------------------------------------------
 template <int P, int PAD, typename InT, bool IS_CPLX>
-__global__ void __launch_bounds__(FftCfg<P>::T)
+__global__ void __launch_bounds__(FftCfg<P>::T, FftCfg<P>::MINB)
 k_rows_fwd(const InT* __restrict__ in, float2* __restrict__ buf, const float2* __restrict__ tw) {
-    constexpr int N = P / PAD, O = (P - N) / 2, T = FftCfg<P>::T, Q = FftCfg<P>::Q;
+    using C = FftCfg<P>;
+    constexpr int N = P / PAD, O = (P - N) / 2, T = C::T, Q = C::Q, SK = C::SKR, SEQ = C::SEQ;
     extern __shared__ float2 s[];
     const int tid = threadIdx.x, f = blockIdx.y, Y0 = blockIdx.x * TILE_W;
     float2* out = buf + size_t(f) * P * P;
@@ -62,113 +75,175 @@ k_rows_fwd(const InT* __restrict__ in, float2* __restrict__ buf, const float2* _
         for (int i = tid; i < TILE_W * P; i += T) out[size_t(Y0) * P + i] = make_float2(0.f, 0.f);
         return;
     }
+    if constexpr (!IS_CPLX && PAD == 1) {
+        // binary state: one 16-byte load = 16 pixels per thread, all loads of the tile in flight
+        constexpr int CH = N / 16;                       // 16-pixel chunks per row
+        constexpr int NI = (TILE_W * CH + T - 1) / T;
+        int4 raw[NI];
 #pragma unroll
-    for (int w = 0; w < TILE_W; ++w) {
-        const int y = Y0 + w - O;
-        const bool rowok = (y >= 0 && y < N);
-        for (int X = tid; X < P; X += T) {
-            const int x = X - O;
-            float2 v = make_float2(0.f, 0.f);
-            if (rowok && x >= 0 && x < N) {
-                const size_t idx = (size_t(f) * N + y) * N + x;
-                if constexpr (IS_CPLX) v = reinterpret_cast<const float2*>(in)[idx];
-                else v.x = ld_real(in, idx);
+        for (int k = 0; k < NI; ++k) {
+            const int i = tid + k * T;
+            if ((TILE_W * CH) % T == 0 || i < TILE_W * CH) {
+                const int w = i / CH, xc = i - w * CH;
+                raw[k] = __ldg(reinterpret_cast<const int4*>(
+                    reinterpret_cast<const int8_t*>(in) + (size_t(f) * N + Y0 + w) * N + 16 * xc));
             }
-            s[X * TILE_WP + w] = v;
         }
+#pragma unroll
+        for (int k = 0; k < NI; ++k) {
+            const int i = tid + k * T;
+            if ((TILE_W * CH) % T == 0 || i < TILE_W * CH) {
+                const int w = i / CH, xc = i - w * CH;
+                const int words[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+                float2* d = s + w * SEQ + padded<SK>(16 * xc);   // 16 | X0: the chunk never straddles a pad slot
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    d[j] = make_float2(float(int8_t((words[j >> 2] >> (8 * (j & 3))) & 0xff)), 0.f);
+            }
+        }
+    } else {
+        constexpr int NX = (P + T - 1) / T;
+        float2 v[TILE_W][NX];
+#pragma unroll
+        for (int w = 0; w < TILE_W; ++w) {
+            const int y = Y0 + w - O;
+            const bool rowok = (y >= 0 && y < N);
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+                const int X = tid + k * T, x = X - O;
+                v[w][k] = make_float2(0.f, 0.f);
+                if ((P % T == 0 || X < P) && rowok && x >= 0 && x < N) {
+                    const size_t idx = (size_t(f) * N + y) * N + x;
+                    if constexpr (IS_CPLX) v[w][k] = reinterpret_cast<const float2*>(in)[idx];
+                    else v[w][k].x = float(reinterpret_cast<const int8_t*>(in)[idx]);
+                }
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < TILE_W; ++w)
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+                const int X = tid + k * T;
+                if (P % T == 0 || X < P) s[w * SEQ + padded<SK>(X)] = v[w][k];
+            }
     }
     __syncthreads();
-    tile_fft<P, Q, TILE_WP, false>(s + (tid % TILE_W), tid / TILE_W, tw);
+    tile_fft<P, Q, 1, SK, false>(s + (tid / Q) * SEQ, tid % Q, tw);
+    constexpr int NXS = (P + T - 1) / T;
 #pragma unroll
     for (int w = 0; w < TILE_W; ++w)
-        for (int X = tid; X < P; X += T) out[size_t(Y0 + w) * P + X] = s[X * TILE_WP + w];
+#pragma unroll
+        for (int k = 0; k < NXS; ++k) {
+            const int X = tid + k * T;
+            if (P % T == 0 || X < P) out[size_t(Y0 + w) * P + X] = s[w * SEQ + padded<SK>(X)];
+        }
 }
 
 // ---------------------------------------------------------------------------
 // pass B: for W canvas columns: FFT along y, multiply by H, inverse FFT along y.
 // In place on buf.  H is pre-scaled by 1/P^2 so no later normalisation.
+// Column layout: thread (w = tid % WC, q = tid / WC), WC = 16 or 8 columns per tile; H
+// points at the colour group of the frames of this launch.
 // ---------------------------------------------------------------------------
 template <int P, int PAD>
-__global__ void __launch_bounds__(FftCfg<P>::T)
-k_cols(float2* __restrict__ buf, const float2* __restrict__ H, const float2* __restrict__ tw,
-       int Fg) {
-    constexpr int N = P / PAD, O = (P - N) / 2, T = FftCfg<P>::T, Q = FftCfg<P>::Q;
+__global__ void __launch_bounds__(FftCfg<P>::TC, FftCfg<P>::MINBC)
+k_cols(float2* __restrict__ buf, const float2* __restrict__ H, const float2* __restrict__ tw) {
+    using C = FftCfg<P>;
+    constexpr int N = P / PAD, O = (P - N) / 2, Q = C::Q, SK = C::SKC, TILE_W = C::WC;
     extern __shared__ float2 s[];
     const int tid = threadIdx.x, f = blockIdx.y, X0 = blockIdx.x * TILE_W;
     float2* b = buf + size_t(f) * P * P + X0;
-    const float2* Hg = H + size_t(f / Fg) * P * P + X0;
+    const float2* Hg = H + X0;
     const int w = tid % TILE_W, q = tid / TILE_W;
-    for (int y = q; y < P; y += Q) {
-        float2 v = make_float2(0.f, 0.f);
-        if (PAD == 1 || (y >= O && y < O + N)) v = b[size_t(y) * P + w];
-        s[y * TILE_WP + w] = v;
+    constexpr int NY = (P + Q - 1) / Q;
+    {
+        float2 v[NY];
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+            const int y = q + k * Q;
+            v[k] = make_float2(0.f, 0.f);
+            if ((P % Q == 0 || y < P) && (PAD == 1 || (y >= O && y < O + N))) v[k] = b[size_t(y) * P + w];
+        }
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+            const int y = q + k * Q;
+            if (P % Q == 0 || y < P) s[padded<SK>(y) * TILE_W + w] = v[k];
+        }
     }
     __syncthreads();
-    tile_fft<P, Q, TILE_WP, false>(s + w, q, tw);
-    for (int y = q; y < P; y += Q)
-        s[y * TILE_WP + w] = cmul(s[y * TILE_WP + w], __ldg(Hg + size_t(y) * P + w));
+    tile_fft<P, Q, TILE_W, SK, false>(s + w, q, tw);
+    {
+        float2 hv[NY];
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+            const int y = q + k * Q;
+            if (P % Q == 0 || y < P) hv[k] = __ldg(Hg + size_t(y) * P + w);
+        }
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+            const int y = q + k * Q;
+            if (P % Q == 0 || y < P) {
+                float2* e = s + padded<SK>(y) * TILE_W + w;
+                *e = cmul(*e, hv[k]);
+            }
+        }
+    }
     __syncthreads();
-    tile_fft<P, Q, TILE_WP, true>(s + w, q, tw);
-    for (int y = q; y < P; y += Q)
-        if (PAD == 1 || (y >= O && y < O + N)) b[size_t(y) * P + w] = s[y * TILE_WP + w];
+    tile_fft<P, Q, TILE_W, SK, true>(s + w, q, tw);
+#pragma unroll
+    for (int k = 0; k < NY; ++k) {
+        const int y = q + k * Q;
+        if ((P % Q == 0 || y < P) && (PAD == 1 || (y >= O && y < O + N)))
+            b[size_t(y) * P + w] = s[padded<SK>(y) * TILE_W + w];
+    }
 }
 
 // ---------------------------------------------------------------------------
-// pass C: inverse FFT along x of W window rows for every frame of one colour
-// group; writes the field U and the frame-averaged intensity I.
-// grid (N / W, groups).  buf may alias U when PAD == 1 (in place).
-// WRITE_I = false gives the bare tt.simulate operator.
+// pass C: inverse FFT along x of W window rows of one frame; writes the field U
+// (cropped to the N x N window).  grid (N / W, frames).  buf may alias U when
+// PAD == 1 (in place).  This alone is the tail of the tt.simulate operator.
 // ---------------------------------------------------------------------------
-template <int P, int PAD, bool WRITE_I>
-__global__ void __launch_bounds__(FftCfg<P>::T)
-k_rows_inv(const float2* buf, float2* U, float* __restrict__ I,
-           const float2* __restrict__ tw, int Fg) {
-    constexpr int N = P / PAD, O = (P - N) / 2, T = FftCfg<P>::T, Q = FftCfg<P>::Q;
-    constexpr int NX = (N + T - 1) / T;
+template <int P, int PAD>
+__global__ void __launch_bounds__(FftCfg<P>::T, FftCfg<P>::MINB)
+k_rows_inv(const float2* buf, float2* U, const float2* __restrict__ tw) {
+    using C = FftCfg<P>;
+    constexpr int N = P / PAD, O = (P - N) / 2, T = C::T, Q = C::Q, SK = C::SKR, SEQ = C::SEQ;
     extern __shared__ float2 s[];
-    const int tid = threadIdx.x, g = blockIdx.y, y0 = blockIdx.x * TILE_W;
-    float acc[TILE_W][NX];
+    const int tid = threadIdx.x, f = blockIdx.y, y0 = blockIdx.x * TILE_W;
+    const float2* src = buf + size_t(f) * P * P + size_t(y0 + O) * P;
+    float2* dst = U + size_t(f) * N * N + size_t(y0) * N;
+    constexpr int NX = (P + T - 1) / T;
+    {
+        float2 v[TILE_W][NX];
+#pragma unroll
+        for (int w = 0; w < TILE_W; ++w)
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+                const int X = tid + k * T;
+                if (P % T == 0 || X < P) v[w][k] = src[size_t(w) * P + X];
+            }
+#pragma unroll
+        for (int w = 0; w < TILE_W; ++w)
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+                const int X = tid + k * T;
+                if (P % T == 0 || X < P) s[w * SEQ + padded<SK>(X)] = v[w][k];
+            }
+    }
+    __syncthreads();
+    tile_fft<P, Q, 1, SK, true>(s + (tid / Q) * SEQ, tid % Q, tw);
+    constexpr int NXO = (N + T - 1) / T;
 #pragma unroll
     for (int w = 0; w < TILE_W; ++w)
 #pragma unroll
-        for (int i = 0; i < NX; ++i) acc[w][i] = 0.f;
-    for (int fi = 0; fi < Fg; ++fi) {
-        const int f = g * Fg + fi;
-        const float2* src = buf + size_t(f) * P * P + size_t(y0 + O) * P;
-        float2* dst = U + size_t(f) * N * N + size_t(y0) * N;
-#pragma unroll
-        for (int w = 0; w < TILE_W; ++w)
-            for (int X = tid; X < P; X += T) s[X * TILE_WP + w] = src[size_t(w) * P + X];
-        __syncthreads();
-        tile_fft<P, Q, TILE_WP, true>(s + (tid % TILE_W), tid / TILE_W, tw);
-#pragma unroll
-        for (int w = 0; w < TILE_W; ++w)
-#pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                const int x = tid + i * T;
-                if (N % T == 0 || x < N) {
-                    const float2 v = s[(x + O) * TILE_WP + w];
-                    dst[size_t(w) * N + x] = v;
-                    acc[w][i] = fmaf(v.x, v.x, fmaf(v.y, v.y, acc[w][i]));
-                }
-            }
-        __syncthreads();
-    }
-    if (WRITE_I) {
-        const float inv = 1.f / float(Fg);
-        float* Ig = I + size_t(g) * N * N + size_t(y0) * N;
-#pragma unroll
-        for (int w = 0; w < TILE_W; ++w)
-#pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                const int x = tid + i * T;
-                if (N % T == 0 || x < N) Ig[size_t(w) * N + x] = acc[w][i] * inv;
-            }
-    }
+        for (int k = 0; k < NXO; ++k) {
+            const int x = tid + k * T;
+            if (N % T == 0 || x < N) dst[size_t(w) * N + x] = s[w * SEQ + padded<SK>(x + O)];
+        }
 }
 
 // ---------------------------------------------------------------------------
-// deterministic block reduction of two doubles (fixed shuffle/tree order)
+// deterministic block reduction helpers (fixed shuffle/tree order)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -176,24 +251,36 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// sum I^2, sum I*T, sum T^2 of one environment -> sums[0..2], PSNR -> sums[3].
-// grid = LOSS_BLOCKS CTAs of 256; the last CTA to finish folds the partials in
-// index order, so the result does not depend on scheduling.
-constexpr int LOSS_BLOCKS = 128;
+// ---------------------------------------------------------------------------
+// k_intensity: I_g = mean_f |U_f|^2 over the Fg frames of one colour group
+// (.abs()**2 + torch.mean(dim=1), env.py:172-173) fused with the partial sums of
+// tt.relativeLoss: sum I^2, sum I*T, sum T^2 in float64.  The field planes were
+// just written by k_rows_inv, so they mostly stream from L2.  One fixed-size
+// grid; partial[(g * gridDim.x + b) * 3 ..] is folded by k_loss_final in index
+// order, so the result does not depend on scheduling.
+// ---------------------------------------------------------------------------
+constexpr int LOSS_BLOCKS = 296;
 __global__ void __launch_bounds__(256)
-k_loss_sums(const float* __restrict__ I, const float* __restrict__ T, size_t n,
-            double* __restrict__ partial /*[LOSS_BLOCKS][3]*/, unsigned* ticket,
-            double* __restrict__ sums /*[4]*/, int relative) {
+k_intensity(const float2* __restrict__ U /* group base [Fg][n2] */, float* __restrict__ I,
+            const float* __restrict__ T, size_t n2, int Fg, double* __restrict__ partial) {
     __shared__ double sh[3][8];
-    __shared__ bool last;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const size_t n4 = n / 4;
-    const size_t per = (n4 + gridDim.x - 1) / gridDim.x;
-    const size_t beg = blockIdx.x * per, end = (beg + per < n4) ? beg + per : n4;
+    const size_t nq = n2 / 4;
+    const float inv = 1.f / float(Fg);
     double a = 0, b = 0, c = 0;
-    for (size_t i = beg + tid; i < end; i += 256) {
-        const float4 iv = __ldg(reinterpret_cast<const float4*>(I) + i);
-        const float4 tv = __ldg(reinterpret_cast<const float4*>(T) + i);
+    for (size_t q = size_t(blockIdx.x) * 256 + tid; q < nq; q += size_t(gridDim.x) * 256) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int f = 0; f < Fg; ++f) {
+            const float4* up = reinterpret_cast<const float4*>(U + size_t(f) * n2) + 2 * q;
+            const float4 u0 = up[0], u1 = up[1];
+            acc.x = fmaf(u0.x, u0.x, fmaf(u0.y, u0.y, acc.x));
+            acc.y = fmaf(u0.z, u0.z, fmaf(u0.w, u0.w, acc.y));
+            acc.z = fmaf(u1.x, u1.x, fmaf(u1.y, u1.y, acc.z));
+            acc.w = fmaf(u1.z, u1.z, fmaf(u1.w, u1.w, acc.w));
+        }
+        const float4 iv = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+        reinterpret_cast<float4*>(I)[q] = iv;
+        const float4 tv = __ldg(reinterpret_cast<const float4*>(T) + q);
         a += double(iv.x) * iv.x + double(iv.y) * iv.y + double(iv.z) * iv.z + double(iv.w) * iv.w;
         b += double(iv.x) * tv.x + double(iv.y) * tv.y + double(iv.z) * tv.z + double(iv.w) * tv.w;
         c += double(tv.x) * tv.x + double(tv.y) * tv.y + double(tv.z) * tv.z + double(tv.w) * tv.w;
@@ -207,23 +294,20 @@ k_loss_sums(const float* __restrict__ I, const float* __restrict__ T, size_t n,
         partial[blockIdx.x * 3 + 0] = x;
         partial[blockIdx.x * 3 + 1] = y;
         partial[blockIdx.x * 3 + 2] = z;
-        __threadfence();
-        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
-    __syncthreads();
-    if (last && tid == 0) {
-        __threadfence();
-        double x = 0, y = 0, z = 0;
-        for (unsigned i = 0; i < gridDim.x; ++i) {
-            x += __ldcg(partial + i * 3 + 0);
-            y += __ldcg(partial + i * 3 + 1);
-            z += __ldcg(partial + i * 3 + 2);
-        }
-        const double mse = relative ? (z - y * y / x) / double(n) : (x - 2.0 * y + z) / double(n);
-        sums[0] = x; sums[1] = y; sums[2] = z;
-        sums[3] = -10.0 * log10(mse);
-        *ticket = 0;
+}
+
+// fold the G * LOSS_BLOCKS partials in index order -> sums[0..2], PSNR -> sums[3]
+__global__ void k_loss_final(const double* __restrict__ partial, int n_partial, double n_elems,
+                             double* __restrict__ sums, int relative) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double x = 0, y = 0, z = 0;
+    for (int i = 0; i < n_partial; ++i) {
+        x += partial[i * 3 + 0]; y += partial[i * 3 + 1]; z += partial[i * 3 + 2];
     }
+    const double mse = relative ? (z - y * y / x) / n_elems : (x - 2.0 * y + z) / n_elems;
+    sums[0] = x; sums[1] = y; sums[2] = z;
+    sums[3] = -10.0 * log10(mse);
 }
 
 // ---------------------------------------------------------------------------

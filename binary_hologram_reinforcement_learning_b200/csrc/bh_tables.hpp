@@ -139,12 +139,39 @@ inline std::shared_ptr<HostTables> get_tables(int P, double wl, double dx, doubl
     return t;
 }
 
+// radix plan of an FFT side; must mirror Plan<N> in bh_fft.cuh (tests/native/host_check.cu
+// runs both against each other)
+inline std::vector<int> plan_radices(int P) {
+    switch (P) {
+        case 32: return {8, 4};
+        case 64: return {8, 8};
+        case 128: return {16, 8};
+        case 256: return {16, 16};
+        case 512: return {8, 8, 8};
+        case 896: return {16, 8, 7};
+        case 1024: return {16, 16, 4};
+        case 1792: return {16, 16, 7};
+        case 2048: return {16, 16, 8};
+    }
+    return {};
+}
+
+// Per-pass twiddle blocks (TwLayout in bh_fft.cuh): for pass p >= 1 with radix R and
+// Ns = product of the earlier radices, tw[off_p + (r-1)*Ns + k] = exp(-2 pi i r k / (Ns R)).
 inline std::vector<float> build_twiddles(int P) {
-    std::vector<float> tw(size_t(P) * 2);
+    const std::vector<int> rad = plan_radices(P);
+    std::vector<float> tw;
     const double two_pi = 6.283185307179586476925286766559;
-    for (int i = 0; i < P; ++i) {
-        tw[2 * i] = float(std::cos(two_pi * i / P));
-        tw[2 * i + 1] = float(-std::sin(two_pi * i / P));
+    int Ns = rad.empty() ? 1 : rad[0];
+    for (size_t p = 1; p < rad.size(); ++p) {
+        const int R = rad[p];
+        for (int r = 1; r < R; ++r)
+            for (int k = 0; k < Ns; ++k) {
+                const double ph = two_pi * double(r) * double(k) / (double(Ns) * double(R));
+                tw.push_back(float(std::cos(ph)));
+                tw.push_back(float(-std::sin(ph)));
+            }
+        Ns *= R;
     }
     return tw;
 }

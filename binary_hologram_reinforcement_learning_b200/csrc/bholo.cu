@@ -87,36 +87,41 @@ extern "C" const char* bh_last_error(const bh_ctx* ctx) {
 // ---------------------------------------------------------------------------
 // propagation dispatch over the supported FFT sides
 // ---------------------------------------------------------------------------
+// The three FFT passes over `frames` consecutive planes (one colour group, or the C planes
+// of the stand-alone operator).  Launching group by group keeps the 8 MB-per-frame
+// intermediate of pass A / pass B resident in the 126 MB L2 between passes.
 template <int P, int PAD, typename InT, bool CPLX>
-static cudaError_t launch_prop(const InT* in, float2* buf, float2* U, float* I, const float2* H,
-                               const float2* tw, int frames, int groups, int Fg, bool write_I,
-                               cudaStream_t st) {
+static cudaError_t launch_prop(const InT* in, float2* buf, float2* U, const float2* H,
+                               const float2* tw, int frames, int Fg, cudaStream_t st,
+                               cudaEvent_t* ev = nullptr) {
     constexpr int N = P / PAD;
     constexpr int T = FftCfg<P>::T;
-    const size_t smem = FftCfg<P>::smem;
+    const size_t smr = FftCfg<P>::smem_row, smc = FftCfg<P>::smem_col;
     auto kA = k_rows_fwd<P, PAD, InT, CPLX>;
     auto kB = k_cols<P, PAD>;
-    auto kC1 = k_rows_inv<P, PAD, true>;
-    auto kC0 = k_rows_inv<P, PAD, false>;
+    auto kC = k_rows_inv<P, PAD>;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return e;
-    if ((e = cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return e;
-    if ((e = cudaFuncSetAttribute(kC1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return e;
-    if ((e = cudaFuncSetAttribute(kC0, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return e;
-    kA<<<dim3(P / TILE_W, frames), T, smem, st>>>(in, buf, tw);
-    kB<<<dim3(P / TILE_W, frames), T, smem, st>>>(buf, H, tw, Fg);
-    if (write_I) kC1<<<dim3(N / TILE_W, groups), T, smem, st>>>(buf, U, I, tw, Fg);
-    else kC0<<<dim3(N / TILE_W, groups), T, smem, st>>>(buf, U, I, tw, Fg);
+    if ((e = cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smr)))) return e;
+    if ((e = cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smc)))) return e;
+    if ((e = cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smr)))) return e;
+    (void)Fg;
+    if (ev) cudaEventRecord(ev[0], st);
+    kA<<<dim3(P / TILE_W, frames), T, smr, st>>>(in, buf, tw);
+    if (ev) cudaEventRecord(ev[1], st);
+    kB<<<dim3(P / FftCfg<P>::WC, frames), FftCfg<P>::TC, smc, st>>>(buf, H, tw);
+    if (ev) cudaEventRecord(ev[2], st);
+    kC<<<dim3(N / TILE_W, frames), T, smr, st>>>(buf, U, tw);
+    if (ev) cudaEventRecord(ev[3], st);
     return cudaGetLastError();
 }
 
 template <typename InT, bool CPLX>
-static cudaError_t dispatch_prop(int P, int pad, const InT* in, float2* buf, float2* U, float* I,
-                                 const float2* H, const float2* tw, int frames, int groups, int Fg,
-                                 bool write_I, cudaStream_t st, bool* supported) {
+static cudaError_t dispatch_prop(int P, int pad, const InT* in, float2* buf, float2* U,
+                                 const float2* H, const float2* tw, int frames, int Fg,
+                                 cudaStream_t st, bool* supported, cudaEvent_t* ev = nullptr) {
     *supported = true;
 #define BH_CASE(PP, PD) \
-    if (P == PP && pad == PD) return launch_prop<PP, PD, InT, CPLX>(in, buf, U, I, H, tw, frames, groups, Fg, write_I, st);
+    if (P == PP && pad == PD) return launch_prop<PP, PD, InT, CPLX>(in, buf, U, H, tw, frames, Fg, st, ev);
     BH_CASE(32, 1) BH_CASE(64, 1) BH_CASE(128, 1) BH_CASE(256, 1) BH_CASE(512, 1)
     BH_CASE(896, 1) BH_CASE(1024, 1)
     BH_CASE(64, 2) BH_CASE(128, 2) BH_CASE(256, 2) BH_CASE(512, 2) BH_CASE(1792, 2) BH_CASE(2048, 2)
@@ -133,22 +138,41 @@ static bool fft_side_supported(int P, int pad) {
     return false;
 }
 
-static int propagate_env(bh_ctx* c, int env) {
-    const size_t n2 = c->n2;
-    const int8_t* st = c->dstate + size_t(env) * c->F * n2;
-    float2* U = c->dU + size_t(env) * c->F * n2;
-    float* I = c->dI + size_t(env) * c->G * n2;
-    const float* T = c->dT + size_t(env) * c->G * n2;
-    float2* buf = (c->pad == 1) ? U : c->dscratch;
-    bool ok = false;
-    BH_CUDA(c, (dispatch_prop<int8_t, false>(c->P, c->pad, st, buf, U, I, c->dH, c->dtw, c->F, c->G,
-                                             c->Fg, true, c->stream, &ok)));
-    if (!ok) BH_FAIL(c, -4, "unsupported FFT side P=%d pad=%d", c->P, c->pad);
-    k_loss_sums<<<LOSS_BLOCKS, 256, 0, c->stream>>>(I, T, size_t(c->G) * n2, c->dloss_partial,
-                                                    c->dloss_ticket, c->dsums + size_t(env) * 4,
-                                                    c->relative);
+static int propagate_env(bh_ctx* c, int env, float* pass_ms = nullptr) {
+    const size_t n2 = c->n2, p2 = size_t(c->P) * c->P;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (pass_ms)
+        for (auto& e : ev) BH_CUDA(c, cudaEventCreate(&e));
+    for (int g = 0; g < c->G; ++g) {
+        const int f0 = g * c->Fg;
+        const int8_t* st = c->dstate + (size_t(env) * c->F + f0) * n2;
+        float2* U = c->dU + (size_t(env) * c->F + f0) * n2;
+        float* I = c->dI + (size_t(env) * c->G + g) * n2;
+        const float* T = c->dT + (size_t(env) * c->G + g) * n2;
+        float2* buf = (c->pad == 1) ? U : c->dscratch;
+        bool ok = false;
+        BH_CUDA(c, (dispatch_prop<int8_t, false>(c->P, c->pad, st, buf, U, c->dH + size_t(g) * p2, c->dtw,
+                                                 c->Fg, c->Fg, c->stream, &ok, pass_ms ? ev : nullptr)));
+        if (!ok) BH_FAIL(c, -4, "unsupported FFT side P=%d pad=%d", c->P, c->pad);
+        k_intensity<<<LOSS_BLOCKS, 256, 0, c->stream>>>(U, I, T, n2, c->Fg,
+                                                        c->dloss_partial + size_t(g) * LOSS_BLOCKS * 3);
+        c->launches += 4;
+        if (pass_ms) {
+            BH_CUDA(c, cudaEventRecord(ev[4], c->stream));
+            BH_CUDA(c, cudaEventSynchronize(ev[4]));
+            for (int i = 0; i < 4; ++i) {
+                float ms = 0.f;
+                BH_CUDA(c, cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+                pass_ms[i] += ms;
+            }
+        }
+    }
+    if (pass_ms)
+        for (auto& e : ev) cudaEventDestroy(e);
+    k_loss_final<<<1, 32, 0, c->stream>>>(c->dloss_partial, c->G * LOSS_BLOCKS, double(c->G) * double(n2),
+                                          c->dsums + size_t(env) * 4, c->relative);
     BH_CUDA(c, cudaGetLastError());
-    c->launches += 4;
+    c->launches += 1;
     return 0;
 }
 
@@ -211,15 +235,15 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
     } while (0)
     BH_TRY(cudaMalloc(&c->dH, size_t(G) * p2 * sizeof(float2)));
     BH_TRY(cudaMalloc(&c->dh, size_t(G) * p2 * sizeof(float2)));
-    BH_TRY(cudaMalloc(&c->dtw, size_t(c->P) * sizeof(float2)));
+    BH_TRY(cudaMalloc(&c->dtw, (build_twiddles(c->P).size() / 2 + 1) * sizeof(float2)));
     BH_TRY(cudaMalloc(&c->dU, size_t(n_env) * F * n2 * sizeof(float2)));
-    if (pad == 2) BH_TRY(cudaMalloc(&c->dscratch, size_t(F) * p2 * sizeof(float2)));
+    if (pad == 2) BH_TRY(cudaMalloc(&c->dscratch, size_t(c->Fg) * p2 * sizeof(float2)));
     BH_TRY(cudaMalloc(&c->dI, size_t(n_env) * G * n2 * sizeof(float)));
     BH_TRY(cudaMalloc(&c->dT, size_t(n_env) * G * n2 * sizeof(float)));
     BH_TRY(cudaMalloc(&c->drecon, size_t(G) * n2 * sizeof(float)));
     BH_TRY(cudaMalloc(&c->dstate, size_t(n_env) * F * n2));
     BH_TRY(cudaMalloc(&c->dsums, size_t(n_env) * 4 * sizeof(double)));
-    BH_TRY(cudaMalloc(&c->dloss_partial, LOSS_BLOCKS * 3 * sizeof(double)));
+    BH_TRY(cudaMalloc(&c->dloss_partial, size_t(G) * LOSS_BLOCKS * 3 * sizeof(double)));
     BH_TRY(cudaMalloc(&c->dloss_ticket, sizeof(unsigned)));
     c->units_per_task = int(n2 / UNIT_PX);
     c->max_tasks = std::max(4096, n_env);
@@ -253,7 +277,7 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
             BH_TRY(cudaMemcpy(c->dh + size_t(g) * p2, t->h.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
         }
         auto tw = build_twiddles(c->P);
-        BH_TRY(cudaMemcpy(c->dtw, tw.data(), size_t(c->P) * sizeof(float2), cudaMemcpyHostToDevice));
+        BH_TRY(cudaMemcpy(c->dtw, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice));
         int nb = 0;
         BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eval, 256, 0));
         c->grid_cap = std::max(1, nb) * prop.multiProcessorCount;
@@ -657,10 +681,10 @@ extern "C" int bh_simulate(int device, void* stream_, const float* in, int is_co
     auto t = get_tables(P, wl, dx, z, method);
     auto tw = build_twiddles(P);
     BH_SIM(cudaMalloc(&dH, p2 * sizeof(float2)));
-    BH_SIM(cudaMalloc(&dtw, size_t(P) * sizeof(float2)));
+    BH_SIM(cudaMalloc(&dtw, (tw.size() / 2 + 1) * sizeof(float2)));
     BH_SIM(cudaMalloc(&din, cnt * sizeof(float2)));
     BH_SIM(cudaMemcpyAsync(dH, t->H.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice, st));
-    BH_SIM(cudaMemcpyAsync(dtw, tw.data(), size_t(P) * sizeof(float2), cudaMemcpyHostToDevice, st));
+    BH_SIM(cudaMemcpyAsync(dtw, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     const cudaMemcpyKind kin = on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     if (is_complex) {
         BH_SIM(cudaMemcpyAsync(din, in, cnt * sizeof(float2), kin, st));
@@ -674,7 +698,7 @@ extern "C" int bh_simulate(int device, void* stream_, const float* in, int is_co
     float2* buf = U;
     if (pad == 2) { BH_SIM(cudaMalloc(&dbuf, size_t(C) * p2 * sizeof(float2))); buf = dbuf; }
     bool ok = false;
-    BH_SIM((dispatch_prop<float2, true>(P, pad, din, buf, U, nullptr, dH, dtw, C, 1, C, false, st, &ok)));
+    BH_SIM((dispatch_prop<float2, true>(P, pad, din, buf, U, dH, dtw, C, C, st, &ok)));
     if (on_host) BH_SIM(cudaMemcpyAsync(out, dout, cnt * sizeof(float2), cudaMemcpyDeviceToHost, st));
     BH_SIM(cudaStreamSynchronize(st));
 #undef BH_SIM
@@ -702,6 +726,17 @@ extern "C" int bh_time_eval(bh_ctx* c, int n, const int32_t* d_env_ids, const in
     float ms = 0.f;
     BH_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     *ms_per_launch = ms / float(reps);
+    return 0;
+}
+
+extern "C" int bh_time_propagate_passes(bh_ctx* c, int env, int reps, float* ms4) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    if (reps < 1 || !ms4) BH_FAIL(c, -1, "bad arguments");
+    if (int rc = propagate_env(c, env)) return rc;
+    for (int i = 0; i < 4; ++i) ms4[i] = 0.f;
+    for (int i = 0; i < reps; ++i)
+        if (int rc = propagate_env(c, env, ms4)) return rc;
+    for (int i = 0; i < 4; ++i) ms4[i] /= float(reps);
     return 0;
 }
 

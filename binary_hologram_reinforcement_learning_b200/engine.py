@@ -22,7 +22,7 @@ ABI_SYMBOLS = (
     "bh_set_target", "bh_load_state", "bh_resync", "bh_get_metrics", "bh_eval_flips",
     "bh_step_batch", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
     "bh_commit_flip", "bh_dbs_run", "bh_get_recon", "bh_get_state", "bh_get_field",
-    "bh_device_ptr", "bh_simulate", "bh_time_eval", "bh_time_propagate", "bh_launch_count",
+    "bh_device_ptr", "bh_simulate", "bh_time_eval", "bh_time_propagate", "bh_time_propagate_passes", "bh_launch_count",
 )
 
 
@@ -85,6 +85,7 @@ def load_library(build_if_missing: bool = True):
         "bh_simulate": (i32, [i32, vp, vp, i32, i32, i32, dbl, dbl, dbl, i32, i32, vp, i32]),
         "bh_time_eval": (i32, [vp, i32, vp, vp, i32, i32, P(C.c_float)]),
         "bh_time_propagate": (i32, [vp, i32, i32, P(C.c_float)]),
+        "bh_time_propagate_passes": (i32, [vp, i32, i32, P(C.c_float)]),
         "bh_launch_count": (i64, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -250,6 +251,11 @@ class HoloEngine:
                                           C.c_void_p(d_actions), n_sets, reps, C.byref(ms)),
                     "bh_time_eval")
         return float(ms.value)
+
+    def time_propagate_passes(self, env: int, reps: int):
+        ms = (C.c_float * 4)()
+        self._check(self.lib.bh_time_propagate_passes(self._h, env, reps, ms), "bh_time_propagate_passes")
+        return [float(x) for x in ms]
 
     def time_propagate(self, env: int, reps: int) -> float:
         ms = C.c_float(0.0)

@@ -138,6 +138,9 @@ int bh_simulate(int device, void* cuda_stream, const float* in, int is_complex, 
 int bh_time_eval(bh_ctx* ctx, int n, const int32_t* d_env_ids, const int64_t* d_actions,
                  int n_sets, int reps, float* ms_per_launch);
 int bh_time_propagate(bh_ctx* ctx, int env, int reps, float* ms_per_launch);
+/* Per-pass split of one propagation (summed over the colour groups), ms4 =
+ * {row FFT, column FFT * H * inverse column FFT, inverse row FFT, intensity + loss sums}. */
+int bh_time_propagate_passes(bh_ctx* ctx, int env, int reps, float* ms4);
 /* Kernels launched by this context since creation (for "gpu_launches"). */
 int64_t bh_launch_count(const bh_ctx* ctx);
 

@@ -14,52 +14,63 @@
 
 using namespace bh;
 
-template <int N, int Q, int WP, bool INV, int R, int Ns>
-static void host_pass(std::vector<float2>& s, int w, const float2* tw) {
+template <int N, int Q, int ES, int SK, bool INV, int R, int Ns>
+static void host_pass(std::vector<float2>& s, int base, const float2* twp) {
     constexpr int NB = PassShape<N, R, Ns, Q>::NB;
     std::vector<float2> regs(size_t(Q) * NB * R);
     for (int q = 0; q < Q; ++q) {
         float2 v[NB][R];
         for (int b = 0; b < NB; ++b) for (int r = 0; r < R; ++r) v[b][r] = make_float2(0, 0);
-        pass_read<N, R, Ns, Q, WP, INV>(s.data() + w, q, tw, v);
+        pass_read<N, R, Ns, Q, ES, SK, INV>(s.data() + base, q, twp, v);
         for (int b = 0; b < NB; ++b) for (int r = 0; r < R; ++r) regs[(size_t(q) * NB + b) * R + r] = v[b][r];
     }
     for (int q = 0; q < Q; ++q) {
         float2 v[NB][R];
         for (int b = 0; b < NB; ++b) for (int r = 0; r < R; ++r) v[b][r] = regs[(size_t(q) * NB + b) * R + r];
-        pass_write<N, R, Ns, Q, WP>(s.data() + w, q, v);
+        pass_write<N, R, Ns, Q, ES, SK>(s.data() + base, q, v);
     }
 }
 
-template <int N, int Q, int WP, bool INV>
-static void host_tile_fft(std::vector<float2>& s, int w, const float2* tw) {
+template <int N, int Q, int ES, int SK, bool INV>
+static void host_tile_fft(std::vector<float2>& s, int base, const float2* tw) {
     using P = Plan<N>;
+    using L = TwLayout<N>;
     constexpr int R0 = P::r[0], R1 = P::r[1], R2 = P::r[2];
-    host_pass<N, Q, WP, INV, R0, 1>(s, w, tw);
-    host_pass<N, Q, WP, INV, R1, R0>(s, w, tw);
-    if constexpr (P::n == 3) host_pass<N, Q, WP, INV, R2, R0 * R1>(s, w, tw);
+    host_pass<N, Q, ES, SK, INV, R0, 1>(s, base, tw);
+    host_pass<N, Q, ES, SK, INV, R1, R0>(s, base, tw + L::off1);
+    if constexpr (P::n == 3) host_pass<N, Q, ES, SK, INV, R2, R0 * R1>(s, base, tw + L::off2);
 }
 
-template <int N, int Q>
-static double check_size() {
-    constexpr int W = 8, WP = 9;
+constexpr int ilog2_h(int v) { return v <= 1 ? 0 : 1 + ilog2_h(v >> 1); }
+
+// COL = false: row layout (ES = 1, base = w * SEQ, skew 4); COL = true: column layout
+// (ES = 8, base = w, skew log2(R0)) -- the two layouts of the CUDA passes
+template <int N, int Q, bool COL>
+static double check_layout() {
+    constexpr int W = 8;
+    constexpr int SK = COL ? ilog2_h(Plan<N>::r[0]) : 4;
+    constexpr int ES = COL ? W : 1;
+    constexpr int SEQ = SeqLen<N, SK>::value;
     std::vector<float> twf = build_twiddles(N);
+    if (int(twf.size()) != 2 * TwLayout<N>::total) { printf("twiddle table size mismatch N=%d\n", N); return 1.0; }
+    std::vector<int> rad = plan_radices(N);
+    if (int(rad.size()) != Plan<N>::n || rad[0] != Plan<N>::r[0] || rad[1] != Plan<N>::r[1] ||
+        (Plan<N>::n == 3 && rad[2] != Plan<N>::r[2])) { printf("plan mismatch N=%d\n", N); return 1.0; }
+    twf.push_back(0.f); twf.push_back(0.f);
     const float2* tw = reinterpret_cast<const float2*>(twf.data());
-    std::vector<float2> s(size_t(N) * WP);
-    std::vector<std::complex<double>> x(size_t(N) * W);
+    auto at = [&](int e, int w) { return COL ? padded<SK>(e) * W + w : w * SEQ + padded<SK>(e); };
+    std::vector<float2> s(size_t(SEQ) * W + 8, make_float2(0, 0));
     srand(N);
     for (int i = 0; i < N; ++i)
-        for (int w = 0; w < W; ++w) {
-            const double a = rand() / double(RAND_MAX) - 0.5, b = rand() / double(RAND_MAX) - 0.5;
-            x[size_t(i) * W + w] = {a, b};
-            s[size_t(i) * WP + w] = make_float2(float(a), float(b));
-        }
+        for (int w = 0; w < W; ++w)
+            s[at(i, w)] = make_float2(float(rand() / double(RAND_MAX) - 0.5), float(rand() / double(RAND_MAX) - 0.5));
     double worst = 0;
     for (int inv = 0; inv < 2; ++inv) {
         std::vector<float2> t = s;
         for (int w = 0; w < W; ++w) {
-            if (inv) host_tile_fft<N, Q, WP, true>(t, w, tw);
-            else host_tile_fft<N, Q, WP, false>(t, w, tw);
+            const int base = COL ? w : w * SEQ;
+            if (inv) host_tile_fft<N, Q, ES, SK, true>(t, base, tw);
+            else host_tile_fft<N, Q, ES, SK, false>(t, base, tw);
         }
         const double sg = inv ? 1.0 : -1.0;
         for (int w = 0; w < W; w += 3) {
@@ -68,19 +79,22 @@ static double check_size() {
                 std::complex<double> acc = 0;
                 for (int i = 0; i < N; ++i) {
                     const double ph = sg * 6.283185307179586 * double((long long)i * k % N) / N;
-                    acc += std::complex<double>(s[size_t(i) * WP + w].x, s[size_t(i) * WP + w].y) *
+                    acc += std::complex<double>(s[at(i, w)].x, s[at(i, w)].y) *
                            std::complex<double>(std::cos(ph), std::sin(ph));
                 }
-                const std::complex<double> got(t[size_t(k) * WP + w].x, t[size_t(k) * WP + w].y);
+                const std::complex<double> got(t[at(k, w)].x, t[at(k, w)].y);
                 err = std::max(err, std::abs(got - acc));
                 scale = std::max(scale, std::abs(acc));
             }
             worst = std::max(worst, err / scale);
         }
     }
-    printf("fft N=%d Q=%d rel_err=%.3e\n", N, Q, worst);
+    printf("fft N=%d Q=%d layout=%s rel_err=%.3e\n", N, Q, COL ? "col" : "row", worst);
     return worst;
 }
+
+template <int N, int Q>
+static double check_size() { return std::max(check_layout<N, Q, false>(), check_layout<N, Q, true>()); }
 
 static double check_tables(int P) {
     // h must be the inverse DFT of H*P^2 (H is stored pre-scaled by 1/P^2)
@@ -114,8 +128,8 @@ int main() {
     worst = std::max(worst, check_size<128, 32>());
     worst = std::max(worst, check_size<256, 32>());
     worst = std::max(worst, check_size<512, 32>());
-    worst = std::max(worst, check_size<896, 32>());
-    worst = std::max(worst, check_size<1024, 32>());
+    worst = std::max(worst, check_size<896, 64>());
+    worst = std::max(worst, check_size<1024, 64>());
     worst = std::max(worst, check_size<1792, 64>());
     worst = std::max(worst, check_size<2048, 64>());
     double tw = std::max(check_tables(64), check_tables(112));
