@@ -185,7 +185,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "env steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -305,6 +305,20 @@ def run_b200(args):
     sweep_s = time.perf_counter() - t0
     with torch.cuda.stream(stream):
         prop_ms = eng.time_propagate(0, 5)
+        prop_pass_ms = eng.time_propagate_passes(0, 3)
+    # exhaustive sweep of all 24*1024^2 candidates of env 0 by FFT correlation (device output)
+    d_map = torch.empty(n_pix, dtype=torch.float64, device=f"cuda:{local}")
+    eng.sweep_all_device(0, d_map.data_ptr())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eng.sweep_all_device(0, d_map.data_ptr())
+    torch.cuda.synchronize()
+    sweep_all_s = time.perf_counter() - t0
+    # greedy DBS (device loop, speculative batches) on env 1
+    order = rng.permutation(n_pix)[:20000]
+    t0 = time.perf_counter()
+    _, _, dbs_nacc, _ = eng.dbs_run(order, env=min(1, E - 1), k_spec=0, resync_every=0)
+    dbs_s = time.perf_counter() - t0
     prop_bytes = FRAMES * (N_SIDE ** 2 + 40.0 * N_SIDE ** 2) + 8.0 * GROUPS * N_SIDE ** 2
     clocks = sampler.stop(windows)
 
@@ -347,13 +361,18 @@ def run_b200(args):
             "extra": {
                 "flip_evals_per_s_kernel": E / (eval_ms / 1000.0) * world,
                 "flip_evals_per_s_sweep_api": n_cand / sweep_s * world,
+                "flip_evals_per_s_exhaustive_sweep_all": n_pix / sweep_all_s * world,
+                "sweep_all_ms_25M_candidates": sweep_all_s * 1e3,
+                "dbs_greedy_candidates_per_s": len(order) / dbs_s * world,
+                "dbs_greedy_accept_rate": dbs_nacc / len(order),
                 "propagate_ms_24_frames": prop_ms,
+                "propagate_pass_ms": prop_pass_ms,
                 "propagate_gbs_algorithmic": prop_bytes / (prop_ms / 1000.0) / 1e9,
                 "episode_stats_rows_gathered": int(all_stats.shape[0]),
                 "psnr_env0_initial": psnr0[0],
             },
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     vec.close()
     if world > 1:
         import torch.distributed as tdist
@@ -361,8 +380,28 @@ def run_b200(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route fd 1 to stderr so library banners (NCCL prints its version on stdout) cannot
+    precede the JSON line; emit() writes the line to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:

@@ -344,6 +344,8 @@ struct DeltaArgs {
     unsigned* tickets;             // [n_tasks]
     Result* results;               // [n_tasks]
     Result* results_host;          // optional mapped pinned mirror written by the finaliser
+    // speculative greedy DBS (k_commit does the selection): decision log, PSNR trace, counter
+    uint8_t* dbs_accepted; double* dbs_trace; long long* dbs_count; long long* dbs_cursor;
     // small batches (one env step of <= INLINE_MAX envs) carry their tasks in the
     // kernel parameters: no host-to-device copy on the step path
     int n_inline;
@@ -580,8 +582,33 @@ k_commit(const DeltaArgs a) {
     const int tid = threadIdx.x;
     if (tid == 0) {
         int n = 0;
-        for (int k = 0; k < a.n_tasks; ++k)
-            if (a.results[k].accept) s_list[n++] = k;
+        if (a.dbs_cursor) {
+            // speculative greedy DBS (DBS.py:247-294 order): all K candidates were scored against
+            // the same state; keep the first accepted one, the candidates after it are scored
+            // again by the next batch.  Block 0 logs the decisions and advances the cursor
+            // (idle slots carry accept = 0, so no other block needs the cursor).
+            int first = -1;
+            for (int k = 0; k < a.n_tasks; ++k)
+                if (a.results[k].accept) { first = k; break; }
+            if (first >= 0) s_list[n++] = first;
+            if (blockIdx.x == 0) {
+                const long long off = *a.dbs_cursor;
+                long long cnt = a.n_total - off;
+                if (cnt > a.n_tasks) cnt = a.n_tasks;
+                if (cnt > 0) {
+                    const int used = first >= 0 ? first + 1 : int(cnt);
+                    for (int k = 0; k < used; ++k) {
+                        a.dbs_accepted[off + k] = (k == first) ? 1 : 0;
+                        if (a.dbs_trace) a.dbs_trace[off + k] = a.results[k].psnr_after;
+                    }
+                    if (first >= 0) *a.dbs_count += 1;
+                    *a.dbs_cursor = off + used;
+                }
+            }
+        } else {
+            for (int k = 0; k < a.n_tasks; ++k)
+                if (a.results[k].accept) s_list[n++] = k;
+        }
         s_cnt = n;
     }
     __syncthreads();
@@ -655,29 +682,89 @@ k_recon_candidate(const float2* __restrict__ U, const float2* __restrict__ h,
     }
 }
 
-// speculative greedy DBS: among the K results of one batch (all evaluated
-// against the same state) keep the first accepted one, cancel the rest, log
-// the decisions and advance the cursor (DBS.py:247-294 order is preserved:
-// candidates after the first accept are re-evaluated by the next batch).
-__global__ void k_dbs_select(Result* results, int K, long long* offset_ptr, long long n_total,
-                             uint8_t* accepted_out, double* trace_out, long long* n_accepted) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const long long off = *offset_ptr;
-    long long cnt = n_total - off;
-    if (cnt <= 0) return;
-    if (cnt > K) cnt = K;
-    int first = -1;
-    for (int k = 0; k < cnt; ++k)
-        if (results[k].accept) { first = k; break; }
-    const int used = first >= 0 ? first + 1 : int(cnt);
-    for (int k = 0; k < used; ++k) {
-        accepted_out[off + k] = (k == first) ? 1 : 0;
-        if (trace_out) trace_out[off + k] = results[k].psnr_after;
+// ---------------------------------------------------------------------------
+// exhaustive sweep by correlation (score EVERY pixel of every frame against the
+// fixed state: dbs-1024-1024-24-6464.py:330-395, range.py:294-335).
+//
+// For a flip of pixel (r,c) of frame f (sign s), with h_s = h shifted to (r,c),
+//   a = Re(conj(U) h_s), m = |h_s|^2, dI = (2 s a + m)/Fg   and
+//   d sum(I T) = (2s/Fg) Re C1 + (1/Fg) BT
+//   d sum(I^2) = 2[(2s/Fg) Re C2 + (1/Fg) BI] + (1/Fg^2)[2 C4 + 2 Re C5 + 4 s Re C3 + sum|h|^4]
+// where every term is a circular cross-correlation with an EVEN kernel,
+//   C1 = (conj(U) T) * h      C2 = (conj(U) I) * h      C3 = conj(U) * (h|h|^2)
+//   C4 = |U|^2 * |h|^2        C5 = conj(U)^2 * h^2      BT + i BI = (T + i I) * |h|^2
+// i.e. ifft2(fft2(W) K) -- the propagation passes with a different spectrum K.
+// All N^2 candidates of a frame cost a handful of FFTs instead of N^2 delta passes.
+// ---------------------------------------------------------------------------
+enum { PREP_UA = 0, PREP_U = 1, PREP_U2 = 2, PREP_ABS2_PAIR = 3, PREP_TI = 4 };
+
+// grid (blocks, planes).  U: group base [Fg][n2]; A, B: real planes of the group.
+__global__ void __launch_bounds__(256)
+k_sweep_prep(const float2* __restrict__ U, const float* __restrict__ A, const float* __restrict__ B,
+             float2* __restrict__ out, size_t n2, int mode) {
+    const int pl = blockIdx.y;
+    float2* o = out + size_t(pl) * n2;
+    for (size_t p = size_t(blockIdx.x) * 256 + threadIdx.x; p < n2; p += size_t(gridDim.x) * 256) {
+        float2 v;
+        if (mode == PREP_UA) {
+            const float2 u = U[size_t(pl) * n2 + p]; const float a = A[p];
+            v = make_float2(u.x * a, -u.y * a);
+        } else if (mode == PREP_U) {
+            const float2 u = U[size_t(pl) * n2 + p];
+            v = make_float2(u.x, -u.y);
+        } else if (mode == PREP_U2) {
+            const float2 u = U[size_t(pl) * n2 + p];
+            v = make_float2(u.x * u.x - u.y * u.y, -2.f * u.x * u.y);
+        } else if (mode == PREP_ABS2_PAIR) {
+            const float2 u0 = U[size_t(2 * pl) * n2 + p], u1 = U[size_t(2 * pl + 1) * n2 + p];
+            v = make_float2(u0.x * u0.x + u0.y * u0.y, u1.x * u1.x + u1.y * u1.y);
+        } else {
+            v = make_float2(A[p], B[p]);
+        }
+        o[p] = v;
     }
-    for (int k = 0; k < K; ++k)
-        if (k != first) results[k].accept = 0;
-    if (first >= 0) *n_accepted += 1;
-    *offset_ptr = off + used;
+}
+
+enum { ACC_RE = 0, ACC_PAIR = 1, ACC_GROUP = 2 };
+
+// accumulate coef * part(S) into the per-candidate planes.
+//   ACC_RE    plane i -> frame i:   dst[i] += coef * (use_sign ? sgn : 1) * Re S[i]
+//   ACC_PAIR  plane i -> frames 2i (Re) and 2i+1 (Im) of dII
+//   ACC_GROUP plane 0 -> every frame: dIT += cT * Re S, dII += cI * Im S + cst
+__global__ void __launch_bounds__(256)
+k_sweep_acc(const float2* __restrict__ S, float* __restrict__ dIT, float* __restrict__ dII,
+            const int8_t* __restrict__ state /*group base*/, size_t n2, int Fg, int mode,
+            int to_ii, int use_sign, float coef, float coef2, float cst) {
+    const int pl = blockIdx.y;
+    for (size_t p = size_t(blockIdx.x) * 256 + threadIdx.x; p < n2; p += size_t(gridDim.x) * 256) {
+        if (mode == ACC_RE) {
+            float v = coef * S[size_t(pl) * n2 + p].x;
+            if (use_sign) v *= 1.f - 2.f * float(state[size_t(pl) * n2 + p]);
+            float* d = (to_ii ? dII : dIT) + size_t(pl) * n2 + p;
+            *d += v;
+        } else if (mode == ACC_PAIR) {
+            const float2 v = S[size_t(pl) * n2 + p];
+            dII[size_t(2 * pl) * n2 + p] += coef * v.x;
+            dII[size_t(2 * pl + 1) * n2 + p] += coef * v.y;
+        } else {
+            const float2 v = S[p];
+            dIT[size_t(pl) * n2 + p] += coef * v.x;
+            dII[size_t(pl) * n2 + p] += coef2 * v.y + cst;
+        }
+    }
+}
+
+// PSNR of every candidate of the group from the accumulated deltas (float64 closed form)
+__global__ void __launch_bounds__(256)
+k_sweep_final(const float* __restrict__ dIT, const float* __restrict__ dII,
+              const double* __restrict__ sums, double* __restrict__ out, size_t count,
+              double n_elems, int relative) {
+    const double sii0 = sums[0], sit0 = sums[1], stt = sums[2];
+    for (size_t p = size_t(blockIdx.x) * 256 + threadIdx.x; p < count; p += size_t(gridDim.x) * 256) {
+        const double sii = sii0 + double(dII[p]), sit = sit0 + double(dIT[p]);
+        const double mse = relative ? (stt - sit * sit / sii) / n_elems : (sii - 2.0 * sit + stt) / n_elems;
+        out[p] = -10.0 * log10(mse);
+    }
 }
 
 }  // namespace bh

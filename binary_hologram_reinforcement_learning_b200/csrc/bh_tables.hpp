@@ -139,6 +139,37 @@ inline std::shared_ptr<HostTables> get_tables(int P, double wl, double dx, doubl
     return t;
 }
 
+// Spectra of the even kernels of the correlation sweep, derived from the float impulse
+// response the delta kernel uses: K3 = fft2(h|h|^2), K4 = fft2(|h|^2), K5 = fft2(h^2),
+// each pre-scaled by 1/P^2 like H; m4 = sum |h|^4.
+struct SweepTables {
+    std::vector<float> K3, K4, K5;   // interleaved complex [P][P]
+    double m4 = 0.0;
+};
+
+inline std::shared_ptr<SweepTables> build_sweep_tables(const HostTables& t) {
+    const int P = t.P;
+    const size_t n = size_t(P) * P;
+    auto out = std::make_shared<SweepTables>();
+    std::vector<cd> k3(n), k4(n), k5(n);
+    double m4 = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        const cd h(double(t.h[2 * i]), double(t.h[2 * i + 1]));
+        const double a2 = std::norm(h);
+        k3[i] = h * a2; k4[i] = cd(a2, 0.0); k5[i] = h * h;
+        m4 += a2 * a2;
+    }
+    out->m4 = m4;
+    const double inv = 1.0 / (double(P) * double(P));
+    auto run = [&](std::vector<cd>& k, std::vector<float>& K) {
+        fft2_host(k, P, -1);
+        K.resize(2 * n);
+        for (size_t i = 0; i < n; ++i) { K[2 * i] = float(k[i].real() * inv); K[2 * i + 1] = float(k[i].imag() * inv); }
+    };
+    run(k3, out->K3); run(k4, out->K4); run(k5, out->K5);
+    return out;
+}
+
 // radix plan of an FFT side; must mirror Plan<N> in bh_fft.cuh (tests/native/host_check.cu
 // runs both against each other)
 inline std::vector<int> plan_radices(int P) {

@@ -41,6 +41,11 @@ struct bh_ctx {
     unsigned long long* d_acc = nullptr;
     unsigned* d_tickets = nullptr;
     long long* d_scalars = nullptr;      // [0] dbs cursor, [1] accepted count
+    // correlation sweep (allocated on first use)
+    float2 *dK3 = nullptr, *dK4 = nullptr, *dK5 = nullptr, *dsw_in = nullptr, *dsw_out = nullptr;
+    float *dsw_it = nullptr, *dsw_ii = nullptr;
+    double* dsw_psnr = nullptr;
+    std::vector<double> m4;
     int32_t* h_envs = nullptr;           // pinned staging
     long long* h_actions = nullptr;
     Result* h_results = nullptr;
@@ -188,6 +193,8 @@ extern "C" int bh_destroy(bh_ctx* c) {
     cudaFree(c->dloss_partial); cudaFree(c->dloss_ticket);
     cudaFree(c->d_envs); cudaFree(c->d_actions); cudaFree(c->d_results); cudaFree(c->d_acc);
     cudaFree(c->d_tickets); cudaFree(c->d_scalars);
+    cudaFree(c->dK3); cudaFree(c->dK4); cudaFree(c->dK5); cudaFree(c->dsw_in); cudaFree(c->dsw_out);
+    cudaFree(c->dsw_it); cudaFree(c->dsw_ii); cudaFree(c->dsw_psnr);
     cudaFreeHost(c->h_envs); cudaFreeHost(c->h_actions); cudaFreeHost(c->h_results);
     cudaFreeHost(c->h_scalars); cudaFreeHost(c->h_sums);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -363,6 +370,7 @@ static DeltaArgs make_args(bh_ctx* c, int n, int env_fixed, const int32_t* d_env
     a.unit_dy = UNIT_PX / c->N; a.unit_dx = UNIT_PX % c->N;
     a.acc = c->d_acc; a.tickets = c->d_tickets; a.results = d_results;
     a.results_host = nullptr; a.n_inline = 0;
+    a.dbs_accepted = nullptr; a.dbs_trace = nullptr; a.dbs_count = nullptr; a.dbs_cursor = nullptr;
     return a;
 }
 
@@ -563,11 +571,12 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
             DeltaArgs a = make_args(c, K, env, nullptr, d_order, RULE_DBS, c->d_results);
             a.offset_ptr = c->d_scalars;
             a.n_total = n;
+            DeltaArgs ac = a;                   // the commit kernel also selects and logs
+            ac.dbs_cursor = c->d_scalars; ac.dbs_count = c->d_scalars + 1;
+            ac.dbs_accepted = d_acc; ac.dbs_trace = d_trace;
             for (int it = 0; it < iters_per_sync; ++it) {
                 launch_eval(c, a);
-                k_dbs_select<<<1, 32, 0, c->stream>>>(c->d_results, K, c->d_scalars, n, d_acc, d_trace, c->d_scalars + 1);
-                launch_commit(c, a);
-                c->launches += 1;
+                launch_commit(c, ac);
             }
             BH_DBS(cudaGetLastError());
             BH_DBS(cudaMemcpyAsync(c->h_scalars, c->d_scalars, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
@@ -597,6 +606,95 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
 #undef BH_DBS
     cleanup();
     if (final_psnr) return bh_get_metrics(c, env, final_psnr, nullptr, nullptr);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// exhaustive sweep by correlation
+// ---------------------------------------------------------------------------
+static int sweep_setup(bh_ctx* c) {
+    if (c->dK3) return 0;
+    const size_t p2 = size_t(c->P) * c->P, n2 = c->n2;
+    BH_CUDA(c, cudaMalloc(&c->dK3, size_t(c->G) * p2 * sizeof(float2)));
+    BH_CUDA(c, cudaMalloc(&c->dK4, size_t(c->G) * p2 * sizeof(float2)));
+    BH_CUDA(c, cudaMalloc(&c->dK5, size_t(c->G) * p2 * sizeof(float2)));
+    BH_CUDA(c, cudaMalloc(&c->dsw_in, size_t(c->Fg) * n2 * sizeof(float2)));
+    BH_CUDA(c, cudaMalloc(&c->dsw_out, size_t(c->Fg) * n2 * sizeof(float2)));
+    BH_CUDA(c, cudaMalloc(&c->dsw_it, size_t(c->Fg) * n2 * sizeof(float)));
+    BH_CUDA(c, cudaMalloc(&c->dsw_ii, size_t(c->Fg) * n2 * sizeof(float)));
+    BH_CUDA(c, cudaMalloc(&c->dsw_psnr, size_t(c->Fg) * n2 * sizeof(double)));
+    c->m4.assign(c->G, 0.0);
+    for (int g = 0; g < c->G; ++g) {
+        auto t = get_tables(c->P, c->wl[g], c->dx, c->z, c->method);
+        auto sw = build_sweep_tables(*t);
+        c->m4[g] = sw->m4;
+        BH_CUDA(c, cudaMemcpy(c->dK3 + size_t(g) * p2, sw->K3.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
+        BH_CUDA(c, cudaMemcpy(c->dK4 + size_t(g) * p2, sw->K4.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
+        BH_CUDA(c, cudaMemcpy(c->dK5 + size_t(g) * p2, sw->K5.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+extern "C" int bh_sweep_all(bh_ctx* c, int env, double* psnr_after, int on_host) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    if (!psnr_after) BH_FAIL(c, -1, "psnr_after is null");
+    if (c->pad != 1) BH_FAIL(c, -4, "bh_sweep_all supports pad = 1 (circular) only; use bh_eval_flips");
+    if (c->Fg % 2) BH_FAIL(c, -4, "bh_sweep_all needs an even number of frames per colour group");
+    if (int rc = sweep_setup(c)) return rc;
+    const size_t n2 = c->n2, p2 = size_t(c->P) * c->P;
+    const int Fg = c->Fg;
+    const float iF = 1.f / float(Fg), iF2 = iF * iF;
+    const dim3 blk(256);
+    const int gx = int(std::min<size_t>((n2 + 255) / 256, 148 * 8));
+    cudaStream_t st = c->stream;
+    for (int g = 0; g < c->G; ++g) {
+        const float2* U = c->dU + (size_t(env) * c->F + size_t(g) * Fg) * n2;
+        const float* I = c->dI + (size_t(env) * c->G + g) * n2;
+        const float* T = c->dT + (size_t(env) * c->G + g) * n2;
+        const int8_t* stt = c->dstate + (size_t(env) * c->F + size_t(g) * Fg) * n2;
+        const float2 *Hh = c->dH + size_t(g) * p2, *K3 = c->dK3 + size_t(g) * p2,
+                     *K4 = c->dK4 + size_t(g) * p2, *K5 = c->dK5 + size_t(g) * p2;
+        BH_CUDA(c, cudaMemsetAsync(c->dsw_it, 0, size_t(Fg) * n2 * sizeof(float), st));
+        BH_CUDA(c, cudaMemsetAsync(c->dsw_ii, 0, size_t(Fg) * n2 * sizeof(float), st));
+        auto corr = [&](int mode, const float* A, const float* B, int planes, const float2* K) -> int {
+            k_sweep_prep<<<dim3(gx, planes), blk, 0, st>>>(U, A, B, c->dsw_in, n2, mode);
+            bool ok = false;
+            BH_CUDA(c, (dispatch_prop<float2, true>(c->P, 1, c->dsw_in, c->dsw_out, c->dsw_out, K, c->dtw,
+                                                    planes, planes, st, &ok)));
+            if (!ok) BH_FAIL(c, -4, "unsupported FFT side P=%d", c->P);
+            c->launches += 4;
+            return 0;
+        };
+        auto acc = [&](int mode, int planes, int to_ii, int use_sign, float c1, float c2, float cst) {
+            k_sweep_acc<<<dim3(gx, planes), blk, 0, st>>>(c->dsw_out, c->dsw_it, c->dsw_ii, stt, n2, Fg, mode,
+                                                         to_ii, use_sign, c1, c2, cst);
+            c->launches += 1;
+        };
+        int rc;
+        if ((rc = corr(PREP_UA, T, nullptr, Fg, Hh))) return rc;          // C1
+        acc(ACC_RE, Fg, 0, 1, 2.f * iF, 0.f, 0.f);
+        if ((rc = corr(PREP_UA, I, nullptr, Fg, Hh))) return rc;          // C2
+        acc(ACC_RE, Fg, 1, 1, 4.f * iF, 0.f, 0.f);
+        if ((rc = corr(PREP_U, nullptr, nullptr, Fg, K3))) return rc;     // C3
+        acc(ACC_RE, Fg, 1, 1, 4.f * iF2, 0.f, 0.f);
+        if ((rc = corr(PREP_U2, nullptr, nullptr, Fg, K5))) return rc;    // C5
+        acc(ACC_RE, Fg, 1, 0, 2.f * iF2, 0.f, 0.f);
+        if ((rc = corr(PREP_ABS2_PAIR, nullptr, nullptr, Fg / 2, K4))) return rc;   // C4, two frames per plane
+        acc(ACC_PAIR, Fg / 2, 1, 0, 2.f * iF2, 0.f, 0.f);
+        if ((rc = corr(PREP_TI, T, I, 1, K4))) return rc;                 // BT + i BI
+        acc(ACC_GROUP, Fg, 1, 0, iF, 2.f * iF, float(c->m4[g] * double(iF2)));
+        const size_t count = size_t(Fg) * n2;
+        double* dst = on_host ? c->dsw_psnr : psnr_after + size_t(g) * count;
+        k_sweep_final<<<int(std::min<size_t>((count + 255) / 256, 148 * 16)), blk, 0, st>>>(
+            c->dsw_it, c->dsw_ii, c->dsums + size_t(env) * 4, dst, count, double(c->G) * double(n2), c->relative);
+        c->launches += 1;
+        BH_CUDA(c, cudaGetLastError());
+        if (on_host) {
+            BH_CUDA(c, cudaMemcpyAsync(psnr_after + size_t(g) * count, c->dsw_psnr, count * sizeof(double),
+                                       cudaMemcpyDeviceToHost, st));
+            BH_CUDA(c, cudaStreamSynchronize(st));
+        }
+    }
     return 0;
 }
 

@@ -181,13 +181,24 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
 # score-and-revert sweep
 # ---------------------------------------------------------------------------
 def sweep_engine(eng: HoloEngine, env_index: int, pre_model: np.ndarray, order: np.ndarray,
-                 initial_psnr: float):
+                 initial_psnr: float, psnr_map: Optional[np.ndarray] = None, exhaustive="auto"):
     """Score ``order`` against the fixed state of one env; decile statistics.
 
-    Returns dict(psnr_after, attempted, improved, gains, flip_count).
+    Large sweeps (at least a quarter of all pixels) are scored by ``bh_sweep_all`` --
+    every pixel at once through FFT correlations -- and gathered in ``order``; small ones
+    by the batched delta kernel (``bh_eval_flips``).  ``psnr_map`` passes a map already
+    computed for this state.  Returns dict(psnr_after, attempted, improved, gains, flip_count).
     """
     order = np.asarray(order, dtype=np.int64)
-    psnr_after = eng.eval_flips(order, env=env_index)
+    use_map = psnr_map is not None or exhaustive is True or (
+        exhaustive == "auto" and eng.pad == 1 and eng.Fg % 2 == 0
+        and order.shape[0] * 4 >= eng.num_pixels)
+    if use_map:
+        if psnr_map is None:
+            psnr_map = eng.sweep_all(env_index)
+        psnr_after = psnr_map.reshape(-1)[order]
+    else:
+        psnr_after = eng.eval_flips(order, env=env_index)
     better = psnr_after > initial_psnr                    # dbs-...-6464.py:381,393
     d = decile_index(pre_model.ravel()[order])
     ok = d >= 0
@@ -263,9 +274,13 @@ def dbs_sweep(target_function: Callable, trainloader: Iterable, z=2e-3, pixel_pi
         gains = np.zeros(nb)
         psnr_all = np.empty(hi_all - lo_all, dtype=np.float64)
         flip_count = 0
+        psnr_map = None
+        if eng.pad == 1 and eng.Fg % 2 == 0 and (hi_all - lo_all) * 4 >= n:
+            psnr_map = eng.sweep_all(0)                    # every candidate in one call
         for lo in range(lo_all, hi_all, chunk):
             hi = min(hi_all, lo + chunk)
-            r = sweep_engine(eng, 0, cpre, perm[lo:hi], initial_psnr)
+            r = sweep_engine(eng, 0, cpre, perm[lo:hi], initial_psnr, psnr_map=psnr_map,
+                             exhaustive=False)
             psnr_all[lo - lo_all:hi - lo_all] = r["psnr_after"]
             attempted += r["attempted"]; improved += r["improved"]; gains += r["gains"]
             flip_count += r["flip_count"]

@@ -43,7 +43,10 @@ def init_process_group(backend: str = None):
     os.environ.setdefault("MASTER_PORT", "29531")
     if backend == "nccl":
         torch.cuda.set_device(local)
-    dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
 
 
 def _device():

@@ -21,7 +21,7 @@ ABI_SYMBOLS = (
     "bh_abi_version", "bh_last_error", "bh_create", "bh_destroy", "bh_set_stream",
     "bh_set_target", "bh_load_state", "bh_resync", "bh_get_metrics", "bh_eval_flips",
     "bh_step_batch", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
-    "bh_commit_flip", "bh_dbs_run", "bh_get_recon", "bh_get_state", "bh_get_field",
+    "bh_commit_flip", "bh_dbs_run", "bh_sweep_all", "bh_get_recon", "bh_get_state", "bh_get_field",
     "bh_device_ptr", "bh_simulate", "bh_time_eval", "bh_time_propagate", "bh_time_propagate_passes", "bh_launch_count",
 )
 
@@ -78,6 +78,7 @@ def load_library(build_if_missing: bool = True):
         "bh_max_tasks": (i32, [vp]),
         "bh_commit_flip": (i32, [vp, i32, i64]),
         "bh_dbs_run": (i32, [vp, i32, vp, i64, i32, i64, vp, vp, P(i64), P(dbl)]),
+        "bh_sweep_all": (i32, [vp, i32, vp, i32]),
         "bh_get_recon": (i32, [vp, i32, vp, i32, i64]),
         "bh_get_state": (i32, [vp, i32, vp, i32]),
         "bh_get_field": (i32, [vp, i32, i32, vp, i32]),
@@ -224,6 +225,16 @@ class HoloEngine:
         self._check(self.lib.bh_dbs_run(self._h, env, _ptr(o), n, k_spec, resync_every, _ptr(acc),
                                         _ptr(tr), C.byref(nacc), C.byref(fin)), "bh_dbs_run")
         return acc, tr, int(nacc.value), fin.value
+
+    def sweep_all(self, env: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """PSNR after flipping each pixel of each frame (fixed state): float64 (F, N, N)."""
+        if out is None:
+            out = np.empty((self.F, self.N, self.N), dtype=np.float64)
+        self._check(self.lib.bh_sweep_all(self._h, env, _ptr(out), 1), "bh_sweep_all")
+        return out
+
+    def sweep_all_device(self, env: int, d_out: int):
+        self._check(self.lib.bh_sweep_all(self._h, env, C.c_void_p(d_out), 0), "bh_sweep_all")
 
     # -- read-back --------------------------------------------------------
     def recon(self, env: int = 0, candidate_action: int = -1,

@@ -82,6 +82,15 @@ int bh_get_metrics(bh_ctx* ctx, int env, double* psnr, double* mse, double* sums
 int bh_eval_flips(bh_ctx* ctx, int env, int64_t n, const int32_t* env_ids,
                   const int64_t* actions, double* psnr_after);
 
+/* Score EVERY single-pixel flip of every frame against the current state in one
+ * call (the exhaustive loops of dbs-1024-1024-24-6464.py:330-395, range.py:294-335,
+ * DBS_1024_24-128.py:310-373): psnr_after[frame][row][col], F*N*N doubles, equal to
+ * what bh_eval_flips returns for the same action.  Evaluated as cross-correlations
+ * with the (even) impulse-response kernels through the FFT passes -- O(N^2 log N)
+ * per frame instead of N^2 delta passes.  pad = 1 only.  Device pointer when
+ * on_host = 0. */
+int bh_sweep_all(bh_ctx* ctx, int env, double* psnr_after, int on_host);
+
 /* One environment step for n distinct environments: score the flip, keep or
  * revert it under `rule` (env.py:154-196 / DBS_1024_24.py:313-422 body).
  * results: n records. */

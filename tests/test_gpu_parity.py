@@ -112,6 +112,38 @@ def test_eval_flips_matches_full_resimulation(N, F, wl, pad, relative):
     eng.close()
 
 
+@pytest.mark.parametrize("N,F,wl,relative", [
+    (64, 8, O.WL_MONO, True), (64, 6, O.WL_RGB, True), (128, 6, O.WL_RGB, False), (256, 8, O.WL_MONO, True),
+])
+def test_sweep_all_correlation_matches_oracle_and_delta_kernel(N, F, wl, relative):
+    """bh_sweep_all (FFT correlations) == bh_eval_flips (delta kernel) == full re-simulation."""
+    pre, tgt, st = _problem(N, F, wl, seed=23)
+    cfg = O.HoloConfig(N=N, F=F, wl=wl, relative=relative)
+    eng = _engine(N, F, wl, 1, relative)
+    eng.set_target(0, tgt)
+    eng.load_state(0, st)
+    psnr0 = eng.metrics(0)[0]
+    pm = eng.sweep_all(0)
+    assert pm.shape == (F, N, N) and np.all(np.isfinite(pm))
+    rng = np.random.default_rng(4)
+    actions = np.concatenate([rng.integers(0, F * N * N, size=300), [0, N * N - 1, F * N * N - 1]])
+    d_map = pm.reshape(-1)[actions] - psnr0
+    d_delta = eng.eval_flips(actions) - psnr0
+    np.testing.assert_allclose(d_map, d_delta, rtol=2e-4, atol=2e-8)
+    ref, p0, *_ = O.sweep(cfg, st, tgt, pre, actions[:40])
+    np.testing.assert_allclose(d_map[:40], ref - p0, rtol=2e-4, atol=1e-7)
+    # every pixel scored: the improving fraction agrees with the delta kernel on a sample
+    assert abs((d_map > 0).mean() - (d_delta > 0).mean()) < 1e-9
+    assert np.array_equal(eng.state(0), st) and eng.metrics(0)[0] == psnr0
+    # the sweep driver picks the map for an exhaustive order and the decile stats agree
+    order = rng.permutation(F * N * N)
+    r_map = bh.sweep_engine(eng, 0, pre, order, psnr0)
+    r_del = bh.sweep_engine(eng, 0, pre, order[:2000], psnr0, exhaustive=False)
+    np.testing.assert_allclose(r_map["psnr_after"][:2000], r_del["psnr_after"], rtol=0, atol=1e-8)
+    assert r_map["attempted"].sum() == F * N * N
+    eng.close()
+
+
 # ---------------------------------------------------------------------------
 # golden fixtures (tests/golden/*.npz, made by the float64 oracle)
 # ---------------------------------------------------------------------------
