@@ -13,11 +13,13 @@ from .vec_env import HologramVecEnv
 from .dbs import (optimize_with_random_pixel_flips, dbs_greedy_env, dbs_sweep, sweep_engine,
                   decile_index, OUTPUT_BINS)
 from .synthetic import synthetic_problem, SyntheticLoader
+from .data import ImageFolderLoader, load_image, crop_to
 
 __all__ = [
     "HoloEngine", "HoloError", "RULE_ENV", "RULE_DBS", "RULE_NEVER", "RESULT_DTYPE", "load_library",
     "simulate", "BinaryHologramEnv", "BinaryHologramEnvRGB", "BinaryHologramEnvRGBCrop",
     "BinaryHologramEnvGroup", "RW", "WL_MONO", "WL_RGB", "HologramVecEnv",
     "optimize_with_random_pixel_flips", "dbs_greedy_env", "dbs_sweep", "sweep_engine",
-    "decile_index", "OUTPUT_BINS", "synthetic_problem", "SyntheticLoader",
+    "decile_index", "OUTPUT_BINS", "synthetic_problem", "SyntheticLoader", "ImageFolderLoader",
+    "load_image", "crop_to",
 ]

@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
+#include <map>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -53,6 +55,7 @@ struct bh_ctx {
     double* h_sums = nullptr;
     Result* h_results_dev = nullptr;     // device alias of the mapped h_results
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_eval = nullptr;
+    cudaStream_t own_stream = nullptr;   // capture needs a real stream when the caller gave none
     int64_t launches = 0;
     std::string err;
 };
@@ -200,6 +203,7 @@ extern "C" int bh_destroy(bh_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_eval) cudaEventDestroy(c->ev_eval);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
 }
@@ -547,7 +551,21 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
     if (int rc = check_actions(c, order, n)) return rc;
     long long* d_order = nullptr; uint8_t* d_acc = nullptr; double* d_trace = nullptr;
     int rc = 0;
-    auto cleanup = [&]() { cudaFree(d_order); cudaFree(d_acc); cudaFree(d_trace); };
+    // The iterations of a chunk are identical launches (the cursor lives on the device), so a
+    // chunk is captured once per speculation depth into a CUDA graph and replayed: the loop is
+    // launch bound at small N (256^2: ~4 us of GPU work per iteration).
+    std::map<int, cudaGraphExec_t> graphs;
+    cudaStream_t caller_stream = c->stream;
+    const bool use_graph = n >= 4096 && !std::getenv("BHOLO_NO_GRAPH");
+    if (use_graph && !c->stream) {
+        if (!c->own_stream) BH_CUDA(c, cudaStreamCreate(&c->own_stream));   // blocking: ordered with stream 0
+        c->stream = c->own_stream;
+    }
+    auto cleanup = [&]() {
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        cudaFree(d_order); cudaFree(d_acc); cudaFree(d_trace);
+        c->stream = caller_stream;
+    };
 #define BH_DBS(expr)                                                                       \
     do {                                                                                   \
         cudaError_t _e = (expr);                                                           \
@@ -574,9 +592,24 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
             DeltaArgs ac = a;                   // the commit kernel also selects and logs
             ac.dbs_cursor = c->d_scalars; ac.dbs_count = c->d_scalars + 1;
             ac.dbs_accepted = d_acc; ac.dbs_trace = d_trace;
-            for (int it = 0; it < iters_per_sync; ++it) {
-                launch_eval(c, a);
-                launch_commit(c, ac);
+            if (use_graph) {
+                auto it = graphs.find(K);
+                if (it == graphs.end()) {
+                    cudaGraph_t g = nullptr;
+                    cudaGraphExec_t ge = nullptr;
+                    const int64_t before = c->launches;
+                    BH_DBS(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                    for (int i = 0; i < iters_per_sync; ++i) { launch_eval(c, a); launch_commit(c, ac); }
+                    BH_DBS(cudaStreamEndCapture(c->stream, &g));
+                    c->launches = before;       // captured, not launched
+                    BH_DBS(cudaGraphInstantiate(&ge, g, 0));
+                    cudaGraphDestroy(g);
+                    it = graphs.emplace(K, ge).first;
+                }
+                BH_DBS(cudaGraphLaunch(it->second, c->stream));
+                c->launches += 2 * iters_per_sync;
+            } else {
+                for (int i = 0; i < iters_per_sync; ++i) { launch_eval(c, a); launch_commit(c, ac); }
             }
             BH_DBS(cudaGetLastError());
             BH_DBS(cudaMemcpyAsync(c->h_scalars, c->d_scalars, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));

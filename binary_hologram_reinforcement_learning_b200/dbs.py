@@ -83,8 +83,17 @@ def bin_population(pre_model: np.ndarray) -> np.ndarray:
 def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_datasets=None,
                    order: Optional[np.ndarray] = None, rng=None, k_spec: int = 0,
                    resync_every: int = 1024, segment: int = 1 << 20, verbose: bool = True,
-                   max_candidates: Optional[int] = None, save_dir: Optional[str] = None) -> List[dict]:
-    """DBS.py:202-307 / DBS_1024_24.py:206-469 on the device-resident engine."""
+                   max_candidates: Optional[int] = None, save_dir: Optional[str] = None,
+                   checkpoint: Optional[str] = None, max_segments: Optional[int] = None) -> List[dict]:
+    """DBS.py:202-307 / DBS_1024_24.py:206-469 on the device-resident engine.
+
+    ``checkpoint``: path of an .npz written after every segment (binary state, candidate
+    order, cursor, decisions so far).  If it exists when an image starts and holds the same
+    order, the run resumes from its cursor instead of starting over -- the reference keeps
+    nothing but the before/after reconstructions (DBS_1024_24.py:282-287,446-451).
+    ``max_segments`` bounds the work of one call (the result then has ``complete = False``
+    and a later call with the same checkpoint continues).
+    """
     results = []
     db_num = 0
     if max_datasets is None:
@@ -118,8 +127,25 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
         thresholds = [initial_psnr + i * step_gain for i in range(1, 21 if env.G == 1 else 101)]
         previous = initial_psnr
         flip_count = 0
-        for lo in range(0, perm.shape[0], segment):
+        start = 0
+        if checkpoint and os.path.exists(checkpoint):
+            ck = np.load(checkpoint)
+            if (ck["fname"].item() == file_name and ck["order"].shape == perm.shape
+                    and np.array_equal(ck["order"], perm)):
+                start = int(ck["cursor"])
+                accepted[:start], trace[:start] = ck["accepted"][:start], ck["trace"][:start]
+                eng.load_state(e, ck["state"])             # re-propagates from the saved hologram
+                flip_count = int(np.count_nonzero(accepted[:start]))
+                hits = np.flatnonzero(accepted[:start])
+                previous = trace[hits[-1]] if hits.size else initial_psnr
+                if verbose:
+                    print(f"Resuming {file_name}.png from candidate {start} (PSNR {eng.metrics(e)[0]:.6f})")
+        done_upto = start
+        for seg_i, lo in enumerate(range(start, perm.shape[0], segment)):
+            if max_segments is not None and seg_i >= max_segments:
+                break
             hi = min(perm.shape[0], lo + segment)
+            done_upto = hi
             acc, tr, nacc, psnr_now = eng.dbs_run(perm[lo:hi], env=e, k_spec=k_spec,
                                                   resync_every=resync_every, trace=True)
             accepted[lo:hi], trace[lo:hi] = acc, tr
@@ -137,6 +163,11 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
                               f"\nSuccess Ratio: {np.count_nonzero(accepted[:j + 1]) / (j + 1):.6f} | Flip Count: {np.count_nonzero(accepted[:j + 1])}"
                               f"\nTime taken for this data: {time.time() - t0:.2f} seconds")
                 previous = trace[hit[-1]]
+            if checkpoint:
+                tmp = checkpoint + ".tmp.npz"
+                np.savez_compressed(tmp, fname=np.array(file_name), order=perm, cursor=np.array(hi),
+                                    accepted=accepted, trace=trace, state=eng.state(e))
+                os.replace(tmp, checkpoint)
         # host mirrors follow the device state
         new_state = eng.state(e)
         env._crop(env.state[0])[...] = new_state
@@ -152,9 +183,10 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
             ok = d >= 0
             improved = np.bincount(d[ok], minlength=improved.size)
             gains = np.bincount(d[ok], weights=(trace[acc_idx] - prev_psnr)[ok], minlength=gains.size)
-        steps = int(perm.shape[0])
+        steps = int(done_upto)
+        accepted, trace = accepted[:steps], trace[:steps]
         dt = time.time() - t0
-        out = dict(file=file_name, initial_psnr=initial_psnr, final_psnr=final_psnr, steps=steps,
+        out = dict(complete=steps == perm.shape[0], file=file_name, initial_psnr=initial_psnr, final_psnr=final_psnr, steps=steps,
                    flip_count=int(flip_count), accepted=accepted, psnr_trace=trace, order=perm,
                    seconds=dt, bin_counts=bin_counts + improved, improved_bin_counts=improved,
                    psnr_improvements=gains, state=new_state)

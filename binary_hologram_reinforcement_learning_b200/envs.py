@@ -202,6 +202,7 @@ class BinaryHologramEnv(spaces.Env):
         if self.reward_mode == "group":                               # env_group.py:190-199
             t0 = time.time()
             self.psnr_change_list, self.importance_ranks, pos = self._calculate_pixel_importance()
+            self._psnr_change_arr = np.asarray(self.psnr_change_list, dtype=np.float64)
             if self.verbose:
                 print(f"\nTime taken for psnr_change_list: {time.time() - t0:.2f} seconds")
             self.T_PSNR_DIFF = pos / 4
@@ -286,7 +287,7 @@ class BinaryHologramEnv(spaces.Env):
         psnr_change = psnr_after - self.previous_psnr                 # env.py:184-185
         psnr_diff = psnr_after - self.initial_psnr
         if self.reward_mode == "group":                               # env_group.py:254-255
-            idx = int(np.argmin(np.abs(np.asarray(self.psnr_change_list) - psnr_change)))
+            idx = int(np.argmin(np.abs(self._psnr_change_arr - psnr_change)))
             reward = float(self.importance_ranks[idx])
         else:
             reward = psnr_change * RW                                 # env.py:188

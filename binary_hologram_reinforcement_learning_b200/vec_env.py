@@ -52,8 +52,10 @@ class HologramVecEnv:
         self._ep_reward = np.zeros(self.num_envs)
         # vectorised bookkeeping (env.py:154-260 evaluated for all envs at once); used when no
         # per-step printing, cropping or rank-table reward is involved
-        self._fast = (crop_margin == 0 and reward_mode == "psnr" and not verbose
+        self._fast = (crop_margin == 0 and reward_mode in ("psnr", "group") and not verbose
                       and recon_obs != "eager")
+        self._group = reward_mode == "group"
+        self._changes = self._ranks = None      # (E, num_samples) tables of env_group.py:90-143
         E = self.num_envs
         self._steps = np.zeros(E, dtype=np.int64)
         self._flips = np.zeros(E, dtype=np.int64)
@@ -94,6 +96,12 @@ class HologramVecEnv:
         self._last_cand[i] = -1
         self._tdiff[i], self._tpsnr[i], self._maxsteps[i] = env.T_PSNR_DIFF, env.T_PSNR, env.max_steps
         self._obs_cache[i] = env._obs()
+        if self._group:
+            if self._changes is None:
+                self._changes = np.zeros((self.num_envs, env.num_samples))
+                self._ranks = np.zeros((self.num_envs, env.num_samples))
+            self._changes[i] = env._psnr_change_arr
+            self._ranks[i] = env.importance_ranks
 
     def sync_envs(self):
         """Push the vectorised counters back into the per-env objects."""
@@ -129,7 +137,11 @@ class HologramVecEnv:
         self._record2d[self._ar, acts] += 1                          # env.py:165
         change = psnr_after - self._prev                             # env.py:184-188
         diff = psnr_after - self._init
-        rewards = change * RW
+        if self._group:                                              # env_group.py:254-255
+            idx = np.abs(self._changes - change[:, None]).argmin(axis=1)
+            rewards = self._ranks[self._ar, idx].copy()
+        else:
+            rewards = change * RW
         self._state2d[self._ar[acc], acts[acc]] ^= 1                 # env.py:164 / 191-193
         self._flips += acc
         self._prev[acc] = psnr_after[acc]                            # env.py:214
@@ -144,12 +156,13 @@ class HologramVecEnv:
         for i in np.flatnonzero(event):                              # env.py:216-260
             env = envs[i]
             ratio = self._flips[i] / self._steps[i]
+            linear = 100 + (-200.0 / 1500.0) * (self._steps[i] - 1000)     # env_group.py:294-299
             if diff[i] >= env.T_PSNR_DIFF or (psnr_after[i] >= env.T_PSNR and diff[i] < 0.1):
                 self._sustained[i] += 1
                 if self._sustained[i] >= env.T_steps and diff[i] >= env.T_PSNR_DIFF:
-                    rewards[i] += goal_bonus(ratio, -595.2)
+                    rewards[i] += linear if self._group else goal_bonus(ratio, -595.2)
             if self._steps[i] >= env.max_steps:
-                rewards[i] += goal_bonus(ratio, -595.24)
+                rewards[i] += linear if self._group else goal_bonus(ratio, -595.24)
             term = self._steps[i] >= env.max_steps or self._sustained[i] >= env.T_steps
             trunc = self._steps[i] >= env.max_steps
             if term or trunc:

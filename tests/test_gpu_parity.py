@@ -441,3 +441,197 @@ def test_reference_call_sequence_through_compat_shims():
     H = O.transfer_function(N, O.PIXEL_PITCH, 638e-9, O.Z_DEFAULT)
     ref = O.simulate(state[0, :4].astype(np.float64), H, 1)
     assert np.abs(U.cpu().numpy()[0] - ref).max() < 1e-5 * np.abs(ref).max()
+
+
+# ---------------------------------------------------------------------------
+# DBS drivers (reference entry points) incl. checkpoint / resume
+# ---------------------------------------------------------------------------
+def test_dbs_greedy_driver_and_resume(golden_dir, tmp_path):
+    """optimize_with_random_pixel_flips(env): DBS.py:202-307 through the env, resumable."""
+    N, F, wl, pad, relative, seed = MG.CASES["mono64"]
+    g = np.load(os.path.join(golden_dir, "mono64.npz"))
+    order = g["dbs_order"]
+
+    def make_env():
+        ld = bh.SyntheticLoader(N, F, 1, seeds=(seed,))
+        return bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, verbose=False)
+
+    env = make_env()
+    res = bh.optimize_with_random_pixel_flips(env, max_datasets=0, order=order, verbose=False)
+    assert len(res) == 1 and res[0]["complete"]
+    r = res[0]
+    assert np.array_equal(r["accepted"].astype(bool), g["dbs_accepted"])
+    assert r["flip_count"] == int(g["dbs_accepted"].sum())
+    assert int(env.state.sum()) == int(g["dbs_final_state_sum"])          # host mirror follows the device
+    assert np.array_equal(env.engine.state(0), env.state[0])
+    assert r["improved_bin_counts"].sum() == r["flip_count"]
+    env.close()
+    # same run in two calls through a checkpoint
+    ck = str(tmp_path / "dbs_ck.npz")
+    env = make_env()
+    part = bh.dbs_greedy_env(env, max_datasets=0, order=order, verbose=False, segment=64,
+                             checkpoint=ck, max_segments=2)[0]
+    assert not part["complete"] and part["steps"] == 128 and os.path.exists(ck)
+    env.close()
+    env = make_env()                                                       # fresh process stand-in
+    rest = bh.dbs_greedy_env(env, max_datasets=0, order=order, verbose=False, segment=64, checkpoint=ck)[0]
+    assert rest["complete"] and np.array_equal(rest["accepted"], r["accepted"])
+    np.testing.assert_allclose(rest["psnr_trace"], r["psnr_trace"], rtol=0, atol=1e-6)
+    assert np.array_equal(rest["state"], r["state"])
+    env.close()
+
+
+def test_dbs_sweep_driver_with_crop():
+    """dbs-1024-1024-24-6464.py:194-478 at a small shape: crop 8 of 80 -> 64^2 x 6, all pixels scored."""
+    N, F, m = 80, 6, 8
+    ld = bh.SyntheticLoader(N, F, 3, seeds=(61,))
+    res = bh.optimize_with_random_pixel_flips(ld.target_function, ld, 2e-3, 7.56e-6, m, CH=F,
+                                              max_datasets=0, rng=np.random.default_rng(1), verbose=False)
+    assert len(res) == 1
+    r = res[0]
+    n = F * 64 * 64
+    assert r["steps"] == n and r["attempted"].sum() == n and np.array_equal(r["attempted"], r["bin_counts"])
+    pre, tgt = bh.synthetic_problem(N, F, 3, 61)
+    cfg = O.HoloConfig(N=64, F=F, wl=O.WL_RGB)
+    st = (pre >= 0.5).astype(np.int8)[:, m:-m, m:-m]
+    sub = r["order"][:50]
+    ref, p0, *_ = O.sweep(cfg, st, tgt[:, m:-m, m:-m], pre[:, m:-m, m:-m], sub)
+    assert abs(r["initial_psnr"] - p0) < 1e-4
+    np.testing.assert_allclose(r["psnr_after"][:50] - r["initial_psnr"], ref - p0, rtol=2e-4, atol=1e-7)
+    assert 0 < r["flip_count"] < n and r["improved"].sum() == r["flip_count"]
+
+
+# ---------------------------------------------------------------------------
+# golden fixtures at the BASELINE shapes (tests/golden/large_*.npz, make_golden_large.py)
+# ---------------------------------------------------------------------------
+from tests.golden import make_golden_large as MGL  # noqa: E402
+
+
+def _need(golden_dir, name):
+    path = os.path.join(golden_dir, f"{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{name}.npz not generated")
+    return np.load(path)
+
+
+@pytest.mark.parametrize("name", list(MGL.CASES))
+def test_large_golden(name, golden_dir):
+    g = _need(golden_dir, name)
+    N, F, wl, seed, n_steps, n_dbs, n_sweep = MGL.CASES[name]
+    G = len(wl)
+    ld = bh.SyntheticLoader(N, F, G, seeds=(seed,))
+    env = bh.BinaryHologramEnv(ld.target_function, ld, max_steps=n_steps - 20, T_PSNR_DIFF=1e9,
+                               IPS=N, CH=F, wl=wl, verbose=False, recon_obs="lazy")
+    env.reset()
+    eng = env.engine
+    # propagation
+    psnr0, mse0, sums = eng.metrics(0)
+    assert abs(psnr0 - float(g["initial_psnr"])) < 1e-4
+    assert abs(mse0 - float(g["initial_mse"])) < 1e-5 * float(g["initial_mse"])
+    np.testing.assert_allclose(sums, g["loss_sums"], rtol=2e-6)
+    rec = eng.recon(0)[:, ::N // 8, ::N // 8]
+    np.testing.assert_allclose(rec, g["recon_samples"], atol=2e-5 * g["recon_samples"].max())
+    for i, f in enumerate(g["field_frames"]):
+        U = eng.field(0, int(f))[::N // 8, ::N // 8]
+        assert np.abs(U - g["field_samples"][i]).max() < 1e-5 * np.abs(g["field_samples"][i]).max()
+    # sweep: delta kernel and correlation map against the oracle
+    d_ref = g["sweep_psnr"] - float(g["initial_psnr"])
+    d_eval = eng.eval_flips(g["sweep_order"]) - psnr0
+    np.testing.assert_allclose(d_eval, d_ref, rtol=2e-4, atol=2e-9)
+    d_map = eng.sweep_all(0).reshape(-1)[g["sweep_order"]] - psnr0
+    np.testing.assert_allclose(d_map, d_ref, rtol=5e-4, atol=5e-9)
+    # greedy DBS prefix on a second context (the env keeps its own state for the trajectory)
+    eng2 = bh.HoloEngine(N, F, wl)
+    pre, tgt = bh.synthetic_problem(N, F, G, seed)
+    eng2.set_target(0, tgt)
+    eng2.load_state(0, (pre >= 0.5).astype(np.int8))
+    acc, tr, nacc, fin = eng2.dbs_run(g["dbs_order"], trace=True)
+    prev = np.maximum.accumulate(np.concatenate([[float(g["initial_psnr"])],
+                                                 np.where(g["dbs_accepted"], g["dbs_trace"], -np.inf)]))[:-1]
+    ok, bad = _decisions_equal_up_to_near_ties(acc, g["dbs_accepted"], g["dbs_trace"] - prev)
+    assert ok, bad
+    if bad.size == 0:
+        np.testing.assert_allclose(tr, g["dbs_trace"], rtol=0, atol=1e-4)
+        assert int(eng2.state(0).sum()) == int(g["dbs_final_state_sum"])
+    eng2.close()
+    # env trajectory incl. the max_steps bonus
+    prev = float(g["initial_psnr"])
+    for i, a in enumerate(g["env_actions"]):
+        flips_before = env.flip_count
+        obs, r, term, trunc, _ = env.step(int(a))
+        acc_ref = bool(g["env_accepted"][i])
+        if (env.flip_count == flips_before + 1) != acc_ref:
+            assert abs(float(g["env_psnr"][i]) - prev) < NEAR_TIE, i
+            break                                            # legitimately diverged on a near-tie
+        r_ref = float(g["env_rewards"][i])
+        assert abs(r - r_ref) <= 1e-5 * abs(r_ref) + 800 * 2e-7, (i, r, r_ref)
+        assert term == bool(g["env_terminated"][i])
+        if acc_ref:
+            prev = float(g["env_psnr"][i])
+    else:
+        assert int(env.state.sum()) == int(g["env_final_state_sum"])
+    env.close()
+
+
+def test_large_golden_dbs64_exhaustive(golden_dir):
+    """Every pixel of a 64^2 x 8 stack visited once (DBS.py:243-294): 32768 sequential decisions."""
+    g = _need(golden_dir, "large_dbs64_exhaustive")
+    N, F, seed = 64, 8, 41
+    pre, tgt, st = _problem(N, F, O.WL_MONO, seed)
+    eng = _engine(N, F, O.WL_MONO)
+    eng.set_target(0, tgt)
+    eng.load_state(0, st)
+    acc, _, nacc, fin = eng.dbs_run(g["order"], resync_every=1024)
+    ref = np.unpackbits(g["accepted"])[:int(g["n"])]
+    mism = int(np.count_nonzero(acc != ref))
+    assert mism <= 0.002 * ref.size, mism                   # near-tie divergences only
+    assert abs(fin - float(g["final_psnr"])) < 5e-3
+    assert abs(nacc - int(g["n_accepted"])) <= 0.002 * ref.size
+    if mism == 0:
+        assert np.array_equal(np.packbits(eng.state(0).astype(np.uint8)), g["final_state"])
+    eng.close()
+
+
+def test_large_golden_group256(golden_dir):
+    """env_group.py:90-143 at 256^2 x 8 with the reference's 10 000 candidates."""
+    g = _need(golden_dir, "large_group256")
+    N, F, seed = 256, 8, 51
+    ld = bh.SyntheticLoader(N, F, 1, seeds=(seed,))
+    env = bh.BinaryHologramEnvGroup(ld.target_function, ld, IPS=N, CH=F, verbose=False,
+                                    rng=np.random.default_rng(seed))
+    env.reset()
+    assert np.array_equal(env.importance_actions, g["actions"])
+    np.testing.assert_allclose(env.psnr_change_list, g["psnr_changes"], rtol=2e-4, atol=2e-8)
+    assert abs(env.T_PSNR_DIFF - float(g["positive_sum"]) / 4) < 1e-4 * float(g["positive_sum"])
+    # rank table: identical wherever the ordering of the changes is unambiguous
+    order_ref = np.argsort(g["psnr_changes"])
+    gaps = np.diff(g["psnr_changes"][order_ref])
+    if gaps.min() > 1e-9:
+        np.testing.assert_allclose(env.importance_ranks, g["ranks"], atol=1e-9)
+    else:
+        assert np.mean(np.abs(env.importance_ranks - g["ranks"]) > 1e-6) < 0.01
+    env.close()
+
+
+def test_group_vec_env_fast_path_matches_per_env_path():
+    """env_group.py reward (rank-table lookup) vectorised across envs == the per-env implementation."""
+    N, F, E = 64, 8, 3
+    def make(verbose):
+        loaders = [bh.SyntheticLoader(N, F, 1, seeds=(300 + i,)) for i in range(E)]
+        tf = lambda t: next(l for l in loaders if np.ascontiguousarray(t[0, 0, 0, :4]).tobytes() in l._pre).target_function(t)
+        return bh.HologramVecEnv(E, tf, loaders, max_steps=25, IPS=N, CH=F, reward_mode="group",
+                                 num_samples=200, seed=5, verbose=verbose)
+    import contextlib, io
+    fast, slow = make(False), make(True)
+    assert fast._fast and not slow._fast
+    with contextlib.redirect_stdout(io.StringIO()):
+        fast.reset(); slow.reset()
+        rng = np.random.default_rng(0)
+        for step in range(60):
+            acts = rng.integers(0, F * N * N, size=E)
+            _, r1, d1, _ = fast.step(acts)
+            _, r2, d2, _ = slow.step(acts)
+            np.testing.assert_allclose(r1, r2, rtol=1e-12, atol=1e-12)
+            assert np.array_equal(d1, d2)
+    assert len(fast.episode_stats) == len(slow.episode_stats) > 0
+    fast.close(); slow.close()

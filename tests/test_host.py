@@ -145,3 +145,22 @@ def test_two_rank_gloo_stats_gather(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"GLOO_OK {r}" in o, o
+
+
+def test_image_folder_loader(tmp_path):
+    """Dataset512-shaped loader (DBS.py:172-199): (1, C, N, N) float32 in [0,1] and [path]."""
+    PIL = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(0)
+    for i, shape in enumerate([(80, 100, 3), (40, 50, 3)]):
+        PIL.fromarray((rng.random(shape) * 255).astype("uint8")).save(tmp_path / f"{i:04d}.png")
+    ld = bh.ImageFolderLoader(str(tmp_path), 64)
+    items = list(ld)
+    assert len(items) == 2 and len(ld) == 2
+    t, p = items[0]
+    assert t.shape == (1, 3, 64, 64) and t.dtype == np.float32 and 0 <= t.min() and t.max() <= 1
+    assert isinstance(p, list) and p[0].endswith("0000.png")
+    assert items[1][0].shape == (1, 3, 64, 64)              # smaller image tiled up, then cropped
+    full = bh.load_image(p[0])
+    assert np.array_equal(t[0], full[:, 8:72, 18:82])       # centre crop
+    g = next(iter(bh.ImageFolderLoader(str(tmp_path), 32, gray=True, random_crop=True, seed=3)))[0]
+    assert g.shape == (1, 1, 32, 32)
