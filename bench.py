@@ -253,6 +253,16 @@ def run_b200(args):
     h2d = R * E * (8 + 4)                       # actions int64 + env ids int32 per vec step
     d2h = R * E * RESULT_DTYPE.itemsize         # bh_result records per vec step
 
+    # ---- e2e with the reference's eager observation: recon_image copied to the host every step
+    n_eager = 64
+    t0 = time.perf_counter()
+    for i in range(n_eager):
+        vec.step(acts_host[i])
+        for j in range(E):
+            vec.refresh_recon(j)                  # 12.6 MB D2H per env into pinned memory
+    torch.cuda.synchronize()
+    eager_s = bdist.max_over_ranks(time.perf_counter() - t0)
+
     # ---- value: device-resident actions, CUDA events ---------------------
     d_acts = torch.from_numpy(rng.integers(0, n_pix, size=(R * (K + W), E), dtype=np.int64)).cuda(local)
     d_envs = torch.arange(E, dtype=torch.int32, device=f"cuda:{local}")
@@ -355,7 +365,9 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "env steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "api": "HologramVecEnv.step (bh_step_batch)",
-                    "checksum_reward_env0": reward_sum},
+                    "checksum_reward_env0": reward_sum,
+                    "with_eager_recon_obs": {"value": world * E * n_eager / eager_s, "unit": "env steps/s",
+                                             "d2h_bytes_per_env_step": 4 * GROUPS * N_SIDE * N_SIDE}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "extra": {

@@ -731,11 +731,30 @@ extern "C" int bh_sweep_all(bh_ctx* c, int env, double* psnr_after, int on_host)
     return 0;
 }
 
+extern "C" void* bh_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        g_err = "cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" int bh_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) { g_err = "cudaFreeHost failed"; return -2; }
+    return 0;
+}
+
 extern "C" int bh_get_recon(bh_ctx* c, int env, float* out, int on_host, int64_t cand) {
     BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
     if (!out) BH_FAIL(c, -1, "out is null");
     const size_t n2 = c->n2, bytes = size_t(c->G) * n2 * sizeof(float);
     const float* I = c->dI + size_t(env) * c->G * n2;
+    if (cand < 0) {                       // committed reconstruction: one copy, no staging
+        BH_CUDA(c, cudaMemcpyAsync(out, I, bytes, on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
+        if (on_host) BH_CUDA(c, cudaStreamSynchronize(c->stream));
+        return 0;
+    }
     float* dst = on_host ? c->drecon : out;
     BH_CUDA(c, cudaMemcpyAsync(dst, I, bytes, cudaMemcpyDeviceToDevice, c->stream));
     if (cand >= 0) {

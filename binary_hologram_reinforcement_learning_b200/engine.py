@@ -22,7 +22,7 @@ ABI_SYMBOLS = (
     "bh_set_target", "bh_load_state", "bh_resync", "bh_get_metrics", "bh_eval_flips",
     "bh_step_batch", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
     "bh_commit_flip", "bh_dbs_run", "bh_sweep_all", "bh_get_recon", "bh_get_state", "bh_get_field",
-    "bh_device_ptr", "bh_simulate", "bh_time_eval", "bh_time_propagate", "bh_time_propagate_passes", "bh_launch_count",
+    "bh_device_ptr", "bh_host_alloc", "bh_host_free", "bh_simulate", "bh_time_eval", "bh_time_propagate", "bh_time_propagate_passes", "bh_launch_count",
 )
 
 
@@ -83,6 +83,8 @@ def load_library(build_if_missing: bool = True):
         "bh_get_state": (i32, [vp, i32, vp, i32]),
         "bh_get_field": (i32, [vp, i32, i32, vp, i32]),
         "bh_device_ptr": (vp, [vp, i32]),
+        "bh_host_alloc": (vp, [C.c_size_t]),
+        "bh_host_free": (i32, [vp]),
         "bh_simulate": (i32, [i32, vp, vp, i32, i32, i32, dbl, dbl, dbl, i32, i32, vp, i32]),
         "bh_time_eval": (i32, [vp, i32, vp, vp, i32, i32, P(C.c_float)]),
         "bh_time_propagate": (i32, [vp, i32, i32, P(C.c_float)]),
@@ -95,6 +97,35 @@ def load_library(build_if_missing: bool = True):
         fn.argtypes = args
     _LIB = lib
     return lib
+
+
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block; freed when the last numpy view dies."""
+
+    def __init__(self, lib, nbytes: int):
+        self.lib, self.nbytes = lib, nbytes
+        self.ptr = lib.bh_host_alloc(nbytes)
+        if not self.ptr:
+            raise HoloError("bh_host_alloc failed")
+
+    def __del__(self):
+        try:
+            self.lib.bh_host_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array in page-locked host memory (falls back to pageable memory without a GPU)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    try:
+        blk = _PinnedBlock(load_library(), max(n, 1))
+    except Exception:
+        return np.empty(shape, dtype=dtype)
+    buf = (C.c_char * max(n, 1)).from_address(blk.ptr)
+    buf._pinned_owner = blk                      # keeps the block alive with the view
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 def _ptr(a: Optional[np.ndarray]):

@@ -22,7 +22,7 @@ from typing import Callable, Iterable, Optional, Sequence
 import numpy as np
 
 from . import spaces
-from .engine import HoloEngine, RULE_ENV, RESULT_DTYPE
+from .engine import HoloEngine, RULE_ENV, RESULT_DTYPE, pinned_empty
 
 RW = 800                                   # env.py:29
 WL_MONO = (515e-9,)                        # env.py:124
@@ -128,7 +128,7 @@ class BinaryHologramEnv(spaces.Env):
         self._res = np.empty(1, dtype=RESULT_DTYPE)
         self._act = np.empty(1, dtype=np.int64)
         self._eid = np.array([self._e], dtype=np.int32)
-        self._recon_buf = np.zeros((1, self.G, self.Nsim, self.Nsim), dtype=np.float32)
+        self._recon_buf = None                            # pinned, allocated with the engine
 
     # ------------------------------------------------------------------
     def _ensure_engine(self, z: float, dx: float):
@@ -166,6 +166,8 @@ class BinaryHologramEnv(spaces.Env):
         if seed is not None:
             self.rng = np.random.default_rng(seed)
         self._ensure_engine(float(z), float(pixel_pitch))
+        if self._recon_buf is None:
+            self._recon_buf = pinned_empty((1, self.G, self.Nsim, self.Nsim), np.float32)
         self.episode_num_count += 1
 
         self.target_image, self.current_file = self._next_target()

@@ -20,6 +20,7 @@
  */
 #ifndef BHOLO_H
 #define BHOLO_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -127,6 +128,10 @@ int bh_get_recon(bh_ctx* ctx, int env, float* out, int on_host, int64_t candidat
 int bh_get_state(bh_ctx* ctx, int env, int8_t* out, int on_host);
 /* Field of one frame, complex64 [N][N] as interleaved floats (test hook). */
 int bh_get_field(bh_ctx* ctx, int env, int frame, float* out, int on_host);
+
+/* Page-locked host memory for observation buffers (bh_get_recon then runs at PCIe speed). */
+void* bh_host_alloc(size_t bytes);
+int bh_host_free(void* p);
 
 /* Device pointers of the resident arrays (for zero-copy views): which =
  * 0 U, 1 I, 2 T, 3 state, 4 sums, 5 h, 6 H. */

@@ -635,3 +635,32 @@ def test_group_vec_env_fast_path_matches_per_env_path():
             assert np.array_equal(d1, d2)
     assert len(fast.episode_stats) == len(slow.episode_stats) > 0
     fast.close(); slow.close()
+
+
+def test_batch_step_beyond_inline_limit_and_pinned_obs():
+    """More than 32 envs per step take the copied-task path (bh_step_batch); same results as the oracle."""
+    N, F, E = 32, 4, 40
+    eng = _engine(N, F, O.WL_MONO, n_env=E)
+    cfg = O.HoloConfig(N=N, F=F)
+    refs = []
+    for e in range(E):
+        pre, tgt = bh.synthetic_problem(N, F, 1, 400 + e)
+        eng.set_target(e, tgt)
+        eng.load_state(e, (pre >= 0.5).astype(np.int8))
+        r = O.OracleEnv(cfg, max_steps=10 ** 9, T_PSNR_DIFF=1e9)
+        r.reset(pre, tgt)
+        refs.append(r)
+    rng = np.random.default_rng(2)
+    for step in range(6):
+        acts = rng.integers(0, F * N * N, size=E)
+        res = eng.step_batch(acts, np.arange(E, dtype=np.int32), RULE_ENV)
+        for e in range(E):
+            rew, _, _, p, acc = refs[e].step(int(acts[e]))
+            assert abs(res["psnr_after"][e] - p) < 1e-4
+            if abs(rew) > 800 * 2e-6:
+                assert bool(res["accept"][e]) == acc
+    from binary_hologram_reinforcement_learning_b200.engine import pinned_empty
+    buf = pinned_empty((1, N, N), np.float32)
+    eng.recon(3, -1, out=buf)
+    np.testing.assert_allclose(buf, refs[3].means, atol=3e-5 * refs[3].means.max())
+    eng.close()
