@@ -476,8 +476,9 @@ __device__ __forceinline__ int cta_of_unit(long long u, long long total, int gri
 // shifted impulse response from L2: 16 N^2 algorithmic HBM bytes per candidate.
 // The last CTA to contribute to a task turns the exact sums into the PSNR and
 // the accept decision.
-__global__ void __launch_bounds__(256, 4)
-k_eval(const DeltaArgs a) {
+template <int UF, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_eval_t(const DeltaArgs a) {
     __shared__ long long sh[2][8];
     __shared__ unsigned s_ticket;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -515,16 +516,18 @@ k_eval(const DeltaArgs a) {
         long long aII = 0, aIT = 0;
         Cursor cu; cu.init(int(u - t_beg), tid, N);
         long long v = u;
-        for (; v + 1 < seg_end; v += 2) {            // two units in flight per thread
-            Quad q0, q1;
-            load_quad<true>(q0, U, I, T, h, cu, N, P, d.r, d.c, pf, pl); cu.next(a);
-            load_quad<true>(q1, U, I, T, h, cu, N, P, d.r, d.c, pf, pl); cu.next(a);
-            eval_quad(q0, s2, invFg, aII, aIT);
-            eval_quad(q1, s2, invFg, aII, aIT);
+        for (; v + UF <= seg_end; v += UF) {         // UF units in flight per thread
+            Quad q[UF];
+#pragma unroll
+            for (int i = 0; i < UF; ++i) {
+                load_quad<true>(q[i], U, I, T, h, cu, N, P, d.r, d.c, pf, pl); cu.next(a);
+            }
+#pragma unroll
+            for (int i = 0; i < UF; ++i) eval_quad(q[i], s2, invFg, aII, aIT);
         }
-        if (v < seg_end) {
+        for (; v < seg_end; ++v) {
             Quad q0;
-            load_quad<true>(q0, U, I, T, h, cu, N, P, d.r, d.c, pf, pl);
+            load_quad<true>(q0, U, I, T, h, cu, N, P, d.r, d.c, pf, pl); cu.next(a);
             eval_quad(q0, s2, invFg, aII, aIT);
         }
         aII = warp_sum_ll(aII); aIT = warp_sum_ll(aIT);

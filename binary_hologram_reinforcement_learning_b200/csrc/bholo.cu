@@ -56,6 +56,7 @@ struct bh_ctx {
     Result* h_results_dev = nullptr;     // device alias of the mapped h_results
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_eval = nullptr;
     cudaStream_t own_stream = nullptr;   // capture needs a real stream when the caller gave none
+    void (*k_eval)(const DeltaArgs) = nullptr;
     int64_t launches = 0;
     std::string err;
 };
@@ -184,6 +185,19 @@ static int propagate_env(bh_ctx* c, int env, float* pass_ms = nullptr) {
     return 0;
 }
 
+// k_eval variants: units in flight per thread x CTAs per SM.  Measured at 1024^2 x 24, 8 candidates
+// per launch (scripts/tune_eval.py, profiles/r1_notes.md): <2,4> 28.6 us, <4,2> 27.4, <2,3> 27.9,
+// <3,2> 27.3 (default), 1 CTA/SM variants 33-35 us.  BHOLO_EVAL_VARIANT selects another one.
+typedef void (*eval_fn)(const DeltaArgs);
+static eval_fn eval_variant(int v) {
+    switch (v) {
+        case 1: return k_eval_t<2, 4>;
+        case 2: return k_eval_t<4, 2>;
+        case 3: return k_eval_t<2, 3>;
+        default: return k_eval_t<3, 2>;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
@@ -290,7 +304,9 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
         auto tw = build_twiddles(c->P);
         BH_TRY(cudaMemcpy(c->dtw, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice));
         int nb = 0;
-        BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eval, 256, 0));
+        const char* ev = std::getenv("BHOLO_EVAL_VARIANT");
+        c->k_eval = eval_variant(ev ? std::atoi(ev) : 0);
+        BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, c->k_eval, 256, 0));
         c->grid_cap = std::max(1, nb) * prop.multiProcessorCount;
         BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_commit, 256, 0));
         c->grid_cap_commit = std::max(1, nb) * prop.multiProcessorCount;
@@ -384,7 +400,7 @@ static inline int delta_grid(const bh_ctx* c, int n) {
 }
 
 static int launch_eval(bh_ctx* c, const DeltaArgs& a) {
-    k_eval<<<delta_grid(c, a.n_tasks), 256, 0, c->stream>>>(a);
+    c->k_eval<<<delta_grid(c, a.n_tasks), 256, 0, c->stream>>>(a);
     c->launches += 1;
     return 0;
 }
