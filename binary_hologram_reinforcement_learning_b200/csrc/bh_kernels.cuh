@@ -405,6 +405,15 @@ __device__ __forceinline__ float2 ld_keep2(const float2* p, uint64_t pol) {
     return v;
 }
 
+// Programmatic dependent launch: the step path is a chain eval -> commit -> eval ... of grids
+// that each fill the machine in one wave.  Every kernel waits for its predecessor's memory
+// (griddepcontrol.wait) and immediately lets its successor be scheduled, so the successor's
+// CTAs land on SMs as this grid's tail drains and the launch latency disappears from the chain.
+__device__ __forceinline__ void pdl_wait_then_release() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 struct Quad {                      // operands of 4 consecutive pixels
     float4 ua, ub, iv, tv;
     float2 h0, h1, h2, h3;
@@ -481,6 +490,7 @@ __global__ void __launch_bounds__(256, MINB)
 k_eval_t(const DeltaArgs a) {
     __shared__ long long sh[2][8];
     __shared__ unsigned s_ticket;
+    pdl_wait_then_release();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = a.N, P = a.P, upt = a.units_per_task;
     const long long total = (long long)a.n_tasks * upt;
@@ -578,11 +588,30 @@ k_eval_t(const DeltaArgs a) {
 // then the balanced unit partition runs over the accepted ones only, so a
 // launch with one accepted flip out of K still uses the whole chip.
 constexpr int COMMIT_MAX_TASKS = 256;
-__global__ void __launch_bounds__(256)
-k_commit(const DeltaArgs a) {
+
+__device__ __forceinline__ void commit_quad(const Quad& q, float2* U, float* I, size_t p, float s2,
+                                            float sg, float invFg) {
+    float4 iv = q.iv, ua = q.ua, ub = q.ub;
+    iv.x += delta_px(ua.x, ua.y, q.h0.x, q.h0.y, s2, invFg);
+    iv.y += delta_px(ua.z, ua.w, q.h1.x, q.h1.y, s2, invFg);
+    iv.z += delta_px(ub.x, ub.y, q.h2.x, q.h2.y, s2, invFg);
+    iv.w += delta_px(ub.z, ub.w, q.h3.x, q.h3.y, s2, invFg);
+    ua.x = fmaf(sg, q.h0.x, ua.x); ua.y = fmaf(sg, q.h0.y, ua.y);
+    ua.z = fmaf(sg, q.h1.x, ua.z); ua.w = fmaf(sg, q.h1.y, ua.w);
+    ub.x = fmaf(sg, q.h2.x, ub.x); ub.y = fmaf(sg, q.h2.y, ub.y);
+    ub.z = fmaf(sg, q.h3.x, ub.z); ub.w = fmaf(sg, q.h3.y, ub.w);
+    float4* Up = reinterpret_cast<float4*>(U + p);
+    Up[0] = ua; Up[1] = ub;
+    *reinterpret_cast<float4*>(I + p) = iv;
+}
+
+template <int UF, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_commit_t(const DeltaArgs a) {
     __shared__ int s_list[COMMIT_MAX_TASKS];
     __shared__ int s_cnt;
     const int tid = threadIdx.x;
+    pdl_wait_then_release();
     if (tid == 0) {
         int n = 0;
         if (a.dbs_cursor) {
@@ -638,22 +667,23 @@ k_commit(const DeltaArgs a) {
         const float2* h = a.h + size_t(d.g) * P * P;
         const float s2 = 2.f * d.sgn * invFg, sg = d.sgn;
         Cursor cu; cu.init(int(u - t_beg), tid, N);
-        for (long long v = u; v < seg_end; ++v) {
+        long long v = u;
+        for (; v + UF <= seg_end; v += UF) {
+            Quad q[UF];
+            size_t p[UF];
+#pragma unroll
+            for (int i = 0; i < UF; ++i) {
+                load_quad<false>(q[i], U, I, nullptr, h, cu, N, P, d.r, d.c, pf, pl);
+                p[i] = size_t(cu.y) * N + cu.x;
+                cu.next(a);
+            }
+#pragma unroll
+            for (int i = 0; i < UF; ++i) commit_quad(q[i], U, I, p[i], s2, sg, invFg);
+        }
+        for (; v < seg_end; ++v) {
             Quad q;
             load_quad<false>(q, U, I, nullptr, h, cu, N, P, d.r, d.c, pf, pl);
-            const size_t p = size_t(cu.y) * N + cu.x;
-            float4 iv = q.iv, ua = q.ua, ub = q.ub;
-            iv.x += delta_px(ua.x, ua.y, q.h0.x, q.h0.y, s2, invFg);
-            iv.y += delta_px(ua.z, ua.w, q.h1.x, q.h1.y, s2, invFg);
-            iv.z += delta_px(ub.x, ub.y, q.h2.x, q.h2.y, s2, invFg);
-            iv.w += delta_px(ub.z, ub.w, q.h3.x, q.h3.y, s2, invFg);
-            ua.x = fmaf(sg, q.h0.x, ua.x); ua.y = fmaf(sg, q.h0.y, ua.y);
-            ua.z = fmaf(sg, q.h1.x, ua.z); ua.w = fmaf(sg, q.h1.y, ua.w);
-            ub.x = fmaf(sg, q.h2.x, ub.x); ub.y = fmaf(sg, q.h2.y, ub.y);
-            ub.z = fmaf(sg, q.h3.x, ub.z); ub.w = fmaf(sg, q.h3.y, ub.w);
-            float4* Up = reinterpret_cast<float4*>(U + p);
-            Up[0] = ua; Up[1] = ub;
-            *reinterpret_cast<float4*>(I + p) = iv;
+            commit_quad(q, U, I, size_t(cu.y) * N + cu.x, s2, sg, invFg);
             cu.next(a);
         }
         if (u == t_beg && tid == 0) {

@@ -57,6 +57,8 @@ struct bh_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_eval = nullptr;
     cudaStream_t own_stream = nullptr;   // capture needs a real stream when the caller gave none
     void (*k_eval)(const DeltaArgs) = nullptr;
+    void (*k_commit)(const DeltaArgs) = nullptr;
+    bool use_pdl = true;
     int64_t launches = 0;
     std::string err;
 };
@@ -189,6 +191,16 @@ static int propagate_env(bh_ctx* c, int env, float* pass_ms = nullptr) {
 // per launch (scripts/tune_eval.py, profiles/r1_notes.md): <2,4> 28.6 us, <4,2> 27.4, <2,3> 27.9,
 // <3,2> 27.3 (default), 1 CTA/SM variants 33-35 us.  BHOLO_EVAL_VARIANT selects another one.
 typedef void (*eval_fn)(const DeltaArgs);
+static eval_fn commit_variant(int v) {
+    switch (v) {
+        case 1: return k_commit_t<1, 6>;
+        case 2: return k_commit_t<2, 4>;
+        case 3: return k_commit_t<3, 2>;
+        case 4: return k_commit_t<4, 2>;
+        case 5: return k_commit_t<2, 3>;
+        default: return k_commit_t<3, 2>;
+    }
+}
 static eval_fn eval_variant(int v) {
     switch (v) {
         case 1: return k_eval_t<2, 4>;
@@ -304,11 +316,14 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
         auto tw = build_twiddles(c->P);
         BH_TRY(cudaMemcpy(c->dtw, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice));
         int nb = 0;
+        c->use_pdl = !std::getenv("BHOLO_NO_PDL");
         const char* ev = std::getenv("BHOLO_EVAL_VARIANT");
         c->k_eval = eval_variant(ev ? std::atoi(ev) : 0);
         BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, c->k_eval, 256, 0));
         c->grid_cap = std::max(1, nb) * prop.multiProcessorCount;
-        BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_commit, 256, 0));
+        const char* cv = std::getenv("BHOLO_COMMIT_VARIANT");
+        c->k_commit = commit_variant(cv ? std::atoi(cv) : 0);
+        BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, c->k_commit, 256, 0));
         c->grid_cap_commit = std::max(1, nb) * prop.multiProcessorCount;
     }
 #undef BH_TRY
@@ -399,8 +414,19 @@ static inline int delta_grid(const bh_ctx* c, int n) {
     return int(std::min<long long>(total, c->grid_cap));
 }
 
+// delta kernels are launched with programmatic stream serialization (see pdl_wait_then_release)
+static cudaError_t launch_delta(bh_ctx* c, void (*kern)(const DeltaArgs), int grid, const DeltaArgs& a) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = c->use_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 static int launch_eval(bh_ctx* c, const DeltaArgs& a) {
-    c->k_eval<<<delta_grid(c, a.n_tasks), 256, 0, c->stream>>>(a);
+    launch_delta(c, c->k_eval, delta_grid(c, a.n_tasks), a);
     c->launches += 1;
     return 0;
 }
@@ -413,7 +439,7 @@ static int launch_commit(bh_ctx* c, const DeltaArgs& a0) {
         a.results += base;
         // one accepted task already fills the chip; more only add units
         const int grid = int(std::min<long long>((long long)a.units_per_task, c->grid_cap_commit));
-        k_commit<<<grid, 256, 0, c->stream>>>(a);
+        launch_delta(c, c->k_commit, grid, a);
         c->launches += 1;
     }
     return 0;
