@@ -119,7 +119,8 @@ def ncu_traffic_bytes():
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         with open(path) as f:
-            return json.load(f).get("k_eval_dram_bytes_per_launch")
+            d = json.load(f)
+            return d.get("k_eval_dram_bytes_per_launch_warm_cache", d.get("k_eval_dram_bytes_per_launch"))
     except Exception:
         return None
 
@@ -257,7 +258,7 @@ def run_b200(args):
     n_eager = 64
     t0 = time.perf_counter()
     for i in range(n_eager):
-        vec.step(acts_host[i])
+        vec.step(acts_host[i % len(acts_host)])
         for j in range(E):
             vec.refresh_recon(j)                  # 12.6 MB D2H per env into pinned memory
     torch.cuda.synchronize()

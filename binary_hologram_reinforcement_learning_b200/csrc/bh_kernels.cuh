@@ -37,6 +37,9 @@ struct Result {            // mirrored by bh_result in include/bholo.h (40 bytes
 enum { RULE_ENV = 0, RULE_DBS = 1, RULE_NEVER = 2 };
 
 constexpr int TILE_W = 8;          // sequences per FFT tile
+#ifndef BH_COLS_W
+#define BH_COLS_W 8                // columns per tile of the column pass (experiments: 16)
+#endif
 
 constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
 
@@ -52,7 +55,7 @@ template <int P> struct FftCfg {
     static constexpr size_t smem_row = size_t(SEQ) * TILE_W * sizeof(float2);
     // column pass: 8 columns per tile (64-byte row segments).  16 columns x 1024 threads was
     // measured equal at best (it spills at the 64-register cap), see profiles/r1_notes.md
-    static constexpr int WC = 8;
+    static constexpr int WC = BH_COLS_W;
     static constexpr int TC = WC * Q;
     static constexpr int MINBC = (TC >= 1024) ? 1 : MINB;
     static constexpr size_t smem_col = size_t(SeqLen<P, SKC>::value) * WC * sizeof(float2);
@@ -297,17 +300,28 @@ k_intensity(const float2* __restrict__ U /* group base [Fg][n2] */, float* __res
     }
 }
 
-// fold the G * LOSS_BLOCKS partials in index order -> sums[0..2], PSNR -> sums[3]
-__global__ void k_loss_final(const double* __restrict__ partial, int n_partial, double n_elems,
-                             double* __restrict__ sums, int relative) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// fold the G * LOSS_BLOCKS partials -> sums[0..2], PSNR -> sums[3].  One CTA; thread t adds
+// partials t, t+256, ... in index order and the 256 thread sums meet in a fixed shuffle/tree
+// order, so the result is independent of scheduling.
+__global__ void __launch_bounds__(256)
+k_loss_final(const double* __restrict__ partial, int n_partial, double n_elems,
+             double* __restrict__ sums, int relative) {
+    __shared__ double sh[3][8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double x = 0, y = 0, z = 0;
-    for (int i = 0; i < n_partial; ++i) {
+    for (int i = tid; i < n_partial; i += 256) {
         x += partial[i * 3 + 0]; y += partial[i * 3 + 1]; z += partial[i * 3 + 2];
     }
-    const double mse = relative ? (z - y * y / x) / n_elems : (x - 2.0 * y + z) / n_elems;
-    sums[0] = x; sums[1] = y; sums[2] = z;
-    sums[3] = -10.0 * log10(mse);
+    x = warp_sum(x); y = warp_sum(y); z = warp_sum(z);
+    if (lane == 0) { sh[0][warp] = x; sh[1][warp] = y; sh[2][warp] = z; }
+    __syncthreads();
+    if (tid == 0) {
+        x = y = z = 0;
+        for (int i = 0; i < 8; ++i) { x += sh[0][i]; y += sh[1][i]; z += sh[2][i]; }
+        const double mse = relative ? (z - y * y / x) / n_elems : (x - 2.0 * y + z) / n_elems;
+        sums[0] = x; sums[1] = y; sums[2] = z;
+        sums[3] = -10.0 * log10(mse);
+    }
 }
 
 // ---------------------------------------------------------------------------

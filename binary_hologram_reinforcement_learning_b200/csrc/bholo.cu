@@ -35,7 +35,6 @@ struct bh_ctx {
     int8_t* dstate = nullptr;
     double* dsums = nullptr;
     double* dloss_partial = nullptr;
-    unsigned* dloss_ticket = nullptr;
     int max_tasks = 0, units_per_task = 0, grid_cap = 0, grid_cap_commit = 0;
     int32_t* d_envs = nullptr;
     long long* d_actions = nullptr;
@@ -180,7 +179,7 @@ static int propagate_env(bh_ctx* c, int env, float* pass_ms = nullptr) {
     }
     if (pass_ms)
         for (auto& e : ev) cudaEventDestroy(e);
-    k_loss_final<<<1, 32, 0, c->stream>>>(c->dloss_partial, c->G * LOSS_BLOCKS, double(c->G) * double(n2),
+    k_loss_final<<<1, 256, 0, c->stream>>>(c->dloss_partial, c->G * LOSS_BLOCKS, double(c->G) * double(n2),
                                           c->dsums + size_t(env) * 4, c->relative);
     BH_CUDA(c, cudaGetLastError());
     c->launches += 1;
@@ -219,7 +218,7 @@ extern "C" int bh_destroy(bh_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream); else cudaDeviceSynchronize();
     cudaFree(c->dH); cudaFree(c->dh); cudaFree(c->dtw); cudaFree(c->dU); cudaFree(c->dscratch);
     cudaFree(c->dI); cudaFree(c->dT); cudaFree(c->drecon); cudaFree(c->dstate); cudaFree(c->dsums);
-    cudaFree(c->dloss_partial); cudaFree(c->dloss_ticket);
+    cudaFree(c->dloss_partial);
     cudaFree(c->d_envs); cudaFree(c->d_actions); cudaFree(c->d_results); cudaFree(c->d_acc);
     cudaFree(c->d_tickets); cudaFree(c->d_scalars);
     cudaFree(c->dK3); cudaFree(c->dK4); cudaFree(c->dK5); cudaFree(c->dsw_in); cudaFree(c->dsw_out);
@@ -281,7 +280,6 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
     BH_TRY(cudaMalloc(&c->dstate, size_t(n_env) * F * n2));
     BH_TRY(cudaMalloc(&c->dsums, size_t(n_env) * 4 * sizeof(double)));
     BH_TRY(cudaMalloc(&c->dloss_partial, size_t(G) * LOSS_BLOCKS * 3 * sizeof(double)));
-    BH_TRY(cudaMalloc(&c->dloss_ticket, sizeof(unsigned)));
     c->units_per_task = int(n2 / UNIT_PX);
     c->max_tasks = std::max(4096, n_env);
     BH_TRY(cudaMalloc(&c->d_envs, size_t(c->max_tasks) * sizeof(int32_t)));
@@ -300,7 +298,6 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
     BH_TRY(cudaEventCreate(&c->ev1));
     BH_TRY(cudaEventCreateWithFlags(&c->ev_eval, cudaEventDisableTiming));
     if (rc == 0) {
-        BH_TRY(cudaMemset(c->dloss_ticket, 0, sizeof(unsigned)));
         BH_TRY(cudaMemset(c->d_tickets, 0, size_t(c->max_tasks) * sizeof(unsigned)));
         BH_TRY(cudaMemset(c->d_acc, 0, size_t(c->max_tasks) * 2 * sizeof(unsigned long long)));
         BH_TRY(cudaMemset(c->dsums, 0, size_t(n_env) * 4 * sizeof(double)));

@@ -55,8 +55,8 @@ if os.path.exists(lp):
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"| {k} | {len(v)} | {sum(v):.1f} | {100 * sum(v) / total:.1f}% | {sum(v) / len(v):.2f} | {min(v):.2f} | {max(v):.2f} |\n")
         # share inside one env step: consecutive k_eval, k_commit pairs
-        ev = [x for x in agg.get("k_eval", [])]
-        cm = [x for x in agg.get("k_commit", [])]
+        ev = [x for k, v in agg.items() if k.startswith("k_eval") for x in v]
+        cm = [x for k, v in agg.items() if k.startswith("k_commit") for x in v]
         if ev and cm:
             f.write(f"\nInside an env step (k_eval + k_commit): k_eval mean {sum(ev) / len(ev):.2f} us, "
                     f"k_commit mean {sum(cm) / len(cm):.2f} us -> k_eval share "
@@ -65,6 +65,7 @@ if os.path.exists(lp):
 
 # ---- full capture ------------------------------------------------------------
 rp = os.path.join(ROOT, "gpurun_out", "prof_hotpath.ncu-rep")
+EXTRA = [("prof_prop.ncu-rep", "propagation"), ("prof_eval_warm.ncu-rep", "eval_warm_cache")]
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -85,7 +86,7 @@ if os.path.exists(rp):
         for r in data:
             w.writerow([short(r[ik])] + [r[i] for i in idx.values()])
     # per-launch DRAM traffic of k_eval (steady-state launches)
-    ev = [r for r in data if short(r[ik]) == "k_eval"]
+    ev = [r for r in data if short(r[ik]).startswith("k_eval")]
     if ev:
         def mb(r, key):
             i = hdr.index(key)
@@ -99,3 +100,33 @@ if os.path.exists(rp):
                    "source": f"profiles/{tag}_hotpath_metrics.csv (ncu --set full, 8 candidates per launch)"},
                   open(os.path.join(out_dir, "roofline_traffic.json"), "w"), indent=1)
     print("wrote hotpath metrics:", len(data), "launches")
+
+for fname, label in EXTRA:
+    path = os.path.join(ROOT, "gpurun_out", fname)
+    if not os.path.exists(path):
+        continue
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    if len(rows) < 3:
+        continue
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {k: hdr.index(k) for k in KEYS if k in hdr}
+    ik = hdr.index("Kernel Name")
+    with open(os.path.join(out_dir, f"{tag}_{label}_metrics.csv"), "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["kernel"] + [f"{k} [{units[i]}]" for k, i in idx.items()])
+        for r in data:
+            w.writerow([short(r[ik])] + [r[i] for i in idx.values()])
+    if label == "eval_warm_cache":
+        def mb(r, key):
+            i = hdr.index(key)
+            v = float(r[i].replace(",", ""))
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(units[i].lower(), 1)
+        tr = [mb(r, "dram__bytes_read.sum") + mb(r, "dram__bytes_write.sum") for r in data]
+        tp = os.path.join(out_dir, "roofline_traffic.json")
+        cur = json.load(open(tp)) if os.path.exists(tp) else {}
+        cur["k_eval_dram_bytes_per_launch_warm_cache"] = sum(tr) / len(tr)
+        cur["note"] = ("cold = ncu default cache control (L2 flushed before every replay: the 25 MB impulse "
+                       "table is re-read from DRAM); warm = --cache-control none (h stays L2 resident as in the live run)")
+        json.dump(cur, open(tp, "w"), indent=1)
+    print("wrote", label, len(data), "launches")

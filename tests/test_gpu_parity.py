@@ -664,3 +664,22 @@ def test_batch_step_beyond_inline_limit_and_pinned_obs():
     eng.recon(3, -1, out=buf)
     np.testing.assert_allclose(buf, refs[3].means, atol=3e-5 * refs[3].means.max())
     eng.close()
+
+
+def test_sharded_sweep_equals_full_sweep():
+    """Candidate ranges sharded over ranks: the concatenated shards are the full sweep, bit for bit."""
+    N, F, m = 80, 6, 8
+    def run(shard):
+        ld = bh.SyntheticLoader(N, F, 3, seeds=(71,))
+        return bh.dbs_sweep(ld.target_function, ld, 2e-3, 7.56e-6, m, CH=F, max_datasets=0,
+                            rng=np.random.default_rng(9), verbose=False, shard=shard)[0]
+    full = run(None)
+    parts = [run((r, 3)) for r in range(3)]
+    assert np.array_equal(np.concatenate([p["order"] for p in parts]), full["order"])
+    assert np.array_equal(np.concatenate([p["psnr_after"] for p in parts]), full["psnr_after"])
+    for key in ("attempted", "improved"):
+        assert np.array_equal(sum(p[key] for p in parts), full[key])
+    np.testing.assert_allclose(sum(p["gains"] for p in parts), full["gains"], rtol=1e-12)
+    # a shard small enough to take the delta-kernel path agrees with the correlation map
+    small = run((0, 64))
+    np.testing.assert_allclose(small["psnr_after"], full["psnr_after"][:small["steps"]], rtol=0, atol=1e-8)

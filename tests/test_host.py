@@ -164,3 +164,28 @@ def test_image_folder_loader(tmp_path):
     assert np.array_equal(t[0], full[:, 8:72, 18:82])       # centre crop
     g = next(iter(bh.ImageFolderLoader(str(tmp_path), 32, gray=True, random_crop=True, seed=3)))[0]
     assert g.shape == (1, 1, 32, 32)
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference: exactly one JSON line on stdout with the contract's keys (CPU only)."""
+    import json
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and d["vs_baseline"] is None
+
+
+def test_sweep_shard_partition_is_a_partition():
+    """dbs_sweep(shard=(rank, world)) slices one globally defined order."""
+    n, world = 1000, 8
+    per = (n + world - 1) // world
+    cover = np.concatenate([np.arange(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)])
+    assert np.array_equal(cover, np.arange(n))
+    assert [dist.shard_range(n, r, world) for r in range(world)] == \
+        [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
