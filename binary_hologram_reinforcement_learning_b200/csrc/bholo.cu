@@ -561,6 +561,38 @@ extern "C" int bh_step_batch(bh_ctx* c, int n, const int32_t* env_ids, const int
     return 0;
 }
 
+extern "C" int bh_vec_step(bh_ctx* c, int n, const int32_t* env_ids, const int64_t* actions, int rule,
+                           bh_result* results, const bh_vec_book* b) {
+    if (!b || !b->prev_psnr || !b->init_psnr || !b->steps || !b->flips || !b->rewards)
+        BH_FAIL(c, -1, "incomplete bh_vec_book");
+    if (int rc = bh_step_batch(c, n, env_ids, actions, rule, results)) return rc;
+    for (int i = 0; i < n; ++i) {
+        const int e = env_ids ? env_ids[i] : i;
+        const bh_result& r = results[i];
+        const int64_t a = actions[i];
+        b->steps[e] += 1;
+        if (b->state_record) b->state_record[size_t(e) * b->stride + a] += 1;      // env.py:165
+        const double change = r.psnr_after - b->prev_psnr[e];                      // env.py:184
+        const double diff = r.psnr_after - b->init_psnr[e];
+        b->rewards[i] = change * b->reward_scale;                                   // env.py:188
+        if (b->psnr_change) b->psnr_change[i] = change;
+        if (b->psnr_diff) b->psnr_diff[i] = diff;
+        uint8_t ev = 0;
+        if (r.accept) {
+            if (b->state) b->state[size_t(e) * b->stride + a] ^= 1;                 // env.py:164
+            b->flips[e] += 1;
+            b->prev_psnr[e] = r.psnr_after;                                         // env.py:214
+            const bool success = b->t_psnr_diff && b->t_psnr &&
+                (diff >= b->t_psnr_diff[e] || (r.psnr_after >= b->t_psnr[e] && diff < 0.1));
+            const bool over = b->max_steps && b->steps[e] >= b->max_steps[e];
+            ev = (success || over) ? 1 : 0;                                          // env.py:216,237
+        }
+        if (b->last_candidate) b->last_candidate[e] = r.accept ? -1 : a;
+        if (b->event) b->event[i] = ev;
+    }
+    return 0;
+}
+
 extern "C" int bh_commit_flip(bh_ctx* c, int env, int64_t action) {
     BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
     if (int rc = check_actions(c, &action, 1)) return rc;

@@ -20,7 +20,7 @@ METHOD_ASM, METHOD_FRESNEL = 0, 1
 ABI_SYMBOLS = (
     "bh_abi_version", "bh_last_error", "bh_create", "bh_destroy", "bh_set_stream",
     "bh_set_target", "bh_load_state", "bh_resync", "bh_get_metrics", "bh_eval_flips",
-    "bh_step_batch", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
+    "bh_step_batch", "bh_vec_step", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
     "bh_commit_flip", "bh_dbs_run", "bh_sweep_all", "bh_get_recon", "bh_get_state", "bh_get_field",
     "bh_device_ptr", "bh_host_alloc", "bh_host_free", "bh_simulate", "bh_time_eval", "bh_time_propagate", "bh_time_propagate_passes", "bh_launch_count",
 )
@@ -35,6 +35,16 @@ class BhResult(C.Structure):
 RESULT_DTYPE = np.dtype([("psnr_after", "<f8"), ("d_sii", "<f8"), ("d_sit", "<f8"),
                          ("action", "<i8"), ("accept", "<i4"), ("sgn", "<i4")])
 assert RESULT_DTYPE.itemsize == C.sizeof(BhResult) == 40
+
+
+class VecBook(C.Structure):
+    """Mirror of ``bh_vec_book`` (host arrays updated by ``bh_vec_step``)."""
+    _fields_ = [("state", C.c_void_p), ("state_record", C.c_void_p), ("stride", C.c_int64),
+                ("prev_psnr", C.c_void_p), ("init_psnr", C.c_void_p), ("steps", C.c_void_p),
+                ("flips", C.c_void_p), ("t_psnr_diff", C.c_void_p), ("t_psnr", C.c_void_p),
+                ("max_steps", C.c_void_p), ("reward_scale", C.c_double), ("rewards", C.c_void_p),
+                ("psnr_change", C.c_void_p), ("psnr_diff", C.c_void_p),
+                ("last_candidate", C.c_void_p), ("event", C.c_void_p)]
 
 
 class HoloError(RuntimeError):
@@ -73,6 +83,7 @@ def load_library(build_if_missing: bool = True):
         "bh_get_metrics": (i32, [vp, i32, P(dbl), P(dbl), P(dbl)]),
         "bh_eval_flips": (i32, [vp, i32, i64, vp, vp, vp]),
         "bh_step_batch": (i32, [vp, i32, vp, vp, i32, vp]),
+        "bh_vec_step": (i32, [vp, i32, vp, vp, i32, vp, vp]),
         "bh_step_batch_device": (i32, [vp, i32, vp, vp, i32, vp]),
         "bh_eval_flips_device": (i32, [vp, i32, i32, vp, vp, vp]),
         "bh_max_tasks": (i32, [vp]),
@@ -230,6 +241,15 @@ class HoloEngine:
             out = np.empty(a.shape[0], dtype=RESULT_DTYPE)
         self._check(self.lib.bh_step_batch(self._h, a.shape[0], _ptr(e), _ptr(a), rule, _ptr(out)),
                     "bh_step_batch")
+        return out
+
+    def vec_step(self, actions: np.ndarray, env_ids: np.ndarray, rule: int, out: np.ndarray,
+                 book: "VecBook"):
+        """One vectorised env step incl. the host bookkeeping (arrays must be C-contiguous)."""
+        rc = self.lib.bh_vec_step(self._h, actions.shape[0], env_ids.ctypes.data, actions.ctypes.data,
+                                  rule, out.ctypes.data, C.addressof(book))
+        if rc != 0:
+            self._check(rc, "bh_vec_step")
         return out
 
     def step_batch_device(self, n: int, d_env_ids: int, d_actions: int, rule: int, d_results: int):

@@ -14,7 +14,7 @@ from typing import Callable, Iterable, List, Optional, Sequence
 
 import numpy as np
 
-from .engine import HoloEngine, RULE_ENV, RESULT_DTYPE
+from .engine import HoloEngine, RULE_ENV, RESULT_DTYPE, VecBook
 from .envs import BinaryHologramEnv, WL_MONO, RW, goal_bonus
 
 
@@ -69,6 +69,12 @@ class HologramVecEnv:
         self._tpsnr = np.full(E, float(T_PSNR))
         self._maxsteps = np.full(E, int(max_steps), dtype=np.int64)
         self._obs_cache = [None] * E
+        self._rewards = np.zeros(E)
+        self._change = np.zeros(E)
+        self._diff = np.zeros(E)
+        self._event = np.zeros(E, dtype=np.uint8)
+        self._no_done = np.zeros(E, dtype=bool)
+        self._book = None
 
     # ------------------------------------------------------------------
     def _pack(self, obs_list):
@@ -85,6 +91,17 @@ class HologramVecEnv:
             self._record = np.zeros(shape, dtype=np.int8)
             self._state2d = self._state.reshape(self.num_envs, -1)
             self._record2d = self._record.reshape(self.num_envs, -1)
+            b = VecBook()
+            b.state, b.state_record = self._state.ctypes.data, self._record.ctypes.data
+            b.stride = self._state2d.shape[1]
+            b.prev_psnr, b.init_psnr = self._prev.ctypes.data, self._init.ctypes.data
+            b.steps, b.flips = self._steps.ctypes.data, self._flips.ctypes.data
+            b.t_psnr_diff, b.t_psnr = self._tdiff.ctypes.data, self._tpsnr.ctypes.data
+            b.max_steps, b.reward_scale = self._maxsteps.ctypes.data, float(RW)
+            b.rewards, b.psnr_change, b.psnr_diff = (self._rewards.ctypes.data, self._change.ctypes.data,
+                                                     self._diff.ctypes.data)
+            b.last_candidate, b.event = self._last_cand.ctypes.data, self._event.ctypes.data
+            self._book = b
         self._state[i] = env.state
         self._record[i] = env.state_record
         env.state, env.state_record = self._state[i], self._record[i]
@@ -130,29 +147,26 @@ class HologramVecEnv:
     def _step_fast(self):
         """env.py:154-260 for all envs with numpy; per-env Python only on episode events."""
         acts, envs, E = self._actions, self.envs, self.num_envs
-        res = self.engine.step_batch(acts, self._eids, RULE_ENV, out=self._res)
-        acc = res["accept"] != 0
+        # scoring on the GPU + mirrors, counters, psnr_change, reward, event mask in one foreign call
+        res = self.engine.vec_step(acts, self._eids, RULE_ENV, self._res, self._book)
         psnr_after = res["psnr_after"]
-        self._steps += 1
-        self._record2d[self._ar, acts] += 1                          # env.py:165
-        change = psnr_after - self._prev                             # env.py:184-188
-        diff = psnr_after - self._init
+        diff = self._diff
         if self._group:                                              # env_group.py:254-255
-            idx = np.abs(self._changes - change[:, None]).argmin(axis=1)
+            idx = np.abs(self._changes - self._change[:, None]).argmin(axis=1)
             rewards = self._ranks[self._ar, idx].copy()
         else:
-            rewards = change * RW
-        self._state2d[self._ar[acc], acts[acc]] ^= 1                 # env.py:164 / 191-193
-        self._flips += acc
-        self._prev[acc] = psnr_after[acc]                            # env.py:214
-        dones = np.zeros(E, dtype=bool)
+            rewards = self._rewards.copy()                           # env.py:188
         infos = [{} for _ in range(E)]
-        self._last_cand = np.where(acc, -1, acts)
-        event = acc & ((diff >= self._tdiff) | ((psnr_after >= self._tpsnr) & (diff < 0.1))
-                       | (self._steps >= self._maxsteps))
         if envs[0].resync_every > 0:
-            for i in np.flatnonzero(acc & (self._flips % envs[0].resync_every == 0)):
-                self.engine.resync(int(i))
+            acc = res["accept"] != 0
+            if acc.any():
+                for i in np.flatnonzero(acc & (self._flips % envs[0].resync_every == 0)):
+                    self.engine.resync(int(i))
+        if not self._event.any():
+            self._ep_reward += rewards
+            return self._pack(self._obs_cache), rewards, self._no_done.copy(), infos
+        dones = np.zeros(E, dtype=bool)
+        event = self._event
         for i in np.flatnonzero(event):                              # env.py:216-260
             env = envs[i]
             ratio = self._flips[i] / self._steps[i]
@@ -179,7 +193,7 @@ class HologramVecEnv:
         return self._pack(self._obs_cache), rewards, dones, infos
 
     def step_async(self, actions):
-        self._actions = np.asarray(actions, dtype=np.int64).reshape(self.num_envs)
+        self._actions = np.ascontiguousarray(actions, dtype=np.int64).reshape(self.num_envs)
 
     def step_wait(self):
         if self._fast:

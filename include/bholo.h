@@ -98,6 +98,35 @@ int bh_sweep_all(bh_ctx* ctx, int env, double* psnr_after, int on_host);
 int bh_step_batch(bh_ctx* ctx, int n, const int32_t* env_ids, const int64_t* actions,
                   int rule, bh_result* results);
 
+/* Host-side bookkeeping of a vectorised env step (env.py:158-167,184-196,214), done in the
+ * same call so that an E-env step is one foreign call.  All arrays are HOST arrays of n
+ * entries indexed like env_ids (state / state_record: [E][stride] int8 mirrors indexed by
+ * env id).  After the flips are scored: steps += 1; state_record[action] += 1; psnr_change =
+ * psnr_after - prev_psnr; rewards = psnr_change * reward_scale; kept flips toggle the state
+ * mirror, count in flips and move prev_psnr; event[i] = 1 where the success / max_steps
+ * branches of env.py:216-254 have to run (evaluated by the caller). */
+typedef struct bh_vec_book {
+    int8_t*        state;           /* may be NULL */
+    int8_t*        state_record;    /* may be NULL */
+    int64_t        stride;          /* elements per env in the two mirrors */
+    double*        prev_psnr;       /* [E] in/out, indexed by env id */
+    const double*  init_psnr;       /* [E] */
+    int64_t*       steps;           /* [E] in/out */
+    int64_t*       flips;           /* [E] in/out */
+    const double*  t_psnr_diff;     /* [E] */
+    const double*  t_psnr;          /* [E] */
+    const int64_t* max_steps;       /* [E] */
+    double         reward_scale;    /* RW = 800 (env.py:29) */
+    double*        rewards;         /* [n] out */
+    double*        psnr_change;     /* [n] out */
+    double*        psnr_diff;       /* [n] out: psnr_after - init_psnr */
+    int64_t*       last_candidate;  /* [E] out: -1 if kept, else the rejected action */
+    uint8_t*       event;           /* [n] out */
+} bh_vec_book;
+
+int bh_vec_step(bh_ctx* ctx, int n, const int32_t* env_ids, const int64_t* actions, int rule,
+                bh_result* results, const bh_vec_book* book);
+
 /* Same with DEVICE pointers and no synchronisation (inputs resident in HBM). */
 int bh_step_batch_device(bh_ctx* ctx, int n, const int32_t* d_env_ids,
                          const int64_t* d_actions, int rule, bh_result* d_results);
