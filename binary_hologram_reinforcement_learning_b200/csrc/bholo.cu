@@ -369,6 +369,19 @@ extern "C" int bh_load_state(bh_ctx* c, int env, const int8_t* state, int on_hos
     return 0;
 }
 
+extern "C" int bh_clone_env(bh_ctx* c, int src, int dst) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, src); BH_CHECK_ENV(c, dst);
+    if (src == dst) return 0;
+    const size_t n2 = c->n2;
+    const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
+    BH_CUDA(c, cudaMemcpyAsync(c->dU + size_t(dst) * c->F * n2, c->dU + size_t(src) * c->F * n2, size_t(c->F) * n2 * sizeof(float2), k, c->stream));
+    BH_CUDA(c, cudaMemcpyAsync(c->dI + size_t(dst) * c->G * n2, c->dI + size_t(src) * c->G * n2, size_t(c->G) * n2 * sizeof(float), k, c->stream));
+    BH_CUDA(c, cudaMemcpyAsync(c->dT + size_t(dst) * c->G * n2, c->dT + size_t(src) * c->G * n2, size_t(c->G) * n2 * sizeof(float), k, c->stream));
+    BH_CUDA(c, cudaMemcpyAsync(c->dstate + size_t(dst) * c->F * n2, c->dstate + size_t(src) * c->F * n2, size_t(c->F) * n2, k, c->stream));
+    BH_CUDA(c, cudaMemcpyAsync(c->dsums + size_t(dst) * 4, c->dsums + size_t(src) * 4, 4 * sizeof(double), k, c->stream));
+    return 0;
+}
+
 extern "C" int bh_resync(bh_ctx* c, int env) {
     BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
     return propagate_env(c, env);

@@ -19,7 +19,7 @@ METHOD_ASM, METHOD_FRESNEL = 0, 1
 # every symbol include/bholo.h declares
 ABI_SYMBOLS = (
     "bh_abi_version", "bh_last_error", "bh_create", "bh_destroy", "bh_set_stream",
-    "bh_set_target", "bh_load_state", "bh_resync", "bh_get_metrics", "bh_eval_flips",
+    "bh_set_target", "bh_load_state", "bh_clone_env", "bh_resync", "bh_get_metrics", "bh_eval_flips",
     "bh_step_batch", "bh_vec_step", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
     "bh_commit_flip", "bh_dbs_run", "bh_sweep_all", "bh_get_recon", "bh_get_state", "bh_get_field",
     "bh_device_ptr", "bh_host_alloc", "bh_host_free", "bh_simulate", "bh_time_eval", "bh_time_propagate", "bh_time_propagate_passes", "bh_launch_count",
@@ -80,6 +80,7 @@ def load_library(build_if_missing: bool = True):
         "bh_set_target": (i32, [vp, i32, vp, i32]),
         "bh_load_state": (i32, [vp, i32, vp, i32]),
         "bh_resync": (i32, [vp, i32]),
+        "bh_clone_env": (i32, [vp, i32, i32]),
         "bh_get_metrics": (i32, [vp, i32, P(dbl), P(dbl), P(dbl)]),
         "bh_eval_flips": (i32, [vp, i32, i64, vp, vp, vp]),
         "bh_step_batch": (i32, [vp, i32, vp, vp, i32, vp]),
@@ -212,6 +213,10 @@ class HoloEngine:
     def load_state(self, env: int, state: np.ndarray):
         s = np.ascontiguousarray(state, dtype=np.int8).reshape(self.F, self.N, self.N)
         self._check(self.lib.bh_load_state(self._h, env, _ptr(s), 1), "bh_load_state")
+
+    def clone_env(self, src: int, dst: int):
+        """Device-side copy of one env's complete state (group rollouts from one reset state)."""
+        self._check(self.lib.bh_clone_env(self._h, src, dst), "bh_clone_env")
 
     def resync(self, env: int):
         self._check(self.lib.bh_resync(self._h, env), "bh_resync")

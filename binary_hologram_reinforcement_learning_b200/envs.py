@@ -219,6 +219,34 @@ class BinaryHologramEnv(spaces.Env):
         self.total_start_time = time.time()
         return obs, {"state": self.state}
 
+    def clone_from(self, leader: "BinaryHologramEnv"):
+        """Start an episode from ``leader``'s freshly reset state without propagating again.
+
+        Group rollouts (env_group.py + GRPO-style groups): M members share one target and one
+        initial hologram; the device state is copied (bh_clone_env), the host mirrors are copied,
+        and for the rank-table reward the leader's 10 000-candidate table is shared.
+        """
+        if leader._engine is not self._engine:
+            raise ValueError("clone_from needs envs that share one engine")
+        self.episode_num_count += 1
+        self.target_image, self.current_file = leader.target_image, leader.current_file
+        self.target_image_np, self.observation = leader.target_image_np, leader.observation
+        self.state, self.state_record = leader.state.copy(), np.zeros_like(leader.state)
+        self.max_psnr_diff = float("-inf")
+        self.steps = self.flip_count = self.psnr_sustained_steps = 0
+        self.initial_psnr = self.previous_psnr = leader.initial_psnr
+        self._commits, self._last_candidate = 0, -1
+        self._engine.clone_env(leader._e, self._e)
+        if self._recon_buf is None:
+            self._recon_buf = pinned_empty((1, self.G, self.Nsim, self.Nsim), np.float32)
+        self._recon_buf[...] = leader._recon_buf
+        if self.reward_mode == "group":
+            self.psnr_change_list, self.importance_ranks = leader.psnr_change_list, leader.importance_ranks
+            self._psnr_change_arr, self.T_PSNR_DIFF = leader._psnr_change_arr, leader.T_PSNR_DIFF
+        self.next_print_thresholds = [self.initial_psnr + i * 0.01 for i in range(1, 21)]
+        self.total_start_time = time.time()
+        return self._obs(), {"state": self.state}
+
     def _obs(self):
         return {"state_record": self.state_record,                   # env.py:135-140
                 "state": self.state,

@@ -144,6 +144,24 @@ class HologramVecEnv:
         self._ep_reward[:] = 0
         return self._pack(obs)
 
+    def reset_groups(self, group_size: int):
+        """GRPO-style groups: envs [k*M, (k+1)*M) start from the reset state of env k*M.
+
+        Only the leaders load a target, run the initial-hologram function, propagate and (for
+        the rank-table reward) score their candidates; members are device-side clones.
+        """
+        if self.num_envs % group_size:
+            raise ValueError("num_envs must be a multiple of group_size")
+        obs = [None] * self.num_envs
+        for lead in range(0, self.num_envs, group_size):
+            obs[lead] = self._reset_env(lead)
+            for m in range(lead + 1, lead + group_size):
+                self.envs[m].clone_from(self.envs[lead])
+                self._adopt(m)
+                obs[m] = self.envs[m]._obs()
+        self._ep_reward[:] = 0
+        return self._pack(obs)
+
     def _step_fast(self):
         """env.py:154-260 for all envs with numpy; per-env Python only on episode events."""
         acts, envs, E = self._actions, self.envs, self.num_envs

@@ -69,6 +69,11 @@ int bh_set_target(bh_ctx* ctx, int env, const float* target, int on_host);
  * (env.py:123-132; env_1024_24.py:140-166).  Fills U, I and the loss sums. */
 int bh_load_state(bh_ctx* ctx, int env, const int8_t* state, int on_host);
 
+/* Copy the complete device state of env src (target, hologram, fields, reconstruction, loss
+ * sums) to env dst: group rollouts that start from one reset state (env_group.py + GRPO-style
+ * groups) pay one propagation per group, not per member. */
+int bh_clone_env(bh_ctx* ctx, int src, int dst);
+
 /* Re-propagate from the device-resident state (bounds fp32 drift of the
  * incremental updates); same arithmetic as bh_load_state. */
 int bh_resync(bh_ctx* ctx, int env);

@@ -25,13 +25,18 @@ from . import hologram_oracle as O
 class TorchRefEnv:
     """Single env, full re-simulation of the flipped colour group per step, fp32."""
 
-    def __init__(self, N, F, wl, dx=O.PIXEL_PITCH, z=O.Z_DEFAULT, pad=1, relative=True, threads=None):
+    def __init__(self, N, F, wl, dx=O.PIXEL_PITCH, z=O.Z_DEFAULT, pad=1, relative=True, threads=None,
+                 device="cpu"):
+        """device="cuda" gives the "reference simply run on a GPU" comparator: torch.fft (cuFFT),
+        the whole colour group re-uploaded every step (env.py:170) and a blocking .item()."""
         if threads:
             torch.set_num_threads(int(threads))
         self.N, self.F, self.wl, self.G = N, F, tuple(wl), len(wl)
         self.Fg, self.pad, self.relative = F // len(wl), pad, relative
+        self.device = torch.device(device)
         P = N * pad
-        self.H = [torch.from_numpy(O.transfer_function(P, dx, w, z).astype(np.complex64)) for w in wl]
+        self.H = [torch.from_numpy(O.transfer_function(P, dx, w, z).astype(np.complex64)).to(self.device)
+                  for w in wl]
 
     def simulate(self, x: torch.Tensor, g: int) -> torch.Tensor:
         """tt.simulate on a (1, Fg, N, N) float tensor."""
@@ -39,7 +44,7 @@ class TorchRefEnv:
         if self.pad == 1:
             return torch.fft.ifft2(torch.fft.fft2(x) * self.H[g])
         o = (P - N) // 2
-        canvas = torch.zeros(x.shape[:-2] + (P, P), dtype=x.dtype)
+        canvas = torch.zeros(x.shape[:-2] + (P, P), dtype=x.dtype, device=x.device)
         canvas[..., o:o + N, o:o + N] = x
         return torch.fft.ifft2(torch.fft.fft2(canvas) * self.H[g])[..., o:o + N, o:o + N]
 
@@ -52,11 +57,11 @@ class TorchRefEnv:
 
     def reset(self, pre_model: np.ndarray, target: np.ndarray):
         self.state = (pre_model >= 0.5).astype(np.int8)[None]           # env.py:120
-        self.target = torch.from_numpy(np.ascontiguousarray(target, dtype=np.float32))[None]
+        self.target = torch.from_numpy(np.ascontiguousarray(target, dtype=np.float32))[None].to(self.device)
         Fg = self.Fg
         self.means = []
         for g in range(self.G):                                          # env_1024_24.py:149-159
-            x = torch.tensor(self.state[:, g * Fg:(g + 1) * Fg], dtype=torch.float32)
+            x = torch.tensor(self.state[:, g * Fg:(g + 1) * Fg], dtype=torch.float32).to(self.device)
             self.means.append(torch.mean(self.simulate(x, g).abs() ** 2, dim=1, keepdim=True))
         self.previous_psnr = self.initial_psnr = self.relative_psnr(torch.cat(self.means, dim=1), self.target)
         return self.initial_psnr
@@ -68,7 +73,7 @@ class TorchRefEnv:
         r, c = divmod(pix, N)
         self.state[0, ch, r, c] = 1 - self.state[0, ch, r, c]
         g = ch // Fg
-        x = torch.tensor(self.state[:, g * Fg:(g + 1) * Fg], dtype=torch.float32)   # env.py:170
+        x = torch.tensor(self.state[:, g * Fg:(g + 1) * Fg], dtype=torch.float32).to(self.device)   # env.py:170
         mean_after = torch.mean(self.simulate(x, g).abs() ** 2, dim=1, keepdim=True)
         rgb = torch.cat([mean_after if k == g else self.means[k] for k in range(self.G)], dim=1)
         psnr_after = self.relative_psnr(rgb, self.target)

@@ -683,3 +683,30 @@ def test_sharded_sweep_equals_full_sweep():
     # a shard small enough to take the delta-kernel path agrees with the correlation map
     small = run((0, 64))
     np.testing.assert_allclose(small["psnr_after"], full["psnr_after"][:small["steps"]], rtol=0, atol=1e-8)
+
+
+def test_group_rollouts_from_cloned_reset_state():
+    """GRPO-style groups: members cloned on the device step exactly like independently reset envs."""
+    N, F, E, M = 64, 8, 6, 3
+    loaders = [bh.SyntheticLoader(N, F, 1, seeds=(500 + i // M,)) for i in range(E)]
+    tf = lambda t: next(l for l in loaders if np.ascontiguousarray(t[0, 0, 0, :4]).tobytes() in l._pre).target_function(t)
+    kw = dict(max_steps=10 ** 6, T_PSNR_DIFF=1e9, IPS=N, CH=F)
+    grp = bh.HologramVecEnv(E, tf, loaders, **kw)
+    ind = bh.HologramVecEnv(E, tf, [bh.SyntheticLoader(N, F, 1, seeds=(500 + i // M,)) for i in range(E)], **kw)
+    launches0 = grp.engine.launch_count
+    grp.reset_groups(M)
+    assert grp.engine.launch_count - launches0 == (E // M) * 5          # one propagation per group leader
+    ind.reset()
+    for i in range(E):
+        assert grp.envs[i].initial_psnr == ind.envs[i].initial_psnr
+        assert np.array_equal(grp.engine.state(i), ind.engine.state(i))
+    rng = np.random.default_rng(3)
+    for _ in range(25):
+        acts = rng.integers(0, F * N * N, size=E)
+        _, r1, d1, _ = grp.step(acts)
+        _, r2, d2, _ = ind.step(acts)
+        assert np.array_equal(r1, r2) and np.array_equal(d1, d2)
+    for i in range(E):
+        assert np.array_equal(grp.envs[i].state, ind.envs[i].state)
+        assert np.array_equal(grp.engine.state(i), ind.engine.state(i))
+    grp.close(); ind.close()
