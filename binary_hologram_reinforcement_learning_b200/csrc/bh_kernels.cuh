@@ -814,4 +814,62 @@ k_sweep_final(const float* __restrict__ dIT, const float* __restrict__ dII,
     }
 }
 
+// ---------------------------------------------------------------------------
+// decile statistics of a sweep on the device (dbs-1024-1024-24-6464.py:377-395):
+// per bin of the pre-model output: attempted, improved (psnr_after > previous) and the
+// summed improvement.  Bins are half-open, the last one closed, compared in double like
+// the reference's numpy code.  Gains are accumulated in 2^-40 fixed point so the sums do
+// not depend on the order of the atomics.
+// ---------------------------------------------------------------------------
+constexpr int N_BINS = 10;
+struct BinEdges { double e[N_BINS + 1]; };
+
+__global__ void __launch_bounds__(256)
+k_sweep_stats(const double* __restrict__ psnr, const float* __restrict__ pre, size_t count,
+              double previous, BinEdges edges, unsigned long long* __restrict__ out /*[3][N_BINS]*/) {
+    __shared__ unsigned long long sh[3][N_BINS];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 3 * N_BINS) (&sh[0][0])[tid] = 0ull;
+    __syncthreads();
+    // per-thread counters in registers (static indices), folded once at the end
+    unsigned att[N_BINS], imp[N_BINS];
+    long long gain[N_BINS];
+#pragma unroll
+    for (int i = 0; i < N_BINS; ++i) { att[i] = 0; imp[i] = 0; gain[i] = 0; }
+    for (size_t p = size_t(blockIdx.x) * 256 + tid; p < count; p += size_t(gridDim.x) * 256) {
+        const double v = double(pre[p]);
+        const double d = psnr[p] - previous;
+        const bool better = d > 0.0;
+        const long long fx = better ? __double2ll_rn(d * 1099511627776.0) : 0ll;
+        bool taken = false;
+#pragma unroll
+        for (int i = 0; i < N_BINS; ++i) {
+            const bool in = !taken && ((i == N_BINS - 1) ? (v >= edges.e[i] && v <= edges.e[i + 1])
+                                                         : (v >= edges.e[i] && v < edges.e[i + 1]));
+            taken = taken || in;
+            att[i] += in ? 1u : 0u;
+            imp[i] += (in && better) ? 1u : 0u;
+            gain[i] += in ? fx : 0ll;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N_BINS; ++i) {
+        unsigned a = att[i], m = imp[i];
+        long long g = gain[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            m += __shfl_xor_sync(0xffffffffu, m, o);
+            g += __shfl_xor_sync(0xffffffffu, g, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&sh[0][i], (unsigned long long)a);
+            atomicAdd(&sh[1][i], (unsigned long long)m);
+            atomicAdd(&sh[2][i], (unsigned long long)g);
+        }
+    }
+    __syncthreads();
+    if (tid < 3 * N_BINS) atomicAdd(out + tid, (&sh[0][0])[tid]);
+}
+
 }  // namespace bh

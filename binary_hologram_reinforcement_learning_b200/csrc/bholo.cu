@@ -815,6 +815,48 @@ extern "C" int bh_sweep_all(bh_ctx* c, int env, double* psnr_after, int on_host)
     return 0;
 }
 
+extern "C" int bh_sweep_stats(bh_ctx* c, int env, const float* pre_model, const double* edges,
+                              int64_t* attempted, int64_t* improved, double* gains, double* psnr_after) {
+    BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
+    if (!pre_model || !edges || !attempted || !improved || !gains) BH_FAIL(c, -1, "bad arguments");
+    const size_t count = size_t(c->F) * c->n2;
+    double* d_map = nullptr; float* d_pre = nullptr; unsigned long long* d_out = nullptr;
+    auto cleanup = [&]() { cudaFree(d_map); cudaFree(d_pre); cudaFree(d_out); };
+#define BH_ST(expr)                                                          \
+    do {                                                                     \
+        cudaError_t _e = (expr);                                             \
+        if (_e != cudaSuccess) {                                             \
+            cleanup();                                                       \
+            BH_FAIL(c, -2, "%s failed: %s", #expr, cudaGetErrorString(_e));  \
+        }                                                                    \
+    } while (0)
+    BH_ST(cudaMalloc(&d_map, count * sizeof(double)));
+    BH_ST(cudaMalloc(&d_pre, count * sizeof(float)));
+    BH_ST(cudaMalloc(&d_out, 3 * N_BINS * sizeof(unsigned long long)));
+    BH_ST(cudaMemcpyAsync(d_pre, pre_model, count * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    BH_ST(cudaMemsetAsync(d_out, 0, 3 * N_BINS * sizeof(unsigned long long), c->stream));
+    double previous = 0.0;
+    if (int rc = bh_get_metrics(c, env, &previous, nullptr, nullptr)) { cleanup(); return rc; }
+    if (int rc = bh_sweep_all(c, env, d_map, 0)) { cleanup(); return rc; }
+    BinEdges be;
+    for (int i = 0; i <= N_BINS; ++i) be.e[i] = edges[i];
+    k_sweep_stats<<<148 * 8, 256, 0, c->stream>>>(d_map, d_pre, count, previous, be, d_out);
+    c->launches += 1;
+    BH_ST(cudaGetLastError());
+    unsigned long long h_out[3 * N_BINS];
+    BH_ST(cudaMemcpyAsync(h_out, d_out, sizeof h_out, cudaMemcpyDeviceToHost, c->stream));
+    if (psnr_after) BH_ST(cudaMemcpyAsync(psnr_after, d_map, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    BH_ST(cudaStreamSynchronize(c->stream));
+#undef BH_ST
+    for (int i = 0; i < N_BINS; ++i) {
+        attempted[i] = (int64_t)h_out[i];
+        improved[i] = (int64_t)h_out[N_BINS + i];
+        gains[i] = double((long long)h_out[2 * N_BINS + i]) * FIX_INV;
+    }
+    cleanup();
+    return 0;
+}
+
 extern "C" void* bh_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {

@@ -307,6 +307,27 @@ def dbs_sweep(target_function: Callable, trainloader: Iterable, z=2e-3, pixel_pi
         psnr_all = np.empty(hi_all - lo_all, dtype=np.float64)
         flip_count = 0
         psnr_map = None
+        if (eng.pad == 1 and eng.Fg % 2 == 0 and shard is None and max_candidates is None
+                and perm.shape[0] == n):
+            # the whole image in one call: correlation sweep + decile statistics on the device
+            att, imp, gn, psnr_map = eng.sweep_stats(cpre, OUTPUT_BINS, 0, want_map=True)
+            psnr_all = psnr_map.reshape(-1)[perm]
+            flip_count = int(imp.sum())
+            dt = time.time() - t0
+            results.append(dict(file=file_name, initial_psnr=initial_psnr, psnr_after=psnr_all, order=perm,
+                                attempted=att, improved=imp, gains=gn, bin_counts=bin_counts,
+                                flip_count=flip_count, steps=int(n), seconds=dt))
+            if verbose:
+                print(f"Step: {n}"
+                      f"\nPSNR Before: {initial_psnr:.6f} | PSNR After: {psnr_all[-1]:.6f} | Change: {psnr_all[-1] - initial_psnr:.6f}"
+                      f"\nSuccess Ratio: {flip_count / n:.6f} | Flip Count: {flip_count}"
+                      f"\nTime taken for this data: {dt:.2f} seconds")
+                print(f"{file_name}.png Optimization completed.")
+                print(f"Time taken for this data: {dt:.2f} seconds\n")
+                print("Pre-model output range statistics:")
+                _print_bins(bin_counts, imp, gn, att)
+                print("\n")
+            continue
         if eng.pad == 1 and eng.Fg % 2 == 0 and (hi_all - lo_all) * 4 >= n:
             psnr_map = eng.sweep_all(0)                    # every candidate in one call
         for lo in range(lo_all, hi_all, chunk):

@@ -21,7 +21,7 @@ ABI_SYMBOLS = (
     "bh_abi_version", "bh_last_error", "bh_create", "bh_destroy", "bh_set_stream",
     "bh_set_target", "bh_load_state", "bh_clone_env", "bh_resync", "bh_get_metrics", "bh_eval_flips",
     "bh_step_batch", "bh_vec_step", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
-    "bh_commit_flip", "bh_dbs_run", "bh_sweep_all", "bh_get_recon", "bh_get_state", "bh_get_field",
+    "bh_commit_flip", "bh_dbs_run", "bh_sweep_all", "bh_sweep_stats", "bh_get_recon", "bh_get_state", "bh_get_field",
     "bh_device_ptr", "bh_host_alloc", "bh_host_free", "bh_simulate", "bh_time_eval", "bh_time_propagate", "bh_time_propagate_passes", "bh_launch_count",
 )
 
@@ -91,6 +91,7 @@ def load_library(build_if_missing: bool = True):
         "bh_commit_flip": (i32, [vp, i32, i64]),
         "bh_dbs_run": (i32, [vp, i32, vp, i64, i32, i64, vp, vp, P(i64), P(dbl)]),
         "bh_sweep_all": (i32, [vp, i32, vp, i32]),
+        "bh_sweep_stats": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
         "bh_get_recon": (i32, [vp, i32, vp, i32, i64]),
         "bh_get_state": (i32, [vp, i32, vp, i32]),
         "bh_get_field": (i32, [vp, i32, i32, vp, i32]),
@@ -288,6 +289,21 @@ class HoloEngine:
             out = np.empty((self.F, self.N, self.N), dtype=np.float64)
         self._check(self.lib.bh_sweep_all(self._h, env, _ptr(out), 1), "bh_sweep_all")
         return out
+
+    def sweep_stats(self, pre_model: np.ndarray, edges: np.ndarray, env: int = 0, want_map: bool = False):
+        """Exhaustive sweep + decile statistics on the device.
+
+        Returns (attempted int64[10], improved int64[10], gains float64[10], psnr_map | None).
+        """
+        pre = np.ascontiguousarray(pre_model, dtype=np.float32).reshape(self.F, self.N, self.N)
+        ed = np.ascontiguousarray(edges, dtype=np.float64)
+        assert ed.shape == (11,)
+        att, imp = np.zeros(10, dtype=np.int64), np.zeros(10, dtype=np.int64)
+        gains = np.zeros(10, dtype=np.float64)
+        pm = np.empty((self.F, self.N, self.N), dtype=np.float64) if want_map else None
+        self._check(self.lib.bh_sweep_stats(self._h, env, _ptr(pre), _ptr(ed), _ptr(att), _ptr(imp),
+                                            _ptr(gains), _ptr(pm)), "bh_sweep_stats")
+        return att, imp, gains, pm
 
     def sweep_all_device(self, env: int, d_out: int):
         self._check(self.lib.bh_sweep_all(self._h, env, C.c_void_p(d_out), 0), "bh_sweep_all")

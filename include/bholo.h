@@ -97,6 +97,14 @@ int bh_eval_flips(bh_ctx* ctx, int env, int64_t n, const int32_t* env_ids,
  * on_host = 0. */
 int bh_sweep_all(bh_ctx* ctx, int env, double* psnr_after, int on_host);
 
+/* bh_sweep_all followed by the decile statistics of dbs-1024-1024-24-6464.py:377-395 on the
+ * device: pre_model float [F][N][N] (host) is the pre-binarisation output that defines the
+ * bins, edges the 11 bin edges (half-open bins, last one closed).  attempted / improved:
+ * int64[10]; gains: double[10] (sum of psnr_after - previous over the improving flips).
+ * psnr_after may be NULL when only the statistics are wanted. */
+int bh_sweep_stats(bh_ctx* ctx, int env, const float* pre_model, const double* edges,
+                   int64_t* attempted, int64_t* improved, double* gains, double* psnr_after);
+
 /* One environment step for n distinct environments: score the flip, keep or
  * revert it under `rule` (env.py:154-196 / DBS_1024_24.py:313-422 body).
  * results: n records. */

@@ -74,6 +74,14 @@ dt_map = time.perf_counter() - t0
 t0 = time.perf_counter()
 r = bh.sweep_engine(eng, 0, pre, cand, p0, psnr_map=pm)    # decile statistics on the host
 dt_stats = time.perf_counter() - t0
+eng.sweep_stats(pre, bh.OUTPUT_BINS, 0)                    # warm (first launch loads the kernel)
+t0 = time.perf_counter()
+att, imp, gn, _ = eng.sweep_stats(pre, bh.OUTPUT_BINS, 0)   # sweep + decile statistics on the device
+dt_dev = time.perf_counter() - t0
+assert np.array_equal(att, r["attempted"]) and np.array_equal(imp, r["improved"])
+out["config3_full_sweep_896x24_device_stats"] = {
+    "seconds_incl_pre_model_upload": dt_dev, "flip_evals_per_s_end_to_end": cand.size / dt_dev,
+    "max_rel_gain_diff_vs_host": float(np.max(np.abs(gn - r["gains"]) / np.maximum(np.abs(r["gains"]), 1e-30)))}
 out["config3_full_sweep_896x24"] = {
     "candidates": int(cand.size), "sweep_all_seconds_incl_d2h": dt_map, "host_decile_stats_seconds": dt_stats,
     "flip_evals_per_s_end_to_end": cand.size / (dt_map + dt_stats), "improving_fraction": r["flip_count"] / cand.size}

@@ -679,7 +679,8 @@ def test_sharded_sweep_equals_full_sweep():
     assert np.array_equal(np.concatenate([p["psnr_after"] for p in parts]), full["psnr_after"])
     for key in ("attempted", "improved"):
         assert np.array_equal(sum(p[key] for p in parts), full[key])
-    np.testing.assert_allclose(sum(p["gains"] for p in parts), full["gains"], rtol=1e-12)
+    # the full sweep takes its statistics on the device (2^-40 fixed-point sums), the shards on the host
+    np.testing.assert_allclose(sum(p["gains"] for p in parts), full["gains"], rtol=1e-8, atol=1e-9)
     # a shard small enough to take the delta-kernel path agrees with the correlation map
     small = run((0, 64))
     np.testing.assert_allclose(small["psnr_after"], full["psnr_after"][:small["steps"]], rtol=0, atol=1e-8)
