@@ -36,28 +36,38 @@ struct Result {            // mirrored by bh_result in include/bholo.h (40 bytes
 
 enum { RULE_ENV = 0, RULE_DBS = 1, RULE_NEVER = 2 };
 
-constexpr int TILE_W = 8;          // sequences per FFT tile
-#ifndef BH_COLS_W
-#define BH_COLS_W 8                // columns per tile of the column pass (experiments: 16)
+// Tile shape knobs (sequences per tile, CTAs per SM the compiler must allow).  Tuned on B200 at
+// P = 1024 (profiles/r1_notes.md): narrow tiles with a large register budget beat wide tiles at
+// the 64-register cap -- the passes are latency bound, and independent small CTAs overlap their
+// load / barrier phases.
+#ifndef BH_ROWS_W
+#define BH_ROWS_W 2
 #endif
+#ifndef BH_ROWS_MINB
+#define BH_ROWS_MINB 4
+#endif
+#ifndef BH_COLS_W
+#define BH_COLS_W 8
+#endif
+#ifndef BH_COLS_MINB
+#define BH_COLS_MINB 1
+#endif
+constexpr int TILE_W = BH_ROWS_W;  // sequences per FFT tile of the row passes
 
 constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
 
-// threads per CTA: P/16 threads per sequence (16 complex values in registers per
-// thread and pass) so that two CTAs share an SM at P = 1024
+// threads: P/16 per sequence at P >= 896 (16 complex values in registers per thread and pass)
 template <int P> struct FftCfg {
-    static constexpr int T = (P >= 896) ? 512 : 256;    // threads per CTA
-    static constexpr int Q = T / TILE_W;                // threads per sequence
-    static constexpr int MINB = (P <= 1024) ? 2 : 1;    // CTAs per SM the compiler must allow
+    static constexpr int Q = (P >= 896) ? 64 : 32;      // threads per sequence
+    static constexpr int T = TILE_W * Q;                // threads per CTA, row passes
+    static constexpr int MINB = (P <= 1024) ? BH_ROWS_MINB : 1;
     static constexpr int SKR = 4;                       // row layout: pad after every 16 elements
     static constexpr int SKC = ilog2_c(Plan<P>::r[0]);  // column layout: pad after every R0 elements
     static constexpr int SEQ = SeqLen<P, SKR>::value;   // row layout: stride between sequences
     static constexpr size_t smem_row = size_t(SEQ) * TILE_W * sizeof(float2);
-    // column pass: 8 columns per tile (64-byte row segments).  16 columns x 1024 threads was
-    // measured equal at best (it spills at the 64-register cap), see profiles/r1_notes.md
-    static constexpr int WC = BH_COLS_W;
+    static constexpr int WC = BH_COLS_W;                // columns per tile of the column pass
     static constexpr int TC = WC * Q;
-    static constexpr int MINBC = (TC >= 1024) ? 1 : MINB;
+    static constexpr int MINBC = (P <= 1024) ? BH_COLS_MINB : 1;
     static constexpr size_t smem_col = size_t(SeqLen<P, SKC>::value) * WC * sizeof(float2);
 };
 
