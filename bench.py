@@ -162,6 +162,36 @@ def cpu_reference_rate(seconds_budget=None, samples=None, sample_steps=8, warm=1
     return rate, times, cores
 
 
+def comparator_rates(seconds=4.0):
+    """Other shapes of the same reference-shaped torch path, part of the cpu_baseline leg:
+    the 256^2 x 8 full step on the host cores, and the call sequence "simply run on the B200"
+    (torch.fft = cuFFT, the colour group re-uploaded every step as env.py:170 does, blocking .item())."""
+    import torch
+    from oracle.torch_path import TorchRefEnv
+    from oracle import hologram_oracle as O
+
+    def rate(N, F, wl, device):
+        pre, tgt = O.synthetic_problem(N, F, len(wl), 0)
+        env = TorchRefEnv(N, F, wl, device=device, threads=os.cpu_count())
+        env.reset(pre, tgt)
+        rng = np.random.default_rng(5)
+        for _ in range(5):
+            env.step(int(rng.integers(0, F * N * N)))
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            env.step(int(rng.integers(0, F * N * N)))
+            n += 1
+        if device != "cpu":
+            torch.cuda.synchronize()
+        return n / (time.perf_counter() - t0)
+
+    out = {"torch_cpu_256x8_full_step_env_steps_per_s": rate(256, 8, O.WL_MONO, "cpu")}
+    if torch.cuda.is_available():
+        out["torch_on_b200_1024x24_single_group_env_steps_per_s"] = rate(N_SIDE, FRAMES, O.WL_RGB, "cuda")
+        out["torch_on_b200_256x8_full_step_env_steps_per_s"] = rate(256, 8, O.WL_MONO, "cuda")
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -345,7 +375,8 @@ def run_b200(args):
         cpu = {"value": rate, "unit": "env steps/s", "cores": cores, "kind": "port",
                "sample": (f"{8 * len(times)} env steps of one 1024x1024x24 env, per-colour-group "
                           f"re-simulation, float32 torch CPU ({cores} threads), "
-                          f"{sum(times):.1f} s (oracle/torch_path.py)")}
+                          f"{sum(times):.1f} s (oracle/torch_path.py)"),
+               "comparators": comparator_rates()}
 
     if rank == 0:
         line = {

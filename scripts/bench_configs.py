@@ -111,34 +111,4 @@ dt = time.perf_counter() - t0
 out["config4_group_rollout_64_envs_256x8_env_steps_per_s"] = 500 * E / dt
 vec.close()
 
-# -- comparators: the reference call sequence on the host CPU and "simply run on the GPU" ----
-import torch  # noqa: E402
-from oracle.torch_path import TorchRefEnv  # noqa: E402
-
-
-def ref_rate(N, F, wl, device, seconds=6.0):
-    pre, tgt = bh.synthetic_problem(N, F, len(wl), 0)
-    env = TorchRefEnv(N, F, wl, device=device, threads=os.cpu_count())
-    env.reset(pre, tgt)
-    rng = np.random.default_rng(5)
-    for _ in range(5):
-        env.step(int(rng.integers(0, F * N * N)))
-    if device != "cpu":
-        torch.cuda.synchronize()
-    n, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < seconds:
-        env.step(int(rng.integers(0, F * N * N)))
-        n += 1
-    if device != "cpu":
-        torch.cuda.synchronize()
-    return n / (time.perf_counter() - t0)
-
-
-out["comparators_env_steps_per_s"] = {
-    "cpu_cores": os.cpu_count(),
-    "torch_cpu_256x8_full_step": ref_rate(256, 8, bh.WL_MONO, "cpu"),
-    "torch_cpu_1024x24_single_group_step": ref_rate(1024, 24, bh.WL_RGB, "cpu", 10.0),
-    "torch_on_b200_256x8 (cuFFT, per-step upload, .item())": ref_rate(256, 8, bh.WL_MONO, "cuda"),
-    "torch_on_b200_1024x24_single_group_step": ref_rate(1024, 24, bh.WL_RGB, "cuda"),
-}
 print(json.dumps(out, indent=1))
