@@ -933,6 +933,31 @@ __global__ void k_real_to_complex(const float* __restrict__ in, float2* __restri
         out[i] = make_float2(in[i], 0.f);
 }
 
+// device tables of the stand-alone operator, kept for the life of the process: a script that
+// calls tt.simulate every step (the reference's loops) must not rebuild and upload 8 MB per call
+struct SimTables { float2* dH = nullptr; float2* dtw = nullptr; };
+static int sim_tables(int device, int P, double wl, double dx, double z, int method, SimTables* out) {
+    using Key = std::tuple<int, int, double, double, double, int>;
+    static std::mutex mu;
+    static std::map<Key, SimTables> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    const Key key(device, P, wl, dx, z, method);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+    bh_ctx* nul = nullptr;
+    const size_t p2 = size_t(P) * P;
+    auto t = get_tables(P, wl, dx, z, method);
+    auto tw = build_twiddles(P);
+    SimTables st;
+    BH_CUDA(nul, cudaMalloc(&st.dH, p2 * sizeof(float2)));
+    BH_CUDA(nul, cudaMalloc(&st.dtw, (tw.size() / 2 + 1) * sizeof(float2)));
+    BH_CUDA(nul, cudaMemcpy(st.dH, t->H.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
+    BH_CUDA(nul, cudaMemcpy(st.dtw, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    cache[key] = st;
+    *out = st;
+    return 0;
+}
+
 extern "C" int bh_simulate(int device, void* stream_, const float* in, int is_complex, int C, int N,
                            double wl, double dx, double z, int pad, int method, float* out, int on_host) {
     bh_ctx* nul = nullptr;
@@ -943,9 +968,12 @@ extern "C" int bh_simulate(int device, void* stream_, const float* in, int is_co
     BH_CUDA(nul, cudaSetDevice(device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
     const size_t n2 = size_t(N) * N, p2 = size_t(P) * P, cnt = size_t(C) * n2;
-    float2 *dH = nullptr, *dtw = nullptr, *din = nullptr, *dbuf = nullptr, *dout = nullptr;
+    float2 *din = nullptr, *dbuf = nullptr, *dout = nullptr;
     float* draw = nullptr;
-    auto cleanup = [&]() { cudaFree(dH); cudaFree(dtw); cudaFree(din); cudaFree(dbuf); cudaFree(dout); cudaFree(draw); };
+    SimTables tabs;
+    if (int rc = sim_tables(device, P, wl, dx, z, method, &tabs)) return rc;
+    float2 *dH = tabs.dH, *dtw = tabs.dtw;
+    auto cleanup = [&]() { cudaFree(din); cudaFree(dbuf); cudaFree(dout); cudaFree(draw); };
 #define BH_SIM(expr)                                                          \
     do {                                                                      \
         cudaError_t _e = (expr);                                              \
@@ -954,13 +982,7 @@ extern "C" int bh_simulate(int device, void* stream_, const float* in, int is_co
             BH_FAIL(nul, -2, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
         }                                                                     \
     } while (0)
-    auto t = get_tables(P, wl, dx, z, method);
-    auto tw = build_twiddles(P);
-    BH_SIM(cudaMalloc(&dH, p2 * sizeof(float2)));
-    BH_SIM(cudaMalloc(&dtw, (tw.size() / 2 + 1) * sizeof(float2)));
     BH_SIM(cudaMalloc(&din, cnt * sizeof(float2)));
-    BH_SIM(cudaMemcpyAsync(dH, t->H.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice, st));
-    BH_SIM(cudaMemcpyAsync(dtw, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     const cudaMemcpyKind kin = on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     if (is_complex) {
         BH_SIM(cudaMemcpyAsync(din, in, cnt * sizeof(float2), kin, st));
