@@ -196,8 +196,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return 0
-    sample_steps = 8
-    # warmup samples are untimed; bounded so K + W samples finish within minutes
+    # one sample = one vectorised step of 8 envs on the CPU path; shrunk for very long runs so that
+    # K + W samples still finish within a few minutes (~35 ms per env step on 16 cores)
+    sample_steps = 8 if args.steps + args.warmup <= 400 else max(1, 3200 // (args.steps + args.warmup))
     import torch  # noqa: F401
     rate, times, cores = cpu_reference_rate(samples=args.steps, sample_steps=sample_steps,
                                             warm=max(1, args.warmup))
