@@ -72,6 +72,18 @@ template <int P> struct FftCfg {
 };
 
 // ---------------------------------------------------------------------------
+// cp.async helpers (LDGSTS): global -> shared without staging registers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(float2* smem, const float2* gmem) {
+    const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---------------------------------------------------------------------------
 // pass A: FFT along x of W canvas rows.  in: [frames][N][N] int8 state (or
 // complex float2 for the stand-alone operator); out: buf [frames][P][P].
 // Row layout: thread (w = tid / Q, q = tid % Q).
@@ -262,6 +274,92 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// ---------------------------------------------------------------------------
+// pass C fused with the reconstruction and the loss sums (reset / re-sync path):
+// one CTA owns W window rows of one colour group and walks the group's Fg frames.  While
+// frame f is transformed in one shared-memory buffer, the rows of frame f+1 stream into the
+// other with cp.async, so the tile load (37 % of the stand-alone pass) hides behind the FFT.
+// |U|^2 accumulates in registers across the frames (.abs()**2 + torch.mean(dim=1),
+// env.py:172-173), the epilogue writes I and this tile's float64 partial sums of
+// tt.relativeLoss (sum I^2, sum I*T, sum T^2); k_loss_final folds them in index order.
+// grid (N / W, groups).  buf may alias U when PAD == 1 (frame f+1 is only read before
+// frame f+1 is written).
+// ---------------------------------------------------------------------------
+template <int P, int PAD>
+__global__ void __launch_bounds__(FftCfg<P>::T, FftCfg<P>::MINB)
+k_rows_inv_group(const float2* buf, float2* U, float* __restrict__ I, const float* __restrict__ Tg,
+                 const float2* __restrict__ tw, int Fg, double* __restrict__ partial) {
+    using C = FftCfg<P>;
+    constexpr int N = P / PAD, O = (P - N) / 2, T = C::T, Q = C::Q, SK = C::SKR, SEQ = C::SEQ;
+    constexpr int NX = (P + T - 1) / T, NXO = (N + T - 1) / T;
+    constexpr int TILE = SEQ * TILE_W;
+    extern __shared__ float2 s[];                   // two tiles
+    __shared__ double sh[3][T / 32];
+    const int tid = threadIdx.x, g = blockIdx.y, y0 = blockIdx.x * TILE_W;
+    const size_t n2 = size_t(N) * N;
+    float acc[TILE_W][NXO];
+#pragma unroll
+    for (int w = 0; w < TILE_W; ++w)
+#pragma unroll
+        for (int k = 0; k < NXO; ++k) acc[w][k] = 0.f;
+    auto prefetch = [&](int fi, float2* dst) {
+        const float2* src = buf + size_t(g * Fg + fi) * P * P + size_t(y0 + O) * P;
+#pragma unroll
+        for (int w = 0; w < TILE_W; ++w)
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+                const int X = tid + k * T;
+                if (P % T == 0 || X < P) cp_async8(dst + w * SEQ + padded<SK>(X), src + size_t(w) * P + X);
+            }
+        cp_async_commit();
+    };
+    prefetch(0, s);
+    for (int fi = 0; fi < Fg; ++fi) {
+        float2* cur = s + (fi & 1) * TILE;
+        if (fi + 1 < Fg) { prefetch(fi + 1, s + ((fi + 1) & 1) * TILE); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        tile_fft<P, Q, 1, SK, true>(cur + (tid / Q) * SEQ, tid % Q, tw);
+        float2* dst = U + size_t(g * Fg + fi) * n2 + size_t(y0) * N;
+#pragma unroll
+        for (int w = 0; w < TILE_W; ++w)
+#pragma unroll
+            for (int k = 0; k < NXO; ++k) {
+                const int x = tid + k * T;
+                if (N % T == 0 || x < N) {
+                    const float2 v = cur[w * SEQ + padded<SK>(x + O)];
+                    dst[size_t(w) * N + x] = v;
+                    acc[w][k] = fmaf(v.x, v.x, fmaf(v.y, v.y, acc[w][k]));
+                }
+            }
+        __syncthreads();                            // the buffer is free for the prefetch of frame fi + 2
+    }
+    const float inv = 1.f / float(Fg);
+    double a = 0, b = 0, c = 0;
+#pragma unroll
+    for (int w = 0; w < TILE_W; ++w)
+#pragma unroll
+        for (int k = 0; k < NXO; ++k) {
+            const int x = tid + k * T;
+            if (N % T == 0 || x < N) {
+                const size_t p = size_t(g) * n2 + size_t(y0 + w) * N + x;
+                const float iv = acc[w][k] * inv, tv = __ldg(Tg + p - size_t(g) * n2);
+                I[p - size_t(g) * n2] = iv;
+                a += double(iv) * iv; b += double(iv) * tv; c += double(tv) * tv;
+            }
+        }
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; sh[2][warp] = c; }
+    __syncthreads();
+    if (tid == 0) {
+        double x = 0, y = 0, z = 0;
+        for (int i = 0; i < T / 32; ++i) { x += sh[0][i]; y += sh[1][i]; z += sh[2][i]; }
+        double* out = partial + (size_t(g) * gridDim.x + blockIdx.x) * 3;
+        out[0] = x; out[1] = y; out[2] = z;
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -100,10 +100,14 @@ extern "C" const char* bh_last_error(const bh_ctx* ctx) {
 // The three FFT passes over `frames` consecutive planes (one colour group, or the C planes
 // of the stand-alone operator).  Launching group by group keeps the 8 MB-per-frame
 // intermediate of pass A / pass B resident in the 126 MB L2 between passes.
+struct FusedC {            // non-null: pass C also produces I and the loss partials of group g
+    float* I; const float* T; double* partial;
+};
+
 template <int P, int PAD, typename InT, bool CPLX>
 static cudaError_t launch_prop(const InT* in, float2* buf, float2* U, const float2* H,
                                const float2* tw, int frames, int Fg, cudaStream_t st,
-                               cudaEvent_t* ev = nullptr) {
+                               cudaEvent_t* ev = nullptr, const FusedC* fused = nullptr) {
     constexpr int N = P / PAD;
     constexpr int T = FftCfg<P>::T;
     const size_t smr = FftCfg<P>::smem_row, smc = FftCfg<P>::smem_col;
@@ -120,7 +124,13 @@ static cudaError_t launch_prop(const InT* in, float2* buf, float2* U, const floa
     if (ev) cudaEventRecord(ev[1], st);
     kB<<<dim3(P / FftCfg<P>::WC, frames), FftCfg<P>::TC, smc, st>>>(buf, H, tw);
     if (ev) cudaEventRecord(ev[2], st);
-    kC<<<dim3(N / TILE_W, frames), T, smr, st>>>(buf, U, tw);
+    if (fused) {
+        auto kCg = k_rows_inv_group<P, PAD>;
+        if ((e = cudaFuncSetAttribute(kCg, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * smr)))) return e;
+        kCg<<<dim3(N / TILE_W, 1), T, 2 * smr, st>>>(buf, U, fused->I, fused->T, tw, Fg, fused->partial);
+    } else {
+        kC<<<dim3(N / TILE_W, frames), T, smr, st>>>(buf, U, tw);
+    }
     if (ev) cudaEventRecord(ev[3], st);
     return cudaGetLastError();
 }
@@ -128,10 +138,11 @@ static cudaError_t launch_prop(const InT* in, float2* buf, float2* U, const floa
 template <typename InT, bool CPLX>
 static cudaError_t dispatch_prop(int P, int pad, const InT* in, float2* buf, float2* U,
                                  const float2* H, const float2* tw, int frames, int Fg,
-                                 cudaStream_t st, bool* supported, cudaEvent_t* ev = nullptr) {
+                                 cudaStream_t st, bool* supported, cudaEvent_t* ev = nullptr,
+                                 const FusedC* fused = nullptr) {
     *supported = true;
 #define BH_CASE(PP, PD) \
-    if (P == PP && pad == PD) return launch_prop<PP, PD, InT, CPLX>(in, buf, U, H, tw, frames, Fg, st, ev);
+    if (P == PP && pad == PD) return launch_prop<PP, PD, InT, CPLX>(in, buf, U, H, tw, frames, Fg, st, ev, fused);
     BH_CASE(32, 1) BH_CASE(64, 1) BH_CASE(128, 1) BH_CASE(256, 1) BH_CASE(512, 1)
     BH_CASE(896, 1) BH_CASE(1024, 1)
     BH_CASE(64, 2) BH_CASE(128, 2) BH_CASE(256, 2) BH_CASE(512, 2) BH_CASE(1792, 2) BH_CASE(2048, 2)
@@ -161,12 +172,12 @@ static int propagate_env(bh_ctx* c, int env, float* pass_ms = nullptr) {
         const float* T = c->dT + (size_t(env) * c->G + g) * n2;
         float2* buf = (c->pad == 1) ? U : c->dscratch;
         bool ok = false;
+        const int tiles = c->N / TILE_W;            // partials of the fused pass C, per group
+        FusedC fused{I, T, c->dloss_partial + size_t(g) * tiles * 3};
         BH_CUDA(c, (dispatch_prop<int8_t, false>(c->P, c->pad, st, buf, U, c->dH + size_t(g) * p2, c->dtw,
-                                                 c->Fg, c->Fg, c->stream, &ok, pass_ms ? ev : nullptr)));
+                                                 c->Fg, c->Fg, c->stream, &ok, pass_ms ? ev : nullptr, &fused)));
         if (!ok) BH_FAIL(c, -4, "unsupported FFT side P=%d pad=%d", c->P, c->pad);
-        k_intensity<<<LOSS_BLOCKS, 256, 0, c->stream>>>(U, I, T, n2, c->Fg,
-                                                        c->dloss_partial + size_t(g) * LOSS_BLOCKS * 3);
-        c->launches += 4;
+        c->launches += 3;
         if (pass_ms) {
             BH_CUDA(c, cudaEventRecord(ev[4], c->stream));
             BH_CUDA(c, cudaEventSynchronize(ev[4]));
@@ -179,7 +190,7 @@ static int propagate_env(bh_ctx* c, int env, float* pass_ms = nullptr) {
     }
     if (pass_ms)
         for (auto& e : ev) cudaEventDestroy(e);
-    k_loss_final<<<1, 256, 0, c->stream>>>(c->dloss_partial, c->G * LOSS_BLOCKS, double(c->G) * double(n2),
+    k_loss_final<<<1, 256, 0, c->stream>>>(c->dloss_partial, c->G * (c->N / TILE_W), double(c->G) * double(n2),
                                           c->dsums + size_t(env) * 4, c->relative);
     BH_CUDA(c, cudaGetLastError());
     c->launches += 1;
@@ -279,7 +290,7 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
     BH_TRY(cudaMalloc(&c->drecon, size_t(G) * n2 * sizeof(float)));
     BH_TRY(cudaMalloc(&c->dstate, size_t(n_env) * F * n2));
     BH_TRY(cudaMalloc(&c->dsums, size_t(n_env) * 4 * sizeof(double)));
-    BH_TRY(cudaMalloc(&c->dloss_partial, size_t(G) * LOSS_BLOCKS * 3 * sizeof(double)));
+    BH_TRY(cudaMalloc(&c->dloss_partial, size_t(G) * std::max(LOSS_BLOCKS, N / TILE_W) * 3 * sizeof(double)));
     c->units_per_task = int(n2 / UNIT_PX);
     c->max_tasks = std::max(4096, n_env);
     BH_TRY(cudaMalloc(&c->d_envs, size_t(c->max_tasks) * sizeof(int32_t)));

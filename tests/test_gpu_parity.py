@@ -696,7 +696,7 @@ def test_group_rollouts_from_cloned_reset_state():
     ind = bh.HologramVecEnv(E, tf, [bh.SyntheticLoader(N, F, 1, seeds=(500 + i // M,)) for i in range(E)], **kw)
     launches0 = grp.engine.launch_count
     grp.reset_groups(M)
-    assert grp.engine.launch_count - launches0 == (E // M) * 5          # one propagation per group leader
+    assert grp.engine.launch_count - launches0 == (E // M) * 4          # one propagation per group leader
     ind.reset()
     for i in range(E):
         assert grp.envs[i].initial_psnr == ind.envs[i].initial_psnr
