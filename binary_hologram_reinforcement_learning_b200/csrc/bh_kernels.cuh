@@ -1,7 +1,8 @@
 // CUDA kernels of the hologram reward / DBS hot path (sm_100a).
 //
 //  propagation (reset / re-sync), per colour group:
-//      k_rows_fwd -> k_cols -> k_rows_inv -> k_intensity ; then k_loss_final
+//      k_rows_fwd -> k_cols -> k_rows_inv_group (inverse rows + intensity + loss partials) ; then k_loss_final
+//      (k_rows_inv alone is the tail of the stand-alone tt.simulate operator)
 //      restates tt.simulate + .abs()**2 + mean(dim=1) + tt.relativeLoss
 //      (reference env.py:123-132, env_1024_24.py:149-166)
 //  incremental path (every step / candidate):  k_eval -> k_commit
@@ -363,52 +364,7 @@ k_rows_inv_group(const float2* buf, float2* U, float* __restrict__ I, const floa
 }
 
 // ---------------------------------------------------------------------------
-// k_intensity: I_g = mean_f |U_f|^2 over the Fg frames of one colour group
-// (.abs()**2 + torch.mean(dim=1), env.py:172-173) fused with the partial sums of
-// tt.relativeLoss: sum I^2, sum I*T, sum T^2 in float64.  The field planes were
-// just written by k_rows_inv, so they mostly stream from L2.  One fixed-size
-// grid; partial[(g * gridDim.x + b) * 3 ..] is folded by k_loss_final in index
-// order, so the result does not depend on scheduling.
-// ---------------------------------------------------------------------------
-constexpr int LOSS_BLOCKS = 296;
-__global__ void __launch_bounds__(256)
-k_intensity(const float2* __restrict__ U /* group base [Fg][n2] */, float* __restrict__ I,
-            const float* __restrict__ T, size_t n2, int Fg, double* __restrict__ partial) {
-    __shared__ double sh[3][8];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const size_t nq = n2 / 4;
-    const float inv = 1.f / float(Fg);
-    double a = 0, b = 0, c = 0;
-    for (size_t q = size_t(blockIdx.x) * 256 + tid; q < nq; q += size_t(gridDim.x) * 256) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int f = 0; f < Fg; ++f) {
-            const float4* up = reinterpret_cast<const float4*>(U + size_t(f) * n2) + 2 * q;
-            const float4 u0 = up[0], u1 = up[1];
-            acc.x = fmaf(u0.x, u0.x, fmaf(u0.y, u0.y, acc.x));
-            acc.y = fmaf(u0.z, u0.z, fmaf(u0.w, u0.w, acc.y));
-            acc.z = fmaf(u1.x, u1.x, fmaf(u1.y, u1.y, acc.z));
-            acc.w = fmaf(u1.z, u1.z, fmaf(u1.w, u1.w, acc.w));
-        }
-        const float4 iv = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-        reinterpret_cast<float4*>(I)[q] = iv;
-        const float4 tv = __ldg(reinterpret_cast<const float4*>(T) + q);
-        a += double(iv.x) * iv.x + double(iv.y) * iv.y + double(iv.z) * iv.z + double(iv.w) * iv.w;
-        b += double(iv.x) * tv.x + double(iv.y) * tv.y + double(iv.z) * tv.z + double(iv.w) * tv.w;
-        c += double(tv.x) * tv.x + double(tv.y) * tv.y + double(tv.z) * tv.z + double(tv.w) * tv.w;
-    }
-    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
-    if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; sh[2][warp] = c; }
-    __syncthreads();
-    if (tid == 0) {
-        double x = 0, y = 0, z = 0;
-        for (int i = 0; i < 8; ++i) { x += sh[0][i]; y += sh[1][i]; z += sh[2][i]; }
-        partial[blockIdx.x * 3 + 0] = x;
-        partial[blockIdx.x * 3 + 1] = y;
-        partial[blockIdx.x * 3 + 2] = z;
-    }
-}
-
-// fold the G * LOSS_BLOCKS partials -> sums[0..2], PSNR -> sums[3].  One CTA; thread t adds
+// fold the per-tile partials of k_rows_inv_group (all colour groups) -> sums[0..2], PSNR -> sums[3].  One CTA; thread t adds
 // partials t, t+256, ... in index order and the 256 thread sums meet in a fixed shuffle/tree
 // order, so the result is independent of scheduling.
 __global__ void __launch_bounds__(256)

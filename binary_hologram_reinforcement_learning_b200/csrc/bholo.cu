@@ -290,7 +290,7 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
     BH_TRY(cudaMalloc(&c->drecon, size_t(G) * n2 * sizeof(float)));
     BH_TRY(cudaMalloc(&c->dstate, size_t(n_env) * F * n2));
     BH_TRY(cudaMalloc(&c->dsums, size_t(n_env) * 4 * sizeof(double)));
-    BH_TRY(cudaMalloc(&c->dloss_partial, size_t(G) * std::max(LOSS_BLOCKS, N / TILE_W) * 3 * sizeof(double)));
+    BH_TRY(cudaMalloc(&c->dloss_partial, size_t(G) * (N / TILE_W) * 3 * sizeof(double)));
     c->units_per_task = int(n2 / UNIT_PX);
     c->max_tasks = std::max(4096, n_env);
     BH_TRY(cudaMalloc(&c->d_envs, size_t(c->max_tasks) * sizeof(int32_t)));

@@ -39,6 +39,6 @@ echo "ncu warm rc=$?"; tail -1 gpurun_out/ncu_warm.log
 # (4) propagation passes
 timeout 120 python scripts/prof_prop.py > gpurun_out/prop_plain.log 2>&1 &&
 timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:"k_(rows_fwd|cols|rows_inv|intensity|loss_final)" -s 13 -c 13 \
+    -k regex:"k_(rows_fwd|cols|rows_inv|loss_final)" -s 10 -c 10 \
     -f -o gpurun_out/prof_prop python scripts/prof_prop.py > gpurun_out/ncu_prop.log 2>&1
 echo "ncu prop rc=$?"; cat gpurun_out/prop_plain.log
