@@ -95,39 +95,64 @@ k_rows_fwd(const InT* __restrict__ in, float2* __restrict__ buf, const float2* _
     using C = FftCfg<P>;
     constexpr int N = P / PAD, O = (P - N) / 2, T = C::T, Q = C::Q, SK = C::SKR, SEQ = C::SEQ;
     extern __shared__ float2 s[];
-    const int tid = threadIdx.x, f = blockIdx.y, Y0 = blockIdx.x * TILE_W;
+    const int tid = threadIdx.x, f = blockIdx.y;
     float2* out = buf + size_t(f) * P * P;
+    if constexpr (!IS_CPLX && PAD == 1) {
+        // Real input: rows 2w and 2w+1 of the tile ride as real and imaginary part of ONE complex
+        // sequence z = a + i b; one FFT gives both spectra, A[k] = (Z[k] + conj Z[-k]) / 2 and
+        // B[k] = (Z[k] - conj Z[-k]) / (2i).  A tile of W sequences covers 2 W rows, so the forward
+        // row pass of the binary state costs half the butterflies.  16 pixels per 128-bit load.
+        const int Y0 = blockIdx.x * (2 * TILE_W);
+        constexpr int CH = N / 16;                       // 16-pixel chunks per row
+        constexpr int NI = (TILE_W * CH + T - 1) / T;
+        int4 ra[NI], rb[NI];
+#pragma unroll
+        for (int k = 0; k < NI; ++k) {
+            const int i = tid + k * T;
+            if ((TILE_W * CH) % T == 0 || i < TILE_W * CH) {
+                const int w = i / CH, xc = i - w * CH;
+                const int8_t* base = reinterpret_cast<const int8_t*>(in) + (size_t(f) * N + Y0 + 2 * w) * N + 16 * xc;
+                ra[k] = __ldg(reinterpret_cast<const int4*>(base));
+                rb[k] = __ldg(reinterpret_cast<const int4*>(base + N));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NI; ++k) {
+            const int i = tid + k * T;
+            if ((TILE_W * CH) % T == 0 || i < TILE_W * CH) {
+                const int w = i / CH, xc = i - w * CH;
+                const int wa[4] = {ra[k].x, ra[k].y, ra[k].z, ra[k].w};
+                const int wb[4] = {rb[k].x, rb[k].y, rb[k].z, rb[k].w};
+                float2* d = s + w * SEQ + padded<SK>(16 * xc);   // 16 | X0: the chunk never straddles a pad slot
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    d[j] = make_float2(float(int8_t((wa[j >> 2] >> (8 * (j & 3))) & 0xff)),
+                                       float(int8_t((wb[j >> 2] >> (8 * (j & 3))) & 0xff)));
+            }
+        }
+        __syncthreads();
+        tile_fft<P, Q, 1, SK, false>(s + (tid / Q) * SEQ, tid % Q, tw);
+        constexpr int NXS = (P + T - 1) / T;
+#pragma unroll
+        for (int w = 0; w < TILE_W; ++w)
+#pragma unroll
+            for (int k = 0; k < NXS; ++k) {
+                const int X = tid + k * T;
+                if ((P % T == 0 || X < P) && X <= P / 2) {       // kx > P/2 follows from Hermitian symmetry
+                    const float2 zk = s[w * SEQ + padded<SK>(X)];
+                    const float2 zm = s[w * SEQ + padded<SK>(X == 0 ? 0 : P - X)];
+                    out[size_t(Y0 + 2 * w) * P + X] = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                    out[size_t(Y0 + 2 * w + 1) * P + X] = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+                }
+            }
+        return;
+    }
+    const int Y0 = blockIdx.x * TILE_W;
     if (PAD > 1 && (Y0 + TILE_W <= O || Y0 >= O + N)) {     // all-zero canvas rows
         for (int i = tid; i < TILE_W * P; i += T) out[size_t(Y0) * P + i] = make_float2(0.f, 0.f);
         return;
     }
-    if constexpr (!IS_CPLX && PAD == 1) {
-        // binary state: one 16-byte load = 16 pixels per thread, all loads of the tile in flight
-        constexpr int CH = N / 16;                       // 16-pixel chunks per row
-        constexpr int NI = (TILE_W * CH + T - 1) / T;
-        int4 raw[NI];
-#pragma unroll
-        for (int k = 0; k < NI; ++k) {
-            const int i = tid + k * T;
-            if ((TILE_W * CH) % T == 0 || i < TILE_W * CH) {
-                const int w = i / CH, xc = i - w * CH;
-                raw[k] = __ldg(reinterpret_cast<const int4*>(
-                    reinterpret_cast<const int8_t*>(in) + (size_t(f) * N + Y0 + w) * N + 16 * xc));
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < NI; ++k) {
-            const int i = tid + k * T;
-            if ((TILE_W * CH) % T == 0 || i < TILE_W * CH) {
-                const int w = i / CH, xc = i - w * CH;
-                const int words[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
-                float2* d = s + w * SEQ + padded<SK>(16 * xc);   // 16 | X0: the chunk never straddles a pad slot
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    d[j] = make_float2(float(int8_t((words[j >> 2] >> (8 * (j & 3))) & 0xff)), 0.f);
-            }
-        }
-    } else {
+    {
         constexpr int NX = (P + T - 1) / T;
         float2 v[TILE_W][NX];
 #pragma unroll
@@ -221,6 +246,84 @@ k_cols(float2* __restrict__ buf, const float2* __restrict__ H, const float2* __r
         const int y = q + k * Q;
         if ((P % Q == 0 || y < P) && (PAD == 1 || (y >= O && y < O + N)))
             b[size_t(y) * P + w] = s[padded<SK>(y) * TILE_W + w];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pass B for REAL input (the binary state, PAD == 1).  Every row spectrum is Hermitian along
+// kx, so column P-kx of the row-transformed frame is the complex conjugate of column kx and
+// pass A stored only kx in [0, P/2].  One forward column FFT F = FFT_y(col_kx) serves two
+// output columns:
+//     out[:, kx]   = IFFT_y(F * H[:, kx])
+//     out[:, P-kx] = conj( IFFT_y(F * conj(H[:, kx])) )        (H is even in kx and ky)
+// i.e. 3 tile FFTs per 16 output columns instead of 4, and half the tile reads.
+// grid (P / (2 W) + 1, frames): the last tile holds the Nyquist column kx = P/2 alone.
+// ---------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(FftCfg<P>::TC, FftCfg<P>::MINBC)
+k_cols_herm(float2* __restrict__ buf, const float2* __restrict__ H, const float2* __restrict__ tw) {
+    using C = FftCfg<P>;
+    constexpr int Q = C::Q, SK = C::SKC, W = C::WC;
+    constexpr int NY = (P + Q - 1) / Q;
+    constexpr int TILE = SeqLen<P, SK>::value * W;
+    extern __shared__ float2 s[];                   // [2][TILE]
+    float2* sA = s;
+    float2* sB = s + TILE;
+    const int tid = threadIdx.x, f = blockIdx.y, X0 = blockIdx.x * W;
+    const int w = tid % W, q = tid / W;
+    const int kx = X0 + w;
+    const bool col_ok = kx <= P / 2;                // only the last tile has invalid columns
+    float2* b = buf + size_t(f) * P * P;
+    {
+        float2 v[NY];
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+            const int y = q + k * Q;
+            v[k] = make_float2(0.f, 0.f);
+            if ((P % Q == 0 || y < P) && col_ok) v[k] = b[size_t(y) * P + kx];
+        }
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+            const int y = q + k * Q;
+            if (P % Q == 0 || y < P) sA[padded<SK>(y) * W + w] = v[k];
+        }
+    }
+    __syncthreads();
+    tile_fft<P, Q, W, SK, false>(sA + w, q, tw);
+    {
+        float2 hv[NY];
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+            const int y = q + k * Q;
+            hv[k] = make_float2(0.f, 0.f);
+            if ((P % Q == 0 || y < P) && col_ok) hv[k] = __ldg(H + size_t(y) * P + kx);
+        }
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+            const int y = q + k * Q;
+            if (P % Q == 0 || y < P) {
+                const int a = padded<SK>(y) * W + w;
+                const float2 F = sA[a];
+                sA[a] = cmul(F, hv[k]);
+                sB[a] = cmul(F, make_float2(hv[k].x, -hv[k].y));
+            }
+        }
+    }
+    __syncthreads();
+    tile_fft<P, Q, W, SK, true>(sA + w, q, tw);
+    tile_fft<P, Q, W, SK, true>(sB + w, q, tw);
+    const bool mirror_ok = col_ok && kx != 0 && kx != P / 2;
+#pragma unroll
+    for (int k = 0; k < NY; ++k) {
+        const int y = q + k * Q;
+        if (P % Q == 0 || y < P) {
+            const int a = padded<SK>(y) * W + w;
+            if (col_ok) b[size_t(y) * P + kx] = sA[a];
+            if (mirror_ok) {
+                const float2 m = sB[a];
+                b[size_t(y) * P + (P - kx)] = make_float2(m.x, -m.y);
+            }
+        }
     }
 }
 
