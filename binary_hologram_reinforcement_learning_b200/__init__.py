@@ -9,7 +9,7 @@ from .engine import (HoloEngine, HoloError, RULE_ENV, RULE_DBS, RULE_NEVER, RESU
                      load_library, simulate)
 from .envs import (BinaryHologramEnv, BinaryHologramEnvRGB, BinaryHologramEnvRGBCrop,
                    BinaryHologramEnvGroup, RW, WL_MONO, WL_RGB)
-from .vec_env import HologramVecEnv
+from .vec_env import HologramVecEnv, as_sb3_vec_env
 from .dbs import (optimize_with_random_pixel_flips, dbs_greedy_env, dbs_sweep, sweep_engine,
                   decile_index, OUTPUT_BINS)
 from .synthetic import synthetic_problem, SyntheticLoader
@@ -18,7 +18,7 @@ from .data import ImageFolderLoader, load_image, crop_to
 __all__ = [
     "HoloEngine", "HoloError", "RULE_ENV", "RULE_DBS", "RULE_NEVER", "RESULT_DTYPE", "load_library",
     "simulate", "BinaryHologramEnv", "BinaryHologramEnvRGB", "BinaryHologramEnvRGBCrop",
-    "BinaryHologramEnvGroup", "RW", "WL_MONO", "WL_RGB", "HologramVecEnv",
+    "BinaryHologramEnvGroup", "RW", "WL_MONO", "WL_RGB", "HologramVecEnv", "as_sb3_vec_env",
     "optimize_with_random_pixel_flips", "dbs_greedy_env", "dbs_sweep", "sweep_engine",
     "decile_index", "OUTPUT_BINS", "synthetic_problem", "SyntheticLoader", "ImageFolderLoader",
     "load_image", "crop_to",

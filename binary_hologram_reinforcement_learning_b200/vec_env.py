@@ -261,3 +261,56 @@ class HologramVecEnv:
 
     def close(self):
         self.engine.close()
+
+
+def as_sb3_vec_env(vec: HologramVecEnv):
+    """Wrap a :class:`HologramVecEnv` in Stable-Baselines3's ``VecEnv`` interface.
+
+    The reference hands a single env to SB3, which wraps it in ``DummyVecEnv``
+    (train-PPO.py:296-298).  With this adapter ``PPO("MultiInputPolicy", as_sb3_vec_env(vec))``
+    trains on E GPU-resident envs whose steps are one batched launch.  Needs
+    stable_baselines3 (not shipped in the build image); observations are stacked per key.
+    """
+    from stable_baselines3.common.vec_env import VecEnv
+
+    class _HologramSB3VecEnv(VecEnv):
+        def __init__(self, inner: HologramVecEnv):
+            self.inner = inner
+            inner.obs_mode = "stacked"
+            super().__init__(inner.num_envs, inner.observation_space, inner.action_space)
+
+        def reset(self):
+            return self.inner.reset()
+
+        def step_async(self, actions):
+            self.inner.step_async(actions)
+
+        def step_wait(self):
+            obs, rewards, dones, infos = self.inner.step_wait()
+            return obs, rewards.astype(np.float32), dones, infos
+
+        def close(self):
+            self.inner.close()
+
+        def seed(self, seed=None):
+            return [None] * self.num_envs
+
+        def _targets(self, indices):
+            idx = range(self.num_envs) if indices is None else ([indices] if isinstance(indices, int) else indices)
+            return [self.inner.envs[i] for i in idx]
+
+        def get_attr(self, attr_name, indices=None):
+            self.inner.sync_envs()
+            return [getattr(e, attr_name) for e in self._targets(indices)]
+
+        def set_attr(self, attr_name, value, indices=None):
+            for e in self._targets(indices):
+                setattr(e, attr_name, value)
+
+        def env_method(self, method_name, *args, indices=None, **kwargs):
+            return [getattr(e, method_name)(*args, **kwargs) for e in self._targets(indices)]
+
+        def env_is_wrapped(self, wrapper_class, indices=None):
+            return [False for _ in self._targets(indices)]
+
+    return _HologramSB3VecEnv(vec)
