@@ -6,6 +6,9 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
+
 timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -25 > gpurun_out/pytest_gpu.log
 echo "pytest rc=${PIPESTATUS[0]}"; tail -3 gpurun_out/pytest_gpu.log
 
