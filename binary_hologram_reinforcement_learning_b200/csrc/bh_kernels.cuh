@@ -910,7 +910,7 @@ k_recon_candidate(const float2* __restrict__ U, const float2* __restrict__ h,
 // i.e. ifft2(fft2(W) K) -- the propagation passes with a different spectrum K.
 // All N^2 candidates of a frame cost a handful of FFTs instead of N^2 delta passes.
 // ---------------------------------------------------------------------------
-enum { PREP_UA = 0, PREP_U = 1, PREP_U2 = 2, PREP_ABS2_PAIR = 3, PREP_TI = 4 };
+enum { PREP_UA = 0, PREP_U = 1, PREP_U2 = 2, PREP_ABS2_PAIR = 3, PREP_TI = 4, PREP_ONES = 5 };
 
 // grid (blocks, planes).  U: group base [Fg][n2]; A, B: real planes of the group.
 __global__ void __launch_bounds__(256)
@@ -932,14 +932,16 @@ k_sweep_prep(const float2* __restrict__ U, const float* __restrict__ A, const fl
         } else if (mode == PREP_ABS2_PAIR) {
             const float2 u0 = U[size_t(2 * pl) * n2 + p], u1 = U[size_t(2 * pl + 1) * n2 + p];
             v = make_float2(u0.x * u0.x + u0.y * u0.y, u1.x * u1.x + u1.y * u1.y);
-        } else {
+        } else if (mode == PREP_TI) {
             v = make_float2(A[p], B[p]);
+        } else {
+            v = make_float2(1.f, 0.f);               // window indicator (pad = 2: sum |h_s|^4 over the window)
         }
         o[p] = v;
     }
 }
 
-enum { ACC_RE = 0, ACC_PAIR = 1, ACC_GROUP = 2 };
+enum { ACC_RE = 0, ACC_PAIR = 1, ACC_GROUP = 2, ACC_GROUP_RE = 3 };
 
 // accumulate coef * part(S) into the per-candidate planes.
 //   ACC_RE    plane i -> frame i:   dst[i] += coef * (use_sign ? sgn : 1) * Re S[i]
@@ -960,10 +962,12 @@ k_sweep_acc(const float2* __restrict__ S, float* __restrict__ dIT, float* __rest
             const float2 v = S[size_t(pl) * n2 + p];
             dII[size_t(2 * pl) * n2 + p] += coef * v.x;
             dII[size_t(2 * pl + 1) * n2 + p] += coef * v.y;
-        } else {
+        } else if (mode == ACC_GROUP) {
             const float2 v = S[p];
             dIT[size_t(pl) * n2 + p] += coef * v.x;
             dII[size_t(pl) * n2 + p] += coef2 * v.y + cst;
+        } else {                                     // ACC_GROUP_RE: plane 0 -> dII of every frame
+            dII[size_t(pl) * n2 + p] += coef * S[p].x;
         }
     }
 }

@@ -143,7 +143,7 @@ inline std::shared_ptr<HostTables> get_tables(int P, double wl, double dx, doubl
 // response the delta kernel uses: K3 = fft2(h|h|^2), K4 = fft2(|h|^2), K5 = fft2(h^2),
 // each pre-scaled by 1/P^2 like H; m4 = sum |h|^4.
 struct SweepTables {
-    std::vector<float> K3, K4, K5;   // interleaved complex [P][P]
+    std::vector<float> K3, K4, K5, K6;   // interleaved complex [P][P]; K6 = fft2(|h|^4) (pad = 2 only)
     double m4 = 0.0;
 };
 
@@ -151,12 +151,12 @@ inline std::shared_ptr<SweepTables> build_sweep_tables(const HostTables& t) {
     const int P = t.P;
     const size_t n = size_t(P) * P;
     auto out = std::make_shared<SweepTables>();
-    std::vector<cd> k3(n), k4(n), k5(n);
+    std::vector<cd> k3(n), k4(n), k5(n), k6(n);
     double m4 = 0.0;
     for (size_t i = 0; i < n; ++i) {
         const cd h(double(t.h[2 * i]), double(t.h[2 * i + 1]));
         const double a2 = std::norm(h);
-        k3[i] = h * a2; k4[i] = cd(a2, 0.0); k5[i] = h * h;
+        k3[i] = h * a2; k4[i] = cd(a2, 0.0); k5[i] = h * h; k6[i] = cd(a2 * a2, 0.0);
         m4 += a2 * a2;
     }
     out->m4 = m4;
@@ -166,7 +166,7 @@ inline std::shared_ptr<SweepTables> build_sweep_tables(const HostTables& t) {
         K.resize(2 * n);
         for (size_t i = 0; i < n; ++i) { K[2 * i] = float(k[i].real() * inv); K[2 * i + 1] = float(k[i].imag() * inv); }
     };
-    run(k3, out->K3); run(k4, out->K4); run(k5, out->K5);
+    run(k3, out->K3); run(k4, out->K4); run(k5, out->K5); run(k6, out->K6);
     return out;
 }
 

@@ -43,7 +43,8 @@ struct bh_ctx {
     unsigned* d_tickets = nullptr;
     long long* d_scalars = nullptr;      // [0] dbs cursor, [1] accepted count
     // correlation sweep (allocated on first use)
-    float2 *dK3 = nullptr, *dK4 = nullptr, *dK5 = nullptr, *dsw_in = nullptr, *dsw_out = nullptr;
+    float2 *dK3 = nullptr, *dK4 = nullptr, *dK5 = nullptr, *dK6 = nullptr, *dsw_in = nullptr, *dsw_out = nullptr;
+    float2* dsw_buf = nullptr;           // pad = 2: P x P working planes of the correlation passes
     float *dsw_it = nullptr, *dsw_ii = nullptr;
     double* dsw_psnr = nullptr;
     std::vector<double> m4;
@@ -241,7 +242,8 @@ extern "C" int bh_destroy(bh_ctx* c) {
     cudaFree(c->dloss_partial);
     cudaFree(c->d_envs); cudaFree(c->d_actions); cudaFree(c->d_results); cudaFree(c->d_acc);
     cudaFree(c->d_tickets); cudaFree(c->d_scalars);
-    cudaFree(c->dK3); cudaFree(c->dK4); cudaFree(c->dK5); cudaFree(c->dsw_in); cudaFree(c->dsw_out);
+    cudaFree(c->dK3); cudaFree(c->dK4); cudaFree(c->dK5); cudaFree(c->dK6); cudaFree(c->dsw_in); cudaFree(c->dsw_out);
+    cudaFree(c->dsw_buf);
     cudaFree(c->dsw_it); cudaFree(c->dsw_ii); cudaFree(c->dsw_psnr);
     cudaFreeHost(c->h_envs); cudaFreeHost(c->h_actions); cudaFreeHost(c->h_results);
     cudaFreeHost(c->h_scalars); cudaFreeHost(c->h_sums);
@@ -755,6 +757,10 @@ static int sweep_setup(bh_ctx* c) {
     BH_CUDA(c, cudaMalloc(&c->dK3, size_t(c->G) * p2 * sizeof(float2)));
     BH_CUDA(c, cudaMalloc(&c->dK4, size_t(c->G) * p2 * sizeof(float2)));
     BH_CUDA(c, cudaMalloc(&c->dK5, size_t(c->G) * p2 * sizeof(float2)));
+    if (c->pad == 2) {
+        BH_CUDA(c, cudaMalloc(&c->dK6, size_t(c->G) * p2 * sizeof(float2)));
+        BH_CUDA(c, cudaMalloc(&c->dsw_buf, size_t(c->Fg) * p2 * sizeof(float2)));
+    }
     BH_CUDA(c, cudaMalloc(&c->dsw_in, size_t(c->Fg) * n2 * sizeof(float2)));
     BH_CUDA(c, cudaMalloc(&c->dsw_out, size_t(c->Fg) * n2 * sizeof(float2)));
     BH_CUDA(c, cudaMalloc(&c->dsw_it, size_t(c->Fg) * n2 * sizeof(float)));
@@ -768,6 +774,8 @@ static int sweep_setup(bh_ctx* c) {
         BH_CUDA(c, cudaMemcpy(c->dK3 + size_t(g) * p2, sw->K3.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
         BH_CUDA(c, cudaMemcpy(c->dK4 + size_t(g) * p2, sw->K4.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
         BH_CUDA(c, cudaMemcpy(c->dK5 + size_t(g) * p2, sw->K5.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
+        if (c->pad == 2)
+            BH_CUDA(c, cudaMemcpy(c->dK6 + size_t(g) * p2, sw->K6.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
     }
     return 0;
 }
@@ -775,7 +783,6 @@ static int sweep_setup(bh_ctx* c) {
 extern "C" int bh_sweep_all(bh_ctx* c, int env, double* psnr_after, int on_host) {
     BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
     if (!psnr_after) BH_FAIL(c, -1, "psnr_after is null");
-    if (c->pad != 1) BH_FAIL(c, -4, "bh_sweep_all supports pad = 1 (circular) only; use bh_eval_flips");
     if (c->Fg % 2) BH_FAIL(c, -4, "bh_sweep_all needs an even number of frames per colour group");
     if (int rc = sweep_setup(c)) return rc;
     const size_t n2 = c->n2, p2 = size_t(c->P) * c->P;
@@ -796,8 +803,10 @@ extern "C" int bh_sweep_all(bh_ctx* c, int env, double* psnr_after, int on_host)
         auto corr = [&](int mode, const float* A, const float* B, int planes, const float2* K) -> int {
             k_sweep_prep<<<dim3(gx, planes), blk, 0, st>>>(U, A, B, c->dsw_in, n2, mode);
             bool ok = false;
-            BH_CUDA(c, (dispatch_prop<float2, true>(c->P, 1, c->dsw_in, c->dsw_out, c->dsw_out, K, c->dtw,
-                                                    planes, planes, st, &ok)));
+            // pad = 2: the N x N plane is embedded in the P x P canvas by pass A and pass C returns the
+            // window, i.e. exactly the window-restricted correlation the linear propagation needs
+            BH_CUDA(c, (dispatch_prop<float2, true>(c->P, c->pad, c->dsw_in, c->pad == 1 ? c->dsw_out : c->dsw_buf,
+                                                    c->dsw_out, K, c->dtw, planes, planes, st, &ok)));
             if (!ok) BH_FAIL(c, -4, "unsupported FFT side P=%d", c->P);
             c->launches += 4;
             return 0;
@@ -819,7 +828,13 @@ extern "C" int bh_sweep_all(bh_ctx* c, int env, double* psnr_after, int on_host)
         if ((rc = corr(PREP_ABS2_PAIR, nullptr, nullptr, Fg / 2, K4))) return rc;   // C4, two frames per plane
         acc(ACC_PAIR, Fg / 2, 1, 0, 2.f * iF2, 0.f, 0.f);
         if ((rc = corr(PREP_TI, T, I, 1, K4))) return rc;                 // BT + i BI
-        acc(ACC_GROUP, Fg, 1, 0, iF, 2.f * iF, float(c->m4[g] * double(iF2)));
+        if (c->pad == 1) {
+            acc(ACC_GROUP, Fg, 1, 0, iF, 2.f * iF, float(c->m4[g] * double(iF2)));    // sum |h|^4 is a constant
+        } else {
+            acc(ACC_GROUP, Fg, 1, 0, iF, 2.f * iF, 0.f);
+            if ((rc = corr(PREP_ONES, nullptr, nullptr, 1, c->dK6 + size_t(g) * p2))) return rc;   // window * |h|^4
+            acc(ACC_GROUP_RE, Fg, 1, 0, iF2, 0.f, 0.f);
+        }
         const size_t count = size_t(Fg) * n2;
         double* dst = on_host ? c->dsw_psnr : psnr_after + size_t(g) * count;
         k_sweep_final<<<int(std::min<size_t>((count + 255) / 256, 148 * 16)), blk, 0, st>>>(

@@ -223,7 +223,7 @@ def sweep_engine(eng: HoloEngine, env_index: int, pre_model: np.ndarray, order: 
     """
     order = np.asarray(order, dtype=np.int64)
     use_map = psnr_map is not None or exhaustive is True or (
-        exhaustive == "auto" and eng.pad == 1 and eng.Fg % 2 == 0
+        exhaustive == "auto" and eng.Fg % 2 == 0
         and order.shape[0] * 4 >= eng.num_pixels)
     if use_map:
         if psnr_map is None:
@@ -307,7 +307,7 @@ def dbs_sweep(target_function: Callable, trainloader: Iterable, z=2e-3, pixel_pi
         psnr_all = np.empty(hi_all - lo_all, dtype=np.float64)
         flip_count = 0
         psnr_map = None
-        if (eng.pad == 1 and eng.Fg % 2 == 0 and shard is None and max_candidates is None
+        if (eng.Fg % 2 == 0 and shard is None and max_candidates is None
                 and perm.shape[0] == n):
             # the whole image in one call: correlation sweep + decile statistics on the device
             att, imp, gn, psnr_map = eng.sweep_stats(cpre, OUTPUT_BINS, 0, want_map=True)
@@ -328,7 +328,7 @@ def dbs_sweep(target_function: Callable, trainloader: Iterable, z=2e-3, pixel_pi
                 _print_bins(bin_counts, imp, gn, att)
                 print("\n")
             continue
-        if eng.pad == 1 and eng.Fg % 2 == 0 and (hi_all - lo_all) * 4 >= n:
+        if eng.Fg % 2 == 0 and (hi_all - lo_all) * 4 >= n:
             psnr_map = eng.sweep_all(0)                    # every candidate in one call
         for lo in range(lo_all, hi_all, chunk):
             hi = min(hi_all, lo + chunk)

@@ -93,8 +93,7 @@ int bh_eval_flips(bh_ctx* ctx, int env, int64_t n, const int32_t* env_ids,
  * DBS_1024_24-128.py:310-373): psnr_after[frame][row][col], F*N*N doubles, equal to
  * what bh_eval_flips returns for the same action.  Evaluated as cross-correlations
  * with the (even) impulse-response kernels through the FFT passes -- O(N^2 log N)
- * per frame instead of N^2 delta passes.  pad = 1 only.  Device pointer when
- * on_host = 0. */
+ * per frame instead of N^2 delta passes.  Device pointer when on_host = 0. */
 int bh_sweep_all(bh_ctx* ctx, int env, double* psnr_after, int on_host);
 
 /* bh_sweep_all followed by the decile statistics of dbs-1024-1024-24-6464.py:377-395 on the

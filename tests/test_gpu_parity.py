@@ -112,14 +112,15 @@ def test_eval_flips_matches_full_resimulation(N, F, wl, pad, relative):
     eng.close()
 
 
-@pytest.mark.parametrize("N,F,wl,relative", [
-    (64, 8, O.WL_MONO, True), (64, 6, O.WL_RGB, True), (128, 6, O.WL_RGB, False), (256, 8, O.WL_MONO, True),
+@pytest.mark.parametrize("N,F,wl,relative,pad", [
+    (64, 8, O.WL_MONO, True, 1), (64, 6, O.WL_RGB, True, 1), (128, 6, O.WL_RGB, False, 1),
+    (256, 8, O.WL_MONO, True, 1), (64, 8, O.WL_MONO, True, 2), (128, 6, O.WL_RGB, True, 2),
 ])
-def test_sweep_all_correlation_matches_oracle_and_delta_kernel(N, F, wl, relative):
+def test_sweep_all_correlation_matches_oracle_and_delta_kernel(N, F, wl, relative, pad):
     """bh_sweep_all (FFT correlations) == bh_eval_flips (delta kernel) == full re-simulation."""
     pre, tgt, st = _problem(N, F, wl, seed=23)
-    cfg = O.HoloConfig(N=N, F=F, wl=wl, relative=relative)
-    eng = _engine(N, F, wl, 1, relative)
+    cfg = O.HoloConfig(N=N, F=F, wl=wl, relative=relative, pad=pad)
+    eng = _engine(N, F, wl, pad, relative)
     eng.set_target(0, tgt)
     eng.load_state(0, st)
     psnr0 = eng.metrics(0)[0]
