@@ -66,7 +66,8 @@ template <int P> struct FftCfg {
     static constexpr int SKC = ilog2_c(Plan<P>::r[0]);  // column layout: pad after every R0 elements
     static constexpr int SEQ = SeqLen<P, SKR>::value;   // row layout: stride between sequences
     static constexpr size_t smem_row = size_t(SEQ) * TILE_W * sizeof(float2);
-    static constexpr int WC = BH_COLS_W;                // columns per tile of the column pass
+    static constexpr int WC = (P > 1024) ? 4 : BH_COLS_W;   // columns per tile of the column pass (32 values per
+                                                            // thread at P = 2048: 4 columns x 64 threads, 255 regs)
     static constexpr int TC = WC * Q;
     static constexpr int MINBC = (P <= 1024) ? BH_COLS_MINB : 1;
     static constexpr size_t smem_col = size_t(SeqLen<P, SKC>::value) * WC * sizeof(float2);
@@ -97,23 +98,42 @@ k_rows_fwd(const InT* __restrict__ in, float2* __restrict__ buf, const float2* _
     extern __shared__ float2 s[];
     const int tid = threadIdx.x, f = blockIdx.y;
     float2* out = buf + size_t(f) * P * P;
-    if constexpr (!IS_CPLX && PAD == 1) {
-        // Real input: rows 2w and 2w+1 of the tile ride as real and imaginary part of ONE complex
-        // sequence z = a + i b; one FFT gives both spectra, A[k] = (Z[k] + conj Z[-k]) / 2 and
+    if constexpr (!IS_CPLX) {
+        // Real input: canvas rows 2w and 2w+1 of the tile ride as real and imaginary part of ONE
+        // complex sequence z = a + i b; one FFT gives both spectra, A[k] = (Z[k] + conj Z[-k]) / 2 and
         // B[k] = (Z[k] - conj Z[-k]) / (2i).  A tile of W sequences covers 2 W rows, so the forward
-        // row pass of the binary state costs half the butterflies.  16 pixels per 128-bit load.
+        // row pass of the binary state costs half the butterflies, and only kx <= P/2 is stored
+        // (the rest follows from Hermitian symmetry, see k_cols_herm).  16 pixels per 128-bit load.
         const int Y0 = blockIdx.x * (2 * TILE_W);
+        constexpr int NXS = (P + T - 1) / T;
+        if (PAD > 1 && (Y0 + 2 * TILE_W <= O || Y0 >= O + N)) {      // all-zero canvas rows
+            for (int i = tid; i < 2 * TILE_W * (P / 2 + 1); i += T) {
+                const int r = i / (P / 2 + 1), X = i - r * (P / 2 + 1);
+                out[size_t(Y0 + r) * P + X] = make_float2(0.f, 0.f);
+            }
+            return;
+        }
+        if (PAD > 1) {                                   // zero margins of the canvas rows
+#pragma unroll
+            for (int w = 0; w < TILE_W; ++w)
+                for (int i = tid; i < P - N; i += T) {
+                    const int X = (i < O) ? i : i + N;
+                    s[w * SEQ + padded<SK>(X)] = make_float2(0.f, 0.f);
+                }
+        }
         constexpr int CH = N / 16;                       // 16-pixel chunks per row
         constexpr int NI = (TILE_W * CH + T - 1) / T;
         int4 ra[NI], rb[NI];
 #pragma unroll
         for (int k = 0; k < NI; ++k) {
             const int i = tid + k * T;
+            ra[k] = make_int4(0, 0, 0, 0); rb[k] = make_int4(0, 0, 0, 0);
             if ((TILE_W * CH) % T == 0 || i < TILE_W * CH) {
                 const int w = i / CH, xc = i - w * CH;
-                const int8_t* base = reinterpret_cast<const int8_t*>(in) + (size_t(f) * N + Y0 + 2 * w) * N + 16 * xc;
-                ra[k] = __ldg(reinterpret_cast<const int4*>(base));
-                rb[k] = __ldg(reinterpret_cast<const int4*>(base + N));
+                const int ya = Y0 + 2 * w - O, yb = ya + 1;
+                const int8_t* base = reinterpret_cast<const int8_t*>(in) + size_t(f) * N * N + 16 * xc;
+                if (PAD == 1 || (ya >= 0 && ya < N)) ra[k] = __ldg(reinterpret_cast<const int4*>(base + size_t(ya) * N));
+                if (PAD == 1 || (yb >= 0 && yb < N)) rb[k] = __ldg(reinterpret_cast<const int4*>(base + size_t(yb) * N));
             }
         }
 #pragma unroll
@@ -123,7 +143,7 @@ k_rows_fwd(const InT* __restrict__ in, float2* __restrict__ buf, const float2* _
                 const int w = i / CH, xc = i - w * CH;
                 const int wa[4] = {ra[k].x, ra[k].y, ra[k].z, ra[k].w};
                 const int wb[4] = {rb[k].x, rb[k].y, rb[k].z, rb[k].w};
-                float2* d = s + w * SEQ + padded<SK>(16 * xc);   // 16 | X0: the chunk never straddles a pad slot
+                float2* d = s + w * SEQ + padded<SK>(O + 16 * xc);   // 16 | O + 16 xc: never straddles a pad slot
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     d[j] = make_float2(float(int8_t((wa[j >> 2] >> (8 * (j & 3))) & 0xff)),
@@ -132,7 +152,6 @@ k_rows_fwd(const InT* __restrict__ in, float2* __restrict__ buf, const float2* _
         }
         __syncthreads();
         tile_fft<P, Q, 1, SK, false>(s + (tid / Q) * SEQ, tid % Q, tw);
-        constexpr int NXS = (P + T - 1) / T;
 #pragma unroll
         for (int w = 0; w < TILE_W; ++w)
 #pragma unroll
@@ -165,8 +184,7 @@ k_rows_fwd(const InT* __restrict__ in, float2* __restrict__ buf, const float2* _
                 v[w][k] = make_float2(0.f, 0.f);
                 if ((P % T == 0 || X < P) && rowok && x >= 0 && x < N) {
                     const size_t idx = (size_t(f) * N + y) * N + x;
-                    if constexpr (IS_CPLX) v[w][k] = reinterpret_cast<const float2*>(in)[idx];
-                    else v[w][k].x = float(reinterpret_cast<const int8_t*>(in)[idx]);
+                    v[w][k] = reinterpret_cast<const float2*>(in)[idx];
                 }
             }
         }
@@ -250,7 +268,7 @@ k_cols(float2* __restrict__ buf, const float2* __restrict__ H, const float2* __r
 }
 
 // ---------------------------------------------------------------------------
-// pass B for REAL input (the binary state, PAD == 1).  Every row spectrum is Hermitian along
+// pass B for REAL input (the binary state).  Every row spectrum is Hermitian along
 // kx, so column P-kx of the row-transformed frame is the complex conjugate of column kx and
 // pass A stored only kx in [0, P/2].  One forward column FFT F = FFT_y(col_kx) serves two
 // output columns:
@@ -259,10 +277,11 @@ k_cols(float2* __restrict__ buf, const float2* __restrict__ H, const float2* __r
 // i.e. 3 tile FFTs per 16 output columns instead of 4, and half the tile reads.
 // grid (P / (2 W) + 1, frames): the last tile holds the Nyquist column kx = P/2 alone.
 // ---------------------------------------------------------------------------
-template <int P>
+template <int P, int PAD>
 __global__ void __launch_bounds__(FftCfg<P>::TC, FftCfg<P>::MINBC)
 k_cols_herm(float2* __restrict__ buf, const float2* __restrict__ H, const float2* __restrict__ tw) {
     using C = FftCfg<P>;
+    constexpr int N = P / PAD, O = (P - N) / 2;         // only window rows carry data / are needed
     constexpr int Q = C::Q, SK = C::SKC, W = C::WC;
     constexpr int NY = (P + Q - 1) / Q;
     constexpr int TILE = SeqLen<P, SK>::value * W;
@@ -280,7 +299,7 @@ k_cols_herm(float2* __restrict__ buf, const float2* __restrict__ H, const float2
         for (int k = 0; k < NY; ++k) {
             const int y = q + k * Q;
             v[k] = make_float2(0.f, 0.f);
-            if ((P % Q == 0 || y < P) && col_ok) v[k] = b[size_t(y) * P + kx];
+            if ((P % Q == 0 || y < P) && col_ok && (PAD == 1 || (y >= O && y < O + N))) v[k] = b[size_t(y) * P + kx];
         }
 #pragma unroll
         for (int k = 0; k < NY; ++k) {
@@ -316,7 +335,7 @@ k_cols_herm(float2* __restrict__ buf, const float2* __restrict__ H, const float2
 #pragma unroll
     for (int k = 0; k < NY; ++k) {
         const int y = q + k * Q;
-        if (P % Q == 0 || y < P) {
+        if ((P % Q == 0 || y < P) && (PAD == 1 || (y >= O && y < O + N))) {
             const int a = padded<SK>(y) * W + w;
             if (col_ok) b[size_t(y) * P + kx] = sA[a];
             if (mirror_ok) {

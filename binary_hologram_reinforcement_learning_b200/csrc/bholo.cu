@@ -121,13 +121,13 @@ static cudaError_t launch_prop(const InT* in, float2* buf, float2* U, const floa
     if ((e = cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smr)))) return e;
     (void)Fg;
     if (ev) cudaEventRecord(ev[0], st);
-    // real int8 input (pad = 1): two rows per sequence, so a tile covers 2 * TILE_W rows
-    constexpr int rows_per_tile = (!CPLX && PAD == 1) ? 2 * TILE_W : TILE_W;
+    // real int8 input: two rows per sequence, so a tile covers 2 * TILE_W rows
+    constexpr int rows_per_tile = !CPLX ? 2 * TILE_W : TILE_W;
     kA<<<dim3(P / rows_per_tile, frames), T, smr, st>>>(in, buf, tw);
     if (ev) cudaEventRecord(ev[1], st);
-    if constexpr (!CPLX && PAD == 1) {
+    if constexpr (!CPLX) {
         // real input: pass A stored kx <= P/2 only; one forward FFT feeds columns kx and P - kx
-        auto kBh = k_cols_herm<P>;
+        auto kBh = k_cols_herm<P, PAD>;
         if ((e = cudaFuncSetAttribute(kBh, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * smc)))) return e;
         kBh<<<dim3(P / (2 * FftCfg<P>::WC) + 1, frames), FftCfg<P>::TC, 2 * smc, st>>>(buf, H, tw);
     } else {
