@@ -56,6 +56,7 @@ class HologramVecEnv:
                       and recon_obs != "eager")
         self._group = reward_mode == "group"
         self._changes = self._ranks = None      # (E, num_samples) tables of env_group.py:90-143
+        self._sorted = [None] * self.num_envs
         E = self.num_envs
         self._steps = np.zeros(E, dtype=np.int64)
         self._flips = np.zeros(E, dtype=np.int64)
@@ -119,6 +120,11 @@ class HologramVecEnv:
                 self._ranks = np.zeros((self.num_envs, env.num_samples))
             self._changes[i] = env._psnr_change_arr
             self._ranks[i] = env.importance_ranks
+            # sorted view for the nearest-value lookup of env_group.py:254 (np.argmin semantics:
+            # the lowest original index among the nearest values)
+            order = np.argsort(env._psnr_change_arr, kind="stable")
+            sv = env._psnr_change_arr[order]
+            self._sorted[i] = (sv, order, np.searchsorted(sv, sv, side="left"))
 
     def sync_envs(self):
         """Push the vectorised counters back into the per-env objects."""
@@ -162,6 +168,23 @@ class HologramVecEnv:
         self._ep_reward[:] = 0
         return self._pack(obs)
 
+    def _nearest(self, i: int, x: float) -> int:
+        """argmin(|psnr_change_list - x|) of env i in O(log n): same index as np.argmin."""
+        sv, order, run_start = self._sorted[i]
+        n = sv.shape[0]
+        j = int(np.searchsorted(sv, x, side="left"))
+        if j == 0:
+            return int(order[0])
+        if j == n:
+            return int(order[run_start[n - 1]])
+        dl, dr = abs(sv[j - 1] - x), abs(sv[j] - x)
+        if dr < dl:
+            return int(order[j])
+        left = int(order[run_start[j - 1]])
+        if dl < dr:
+            return left
+        return min(left, int(order[j]))
+
     def _step_fast(self):
         """env.py:154-260 for all envs with numpy; per-env Python only on episode events."""
         acts, envs, E = self._actions, self.envs, self.num_envs
@@ -170,8 +193,9 @@ class HologramVecEnv:
         psnr_after = res["psnr_after"]
         diff = self._diff
         if self._group:                                              # env_group.py:254-255
-            idx = np.abs(self._changes - self._change[:, None]).argmin(axis=1)
-            rewards = self._ranks[self._ar, idx].copy()
+            rewards = np.empty(E)
+            for i in range(E):
+                rewards[i] = self._ranks[i, self._nearest(i, self._change[i])]
         else:
             rewards = self._rewards.copy()                           # env.py:188
         infos = [{} for _ in range(E)]
