@@ -79,7 +79,8 @@ class BinaryHologramEnv(spaces.Env):
                  recon_obs: str = "eager", device: int = 0, pad: int = 1, relative: bool = True,
                  method: str = "asm", verbose: bool = True, num_samples: int = 10000,
                  engine: Optional[HoloEngine] = None, env_index: int = 0,
-                 rng: Optional[np.random.Generator] = None, resync_every: int = 1024):
+                 rng: Optional[np.random.Generator] = None, resync_every: int = 1024,
+                 action_mode: str = "discrete"):
         super().__init__()
         self.IPS, self.CH, self.wl = int(IPS), int(CH), tuple(wl)
         self.G = len(self.wl)
@@ -101,7 +102,11 @@ class BinaryHologramEnv(spaces.Env):
             "target_image": spaces.Box(low=0, high=1, shape=img_shape, dtype=np.float32),
         })
         self.num_pixels = CH * IPS * IPS                  # env.py:51-52
-        self.action_space = spaces.Discrete(self.num_pixels)
+        self.action_mode = action_mode
+        if action_mode == "multidiscrete":                # env_md.py:54,160: [channel, row, col]
+            self.action_space = spaces.MultiDiscrete([CH, IPS, IPS])
+        else:
+            self.action_space = spaces.Discrete(self.num_pixels)
 
         self.target_function = target_function
         self.trainloader = trainloader
@@ -288,6 +293,11 @@ class BinaryHologramEnv(spaces.Env):
 
     # -- env.py:154-260 --------------------------------------------------
     def step(self, action, z=2e-3, pixel_pitch=7.56e-6):
+        if np.ndim(action) == 1 and len(action) == 3:     # env_md.py:160 (channel, row, col)
+            ch, r, c = (int(v) for v in action)
+            if not (0 <= ch < self.CH and 0 <= r < self.IPS and 0 <= c < self.IPS):
+                raise ValueError(f"action {action} outside MultiDiscrete([{self.CH}, {self.IPS}, {self.IPS}])")
+            action = (ch * self.IPS + r) * self.IPS + c
         action = int(action)
         if not 0 <= action < self.num_pixels:
             raise ValueError(f"action {action} outside Discrete({self.num_pixels})")

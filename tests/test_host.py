@@ -189,3 +189,18 @@ def test_sweep_shard_partition_is_a_partition():
     assert np.array_equal(cover, np.arange(n))
     assert [dist.shard_range(n, r, world) for r in range(world)] == \
         [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+
+
+def test_variant_modules_and_multidiscrete_action_space():
+    """compat/env_md.py (MultiDiscrete action, env_md.py:54) and env_05.py (T_PSNR_DIFF 0.5) resolve."""
+    compat = os.path.join(ROOT, "binary_hologram_reinforcement_learning_b200", "compat")
+    sys.path.insert(0, compat)
+    try:
+        import env_md, env_05
+    finally:
+        sys.path.remove(compat)
+    ld = bh.SyntheticLoader(32, 4, 1, seeds=(1,))
+    e = env_md.BinaryHologramEnv(ld.target_function, ld, IPS=32, CH=4, verbose=False)
+    assert list(e.action_space.nvec) == [4, 32, 32]
+    e5 = env_05.BinaryHologramEnv(ld.target_function, ld, IPS=32, CH=4, verbose=False)
+    assert e5.T_PSNR_DIFF == 0.5 and e5.action_space.n == 4 * 32 * 32
