@@ -712,3 +712,25 @@ def test_group_rollouts_from_cloned_reset_state():
         assert np.array_equal(grp.envs[i].state, ind.envs[i].state)
         assert np.array_equal(grp.engine.state(i), ind.engine.state(i))
     grp.close(); ind.close()
+
+
+def test_multidiscrete_action_equals_flat_action():
+    """env_md.py:160: action (channel, row, col) addresses the same pixel as the flat index."""
+    N, F = 64, 8
+    def make(mode):
+        ld = bh.SyntheticLoader(N, F, 1, seeds=(77,))
+        e = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, verbose=False, T_PSNR_DIFF=1e9,
+                                 action_mode=mode)
+        e.reset()
+        return e
+    a, b = make("multidiscrete"), make("discrete")
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        ch, r, c = int(rng.integers(F)), int(rng.integers(N)), int(rng.integers(N))
+        ra = a.step(np.array([ch, r, c]))
+        rb = b.step((ch * N + r) * N + c)
+        assert ra[1] == rb[1] and ra[2:4] == rb[2:4]
+    assert np.array_equal(a.state, b.state)
+    with pytest.raises(ValueError):
+        a.step(np.array([F, 0, 0]))
+    a.close(); b.close()
