@@ -138,8 +138,34 @@ template <bool INV> BH_HD void dft7(float2* v) {
     v[3] = cadd(a3, ib3); v[4] = csub(a3, ib3);
 }
 
+template <bool INV> BH_HD void dft32(float2* v) {
+    // R1 = 2 (a), R2 = 16 (b): r = a*16 + b ; X[c + 2 d]
+    const float cs[16] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                          0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                          0.19509032201612826785f, 0.f, -0.19509032201612826785f, -0.38268343236508977173f,
+                          -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+                          -0.92387953251128675613f, -0.98078528040323044913f};
+    const float sn[16] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                          0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
+                          0.98078528040323044913f, 1.f, 0.98078528040323044913f, 0.92387953251128675613f,
+                          0.83146961230254523708f, 0.70710678118654752440f, 0.55557023301960222474f,
+                          0.38268343236508977173f, 0.19509032201612826785f};
+#pragma unroll
+    for (int b = 0; b < 16; ++b) dft2<INV>(v[b], v[16 + b]);
+#pragma unroll
+    for (int b = 1; b < 16; ++b) v[16 + b] = cmulw<INV>(v[16 + b], cs[b], -sn[b]);   // W32^b
+    dft16<INV>(v);          // c = 0 -> X[0], X[2], ..., X[30] in v[0..15]
+    dft16<INV>(v + 16);     // c = 1 -> X[1], X[3], ..., X[31] in v[16..31]
+    float2 t[32];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) { t[2 * d] = v[d]; t[2 * d + 1] = v[16 + d]; }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = t[k];
+}
+
 template <int R, bool INV> BH_HD void dft(float2* v) {
-    if (R == 2) dft2<INV>(v[0], v[1]);
+    if (R == 32) dft32<INV>(v);
+    else if (R == 2) dft2<INV>(v[0], v[1]);
     else if (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
     else if (R == 8) dft8<INV>(v);
     else if (R == 16) dft16<INV>(v);
@@ -172,7 +198,7 @@ template <> struct Plan<128>  { static constexpr int n = 2; static constexpr int
 template <> struct Plan<256>  { static constexpr int n = 2; static constexpr int r[3] = {16, 16, 1}; };
 template <> struct Plan<512>  { static constexpr int n = 3; static constexpr int r[3] = {8, 8, 8}; };
 template <> struct Plan<896>  { static constexpr int n = 3; static constexpr int r[3] = {16, 8, 7}; };
-template <> struct Plan<1024> { static constexpr int n = 3; static constexpr int r[3] = {16, 16, 4}; };
+template <> struct Plan<1024> { static constexpr int n = 2; static constexpr int r[3] = {32, 32, 1}; };   // two passes
 template <> struct Plan<1792> { static constexpr int n = 3; static constexpr int r[3] = {16, 16, 7}; };
 template <> struct Plan<2048> { static constexpr int n = 3; static constexpr int r[3] = {16, 16, 8}; };
 

@@ -59,10 +59,12 @@ constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
 
 // threads: P/16 per sequence at P >= 896 (16 complex values in registers per thread and pass)
 template <int P> struct FftCfg {
-    static constexpr int Q = (P >= 896) ? 64 : 32;      // threads per sequence
+    // threads per sequence: one radix-32 butterfly per thread at 1024 = 32 x 32, else P/16 above 896
+    static constexpr int Q = (P >= 896 && P != 1024) ? 64 : 32;
     static constexpr int T = TILE_W * Q;                // threads per CTA, row passes
     static constexpr int MINB = (P <= 1024) ? BH_ROWS_MINB : 1;
-    static constexpr int SKR = 4;                       // row layout: pad after every 16 elements
+    static constexpr int SKR = ilog2_c(Plan<P>::r[0]) > 4 ? ilog2_c(Plan<P>::r[0]) : 4;   // row layout: pad after
+                                                        // every max(16, R0) elements
     static constexpr int SKC = ilog2_c(Plan<P>::r[0]);  // column layout: pad after every R0 elements
     static constexpr int SEQ = SeqLen<P, SKR>::value;   // row layout: stride between sequences
     static constexpr size_t smem_row = size_t(SEQ) * TILE_W * sizeof(float2);

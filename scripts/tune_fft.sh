@@ -1,7 +1,7 @@
 #!/bin/bash
 # build variants locally (nvcc), run them on the GPU: bash scripts/tune_fft.sh build | run
 set -u
-VARIANTS="2,4,8,1 2,3,8,1 4,2,8,1 4,3,8,1 2,6,8,1 2,4,4,2 2,4,4,1 1,8,8,1"
+VARIANTS="2,4,8,1 2,2,8,1 4,2,8,1 4,1,8,1 1,4,8,1 2,3,8,1 2,4,4,2 2,4,4,1 2,4,16,1"
 if [ "$1" = build ]; then
   mkdir -p build
   for v in $VARIANTS; do IFS=, read rw rm cw cm <<< "$v"
