@@ -163,8 +163,30 @@ template <bool INV> BH_HD void dft32(float2* v) {
     for (int k = 0; k < 32; ++k) v[k] = t[k];
 }
 
+template <bool INV> BH_HD void dft28(float2* v) {
+    // R1 = 4 (a), R2 = 7 (b): r = a*7 + b ; X[c + 4 d]
+    const float cs[19] = {1.00000000000000000000f, 0.97492791218182361934f, 0.90096886790241914600f, 0.78183148246802980363f, 0.62348980185873359439f, 0.43388373911755817591f, 0.22252093395631444839f, 0.00000000000000006123f, -0.22252093395631433737f, -0.43388373911755806489f, -0.62348980185873348336f, -0.78183148246802947057f, -0.90096886790241903498f, -0.97492791218182373036f, -1.00000000000000000000f, -0.97492791218182373036f, -0.90096886790241914600f, -0.78183148246802958159f, -0.62348980185873370541f};
+    const float sn[19] = {0.00000000000000000000f, 0.22252093395631439288f, 0.43388373911755812040f, 0.62348980185873348336f, 0.78183148246802980363f, 0.90096886790241914600f, 0.97492791218182361934f, 1.00000000000000000000f, 0.97492791218182361934f, 0.90096886790241914600f, 0.78183148246802991466f, 0.62348980185873392745f, 0.43388373911755823142f, 0.22252093395631408757f, 0.00000000000000012246f, -0.22252093395631383776f, -0.43388373911755800938f, -0.62348980185873381643f, -0.78183148246802969261f};
+#pragma unroll
+    for (int b = 0; b < 7; ++b) dft4<INV>(v[b], v[7 + b], v[14 + b], v[21 + b]);
+#pragma unroll
+    for (int c = 1; c < 4; ++c)
+#pragma unroll
+        for (int b = 1; b < 7; ++b) v[c * 7 + b] = cmulw<INV>(v[c * 7 + b], cs[c * b], -sn[c * b]);   // W28^(c b)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dft7<INV>(v + 7 * c);     // v[c*7 + d] = X[c + 4 d]
+    float2 t[28];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int d = 0; d < 7; ++d) t[c + 4 * d] = v[c * 7 + d];
+#pragma unroll
+    for (int k = 0; k < 28; ++k) v[k] = t[k];
+}
+
 template <int R, bool INV> BH_HD void dft(float2* v) {
     if (R == 32) dft32<INV>(v);
+    else if (R == 28) dft28<INV>(v);
     else if (R == 2) dft2<INV>(v[0], v[1]);
     else if (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
     else if (R == 8) dft8<INV>(v);
@@ -197,7 +219,7 @@ template <> struct Plan<64>   { static constexpr int n = 2; static constexpr int
 template <> struct Plan<128>  { static constexpr int n = 2; static constexpr int r[3] = {16, 8, 1}; };
 template <> struct Plan<256>  { static constexpr int n = 2; static constexpr int r[3] = {16, 16, 1}; };
 template <> struct Plan<512>  { static constexpr int n = 3; static constexpr int r[3] = {8, 8, 8}; };
-template <> struct Plan<896>  { static constexpr int n = 3; static constexpr int r[3] = {16, 8, 7}; };
+template <> struct Plan<896>  { static constexpr int n = 2; static constexpr int r[3] = {32, 28, 1}; };   // two passes
 template <> struct Plan<1024> { static constexpr int n = 2; static constexpr int r[3] = {32, 32, 1}; };   // two passes
 template <> struct Plan<1792> { static constexpr int n = 3; static constexpr int r[3] = {16, 16, 7}; };
 template <> struct Plan<2048> { static constexpr int n = 3; static constexpr int r[3] = {16, 16, 8}; };

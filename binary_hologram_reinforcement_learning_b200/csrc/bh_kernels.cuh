@@ -59,8 +59,9 @@ constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
 
 // threads: P/16 per sequence at P >= 896 (16 complex values in registers per thread and pass)
 template <int P> struct FftCfg {
-    // threads per sequence: one radix-32 butterfly per thread at 1024 = 32 x 32, else P/16 above 896
-    static constexpr int Q = (P >= 896 && P != 1024) ? 64 : 32;
+    // threads per sequence: one radix-32 butterfly per thread for the two-pass plans (896 = 32 x 28,
+    // 1024 = 32 x 32), P/32 = 64 for the three-pass plans above them
+    static constexpr int Q = (P > 1024) ? 64 : 32;
     static constexpr int T = TILE_W * Q;                // threads per CTA, row passes
     static constexpr int MINB = (P <= 1024) ? BH_ROWS_MINB : 1;
     static constexpr int SKR = ilog2_c(Plan<P>::r[0]) > 4 ? ilog2_c(Plan<P>::r[0]) : 4;   // row layout: pad after

@@ -179,7 +179,7 @@ inline std::vector<int> plan_radices(int P) {
         case 128: return {16, 8};
         case 256: return {16, 16};
         case 512: return {8, 8, 8};
-        case 896: return {16, 8, 7};
+        case 896: return {32, 28};
         case 1024: return {32, 32};
         case 1792: return {16, 16, 7};
         case 2048: return {16, 16, 8};

@@ -128,7 +128,7 @@ int main() {
     worst = std::max(worst, check_size<128, 32>());
     worst = std::max(worst, check_size<256, 32>());
     worst = std::max(worst, check_size<512, 32>());
-    worst = std::max(worst, check_size<896, 64>());
+    worst = std::max(worst, check_size<896, 32>());
     worst = std::max(worst, check_size<1024, 32>());
     worst = std::max(worst, check_size<1792, 64>());
     worst = std::max(worst, check_size<2048, 64>());
