@@ -64,8 +64,18 @@ if os.path.exists(lp):
     print("wrote launches summary:", len(order), "launches")
 
 # ---- full capture ------------------------------------------------------------
-rp = os.path.join(ROOT, "gpurun_out", "prof_hotpath.ncu-rep")
-EXTRA = [("prof_prop.ncu-rep", "propagation"), ("prof_eval_warm.ncu-rep", "eval_warm_cache")]
+def raw_page(stem):
+    """Raw metric page of a capture: the CSV written on the GPU box, else the .ncu-rep itself."""
+    csv_path = os.path.join(ROOT, "gpurun_out", stem + "_raw.csv")
+    rep_path = os.path.join(ROOT, "gpurun_out", stem + ".ncu-rep")
+    if os.path.exists(csv_path):
+        return open(csv_path).read()
+    if os.path.exists(rep_path):
+        return subprocess.run(["ncu", "-i", rep_path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    return None
+
+
+EXTRA = [("prof_prop", "propagation"), ("prof_eval_warm", "eval_warm_cache")]
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -74,8 +84,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum"]
-if os.path.exists(rp):
-    raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = raw_page("prof_hotpath")
+if raw:
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {k: hdr.index(k) for k in KEYS if k in hdr}
@@ -101,11 +111,10 @@ if os.path.exists(rp):
                   open(os.path.join(out_dir, "roofline_traffic.json"), "w"), indent=1)
     print("wrote hotpath metrics:", len(data), "launches")
 
-for fname, label in EXTRA:
-    path = os.path.join(ROOT, "gpurun_out", fname)
-    if not os.path.exists(path):
+for stem, label in EXTRA:
+    raw = raw_page(stem)
+    if not raw:
         continue
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     if len(rows) < 3:
         continue
