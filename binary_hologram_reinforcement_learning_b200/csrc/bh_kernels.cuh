@@ -529,6 +529,10 @@ k_loss_final(const double* __restrict__ partial, int n_partial, double n_elems,
 // associative, so sum(dI*(2I+dI)) and sum(dI*T) are bit-identical for every
 // grid size, batch composition, speculation depth and GPU count.
 constexpr int UNIT_PX = 1024;
+// Rows of the impulse-response table carry H_PAD wrapped columns (h[y][P + j] = h[y][j]), so the
+// four taps of a pixel quad are always contiguous: one address, no per-tap wrap.
+constexpr int H_PAD = 4;
+__host__ __device__ constexpr int h_stride(int P) { return P + H_PAD; }
 constexpr float FIX_SCALE = 1099511627776.0f;          // 2^40
 constexpr double FIX_INV = 1.0 / 1099511627776.0;
 
@@ -541,6 +545,7 @@ struct DeltaArgs {
     long long n_total;             // valid entries of actions
     int env_fixed;
     int n_tasks, N, P, F, G, Fg, relative, rule;
+    int HP;                        // row stride of h: P + H_PAD (h_stride)
     int units_per_task;            // N*N / UNIT_PX
     int unit_dy, unit_dx;          // UNIT_PX / N, UNIT_PX % N
     unsigned long long* acc;       // [n_tasks][2] fixed-point accumulators (zero between launches)
@@ -554,6 +559,8 @@ struct DeltaArgs {
     int n_inline;
     long long inl_actions[32];
     int inl_envs[32];
+    // bundled evaluation (k_eval_bundle_t): order a speculation window by frame inside the CTA
+    int sort_window;
 };
 constexpr int INLINE_MAX = 32;
 
@@ -647,12 +654,9 @@ __device__ __forceinline__ void load_quad(Quad& q, const float2* U, const float*
     if (WITH_T) q.tv = ld_stream4(reinterpret_cast<const float4*>(T + p), pf);
     int hy = cu.y - r; if (hy < 0) hy += P;
     int hx = cu.x - c; if (hx < 0) hx += P;
-    const float2* hrow = h + size_t(hy) * P;
-    int hx1 = hx + 1; if (hx1 >= P) hx1 -= P;
-    int hx2 = hx1 + 1; if (hx2 >= P) hx2 -= P;
-    int hx3 = hx2 + 1; if (hx3 >= P) hx3 -= P;
-    q.h0 = ld_keep2(hrow + hx, pl); q.h1 = ld_keep2(hrow + hx1, pl);
-    q.h2 = ld_keep2(hrow + hx2, pl); q.h3 = ld_keep2(hrow + hx3, pl);
+    const float2* hq = h + size_t(hy) * h_stride(P) + hx;
+    q.h0 = ld_keep2(hq, pl); q.h1 = ld_keep2(hq + 1, pl);
+    q.h2 = ld_keep2(hq + 2, pl); q.h3 = ld_keep2(hq + 3, pl);
 }
 
 __device__ __forceinline__ void eval_quad(const Quad& q, float s2, float invFg, long long& aII,
@@ -684,6 +688,148 @@ __device__ __forceinline__ int cta_of_unit(long long u, long long total, int gri
     return int(((u + 1) * grid - 1) / total);
 }
 
+// One CTA's exact partial sums of task k go to the task's accumulators; the last of the n_ctas
+// contributors turns the totals into the PSNR and the accept decision and re-arms the slot.
+__device__ __forceinline__ void contribute_and_finalise(const DeltaArgs& a, int k, const Decoded& d,
+                                                        long long act, long long x, long long y,
+                                                        unsigned n_ctas, size_t n2) {
+    atomicAdd(a.acc + 2 * k, (unsigned long long)x);
+    atomicAdd(a.acc + 2 * k + 1, (unsigned long long)y);
+    __threadfence();
+    const unsigned ticket = atomicAdd(a.tickets + k, 1u);
+    if (ticket != n_ctas - 1u) return;
+    __threadfence();                                         // every contribution has landed
+    const long long sII = (long long)__ldcg(a.acc + 2 * k);
+    const long long sIT = (long long)__ldcg(a.acc + 2 * k + 1);
+    const double dII = double(sII) * FIX_INV, dIT = double(sIT) * FIX_INV;
+    const double* S = a.sums + size_t(d.env) * 4;
+    const double sii = S[0] + dII, sit = S[1] + dIT, stt = S[2];
+    const double n = double(a.G) * double(n2);
+    const double mse = a.relative ? (stt - sit * sit / sii) / n
+                                  : (sii - 2.0 * sit + stt) / n;
+    const double psnr = -10.0 * log10(mse);
+    const double prev = S[3];
+    int acc = 0;
+    if (a.rule == RULE_ENV) acc = !(psnr - prev < 0.0);     // env.py:191
+    else if (a.rule == RULE_DBS) acc = (psnr > prev);       // DBS.py:273
+    Result r; r.psnr_after = psnr; r.d_sii = dII; r.d_sit = dIT;
+    r.action = act; r.accept = acc; r.sgn = int(d.sgn);
+    a.results[k] = r;
+    if (a.results_host) a.results_host[k] = r;
+    a.acc[2 * k] = 0ull; a.acc[2 * k + 1] = 0ull;
+    a.tickets[k] = 0;
+}
+
+__device__ __forceinline__ void write_idle_result(const DeltaArgs& a, int k) {
+    Result r; r.psnr_after = 0.0; r.d_sii = 0.0; r.d_sit = 0.0;
+    r.action = -1; r.accept = 0; r.sgn = 0;
+    a.results[k] = r;
+}
+
+// the action of task k: kernel parameters, or the (cursor-relative) device list; -1 = idle slot
+__device__ __forceinline__ long long task_action(const DeltaArgs& a, int k) {
+    if (a.n_inline) return a.inl_actions[k];
+    long long idx = k;
+    if (a.offset_ptr) idx += *a.offset_ptr;
+    return (idx < a.n_total) ? a.actions[idx] : -1;
+}
+
+// Row-regular images (N divides UNIT_PX, so a unit is UNIT_PX / N whole rows): a thread keeps its
+// column for the whole pass, the pixel offset advances by UNIT_PX per unit, and the impulse
+// response of a candidate is ONE table offset that advances by unit_dy rows (modulo P).  That
+// removes the per-quad decode of (y, x) and the tap addressing of the generic path -- about half
+// of its instructions.  Scores L candidates of one frame per pass over units [w0, w1) of the task,
+// UF units in flight; pixels, per-quad arithmetic and fixed-point sums are those of the generic
+// path, so the results are bit-identical.
+template <int L, int UF>
+__device__ __forceinline__ void eval_run_rows(const DeltaArgs& a, const float2* U, const float* I,
+                                              const float* T, const float2* h, const int* rr,
+                                              const int* cc, const float* s2, long long* aII,
+                                              long long* aIT, int w0, int w1, int tid, float invFg,
+                                              uint64_t pf, uint64_t pl) {
+    const int N = a.N, P = a.P, HP = a.HP, dy = a.unit_dy;
+    const int y0 = (tid * 4) / N, x = tid * 4 - y0 * N;
+    const int y = w0 * dy + y0;
+    size_t p = size_t(y) * N + x;
+    const int hstep = dy * HP, hwrap = P * HP;
+    int ho[L];                                     // offset of the quad's first tap in the table
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        int hx = x - cc[i]; if (hx < 0) hx += P;
+        int hy = y - rr[i]; if (hy < 0) hy += P;
+        ho[i] = hy * HP + hx;
+    }
+    int w = w0;
+#pragma unroll 1
+    for (; w + UF <= w1; w += UF) {
+        float4 ua[UF], ub[UF], iv[UF], tv[UF];
+        float2 hq[UF][L][4];
+#pragma unroll
+        for (int k = 0; k < UF; ++k) {
+            const float4* Up = reinterpret_cast<const float4*>(U + p);
+            ua[k] = ld_stream4(Up, pf);
+            ub[k] = ld_stream4(Up + 1, pf);
+            iv[k] = ld_stream4(reinterpret_cast<const float4*>(I + p), pf);
+            tv[k] = ld_stream4(reinterpret_cast<const float4*>(T + p), pf);
+            p += UNIT_PX;
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+                const float2* hp = h + ho[i];
+                hq[k][i][0] = ld_keep2(hp, pl); hq[k][i][1] = ld_keep2(hp + 1, pl);
+                hq[k][i][2] = ld_keep2(hp + 2, pl); hq[k][i][3] = ld_keep2(hp + 3, pl);
+                ho[i] += hstep; if (ho[i] >= hwrap) ho[i] -= hwrap;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UF; ++k) {
+            Quad q; q.ua = ua[k]; q.ub = ub[k]; q.iv = iv[k]; q.tv = tv[k];
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+                q.h0 = hq[k][i][0]; q.h1 = hq[k][i][1]; q.h2 = hq[k][i][2]; q.h3 = hq[k][i][3];
+                eval_quad(q, s2[i], invFg, aII[i], aIT[i]);
+            }
+        }
+    }
+#pragma unroll 1
+    for (; w < w1; ++w) {
+        Quad q;
+        const float4* Up = reinterpret_cast<const float4*>(U + p);
+        q.ua = ld_stream4(Up, pf);
+        q.ub = ld_stream4(Up + 1, pf);
+        q.iv = ld_stream4(reinterpret_cast<const float4*>(I + p), pf);
+        q.tv = ld_stream4(reinterpret_cast<const float4*>(T + p), pf);
+        p += UNIT_PX;
+        float2 hq[L][4];
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            const float2* hp = h + ho[i];
+            hq[i][0] = ld_keep2(hp, pl); hq[i][1] = ld_keep2(hp + 1, pl);
+            hq[i][2] = ld_keep2(hp + 2, pl); hq[i][3] = ld_keep2(hp + 3, pl);
+            ho[i] += hstep; if (ho[i] >= hwrap) ho[i] -= hwrap;
+        }
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            q.h0 = hq[i][0]; q.h1 = hq[i][1]; q.h2 = hq[i][2]; q.h3 = hq[i][3];
+            eval_quad(q, s2[i], invFg, aII[i], aIT[i]);
+        }
+    }
+}
+
+// units in flight for a run of L candidates: about four quads of taps per thread
+__host__ __device__ constexpr int run_uf(int L) { return L == 1 ? 3 : (L == 2 ? 2 : 1); }
+
+template <int L, int B>
+__device__ __forceinline__ void eval_run_dispatch(int len, const DeltaArgs& a, const float2* U,
+                                                  const float* I, const float* T, const float2* h,
+                                                  const int* rr, const int* cc, const float* s2,
+                                                  long long* aII, long long* aIT, int w0, int w1,
+                                                  int tid, float invFg, uint64_t pf, uint64_t pl) {
+    if (len == L || L == B)
+        eval_run_rows<L, run_uf(L)>(a, U, I, T, h, rr, cc, s2, aII, aIT, w0, w1, tid, invFg, pf, pl);
+    else if constexpr (L < B)
+        eval_run_dispatch<L + 1, B>(len, a, U, I, T, h, rr, cc, s2, aII, aIT, w0, w1, tid, invFg, pf, pl);
+}
+
 // k_eval: streams U (8 B/px), I and T (4 B/px each) once per candidate and the
 // shifted impulse response from L2: 16 N^2 algorithmic HBM bytes per candidate.
 // The last CTA to contribute to a task turns the exact sums into the PSNR and
@@ -692,7 +838,6 @@ template <int UF, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_eval_t(const DeltaArgs a) {
     __shared__ long long sh[2][8];
-    __shared__ unsigned s_ticket;
     pdl_wait_then_release();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = a.N, P = a.P, upt = a.units_per_task;
@@ -707,41 +852,39 @@ k_eval_t(const DeltaArgs a) {
         const int k = int(u / upt);
         const long long t_beg = (long long)k * upt;
         const long long seg_end = (t_beg + upt < end) ? t_beg + upt : end;
-        long long idx = k;
-        if (a.offset_ptr) idx += *a.offset_ptr;
-        const long long act = a.n_inline ? a.inl_actions[k]
-                                         : ((idx < a.n_total) ? a.actions[idx] : -1);
+        const long long act = task_action(a, k);
         const Decoded d = decode_action(a, k, act);
         if (!d.active) {
-            if (u == t_beg && tid == 0) {
-                Result r; r.psnr_after = 0.0; r.d_sii = 0.0; r.d_sit = 0.0;
-                r.action = -1; r.accept = 0; r.sgn = 0;
-                a.results[k] = r;
-            }
+            if (u == t_beg && tid == 0) write_idle_result(a, k);
             u = seg_end;
             continue;
         }
         const float2* U = a.U + (size_t(d.env) * a.F + d.f) * n2;
         const float* I = a.I + (size_t(d.env) * a.G + d.g) * n2;
         const float* T = a.T + (size_t(d.env) * a.G + d.g) * n2;
-        const float2* h = a.h + size_t(d.g) * P * P;
+        const float2* h = a.h + size_t(d.g) * P * a.HP;
         const float s2 = 2.f * d.sgn * invFg;
         long long aII = 0, aIT = 0;
-        Cursor cu; cu.init(int(u - t_beg), tid, N);
-        long long v = u;
-        for (; v + UF <= seg_end; v += UF) {         // UF units in flight per thread
-            Quad q[UF];
+        if (a.unit_dx == 0) {
+            eval_run_rows<1, UF>(a, U, I, T, h, &d.r, &d.c, &s2, &aII, &aIT, int(u - t_beg),
+                                 int(seg_end - t_beg), tid, invFg, pf, pl);
+        } else {
+            Cursor cu; cu.init(int(u - t_beg), tid, N);
+            long long v = u;
+            for (; v + UF <= seg_end; v += UF) {         // UF units in flight per thread
+                Quad q[UF];
 #pragma unroll
-            for (int i = 0; i < UF; ++i) {
-                load_quad<true>(q[i], U, I, T, h, cu, N, P, d.r, d.c, pf, pl); cu.next(a);
+                for (int i = 0; i < UF; ++i) {
+                    load_quad<true>(q[i], U, I, T, h, cu, N, P, d.r, d.c, pf, pl); cu.next(a);
+                }
+#pragma unroll
+                for (int i = 0; i < UF; ++i) eval_quad(q[i], s2, invFg, aII, aIT);
             }
-#pragma unroll
-            for (int i = 0; i < UF; ++i) eval_quad(q[i], s2, invFg, aII, aIT);
-        }
-        for (; v < seg_end; ++v) {
-            Quad q0;
-            load_quad<true>(q0, U, I, T, h, cu, N, P, d.r, d.c, pf, pl); cu.next(a);
-            eval_quad(q0, s2, invFg, aII, aIT);
+            for (; v < seg_end; ++v) {
+                Quad q0;
+                load_quad<true>(q0, U, I, T, h, cu, N, P, d.r, d.c, pf, pl); cu.next(a);
+                eval_quad(q0, s2, invFg, aII, aIT);
+            }
         }
         aII = warp_sum_ll(aII); aIT = warp_sum_ll(aIT);
         if (lane == 0) { sh[0][warp] = aII; sh[1][warp] = aIT; }
@@ -750,36 +893,160 @@ k_eval_t(const DeltaArgs a) {
             long long x = 0, y = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) { x += sh[0][i]; y += sh[1][i]; }
-            atomicAdd(a.acc + 2 * k, (unsigned long long)x);
-            atomicAdd(a.acc + 2 * k + 1, (unsigned long long)y);
-            __threadfence();
             const int first = cta_of_unit(t_beg, total, gridDim.x);
             const int last = cta_of_unit(t_beg + upt - 1, total, gridDim.x);
-            s_ticket = atomicAdd(a.tickets + k, 1u);
-            if (s_ticket == unsigned(last - first)) {        // every contribution has landed
-                __threadfence();
-                const long long sII = (long long)__ldcg(a.acc + 2 * k);
-                const long long sIT = (long long)__ldcg(a.acc + 2 * k + 1);
-                const double dII = double(sII) * FIX_INV, dIT = double(sIT) * FIX_INV;
-                const double* S = a.sums + size_t(d.env) * 4;
-                const double sii = S[0] + dII, sit = S[1] + dIT, stt = S[2];
-                const double n = double(a.G) * double(n2);
-                const double mse = a.relative ? (stt - sit * sit / sii) / n
-                                              : (sii - 2.0 * sit + stt) / n;
-                const double psnr = -10.0 * log10(mse);
-                const double prev = S[3];
-                int acc = 0;
-                if (a.rule == RULE_ENV) acc = !(psnr - prev < 0.0);     // env.py:191
-                else if (a.rule == RULE_DBS) acc = (psnr > prev);       // DBS.py:273
-                Result r; r.psnr_after = psnr; r.d_sii = dII; r.d_sit = dIT;
-                r.action = act; r.accept = acc; r.sgn = int(d.sgn);
-                a.results[k] = r;
-                if (a.results_host) a.results_host[k] = r;
-                a.acc[2 * k] = 0ull; a.acc[2 * k + 1] = 0ull;
-                a.tickets[k] = 0;
-            }
+            contribute_and_finalise(a, k, d, act, x, y, unsigned(last - first) + 1u, n2);
         }
         __syncthreads();
+        u = seg_end;
+    }
+}
+
+// k_eval_bundle: candidate lists that revisit an environment (speculation windows of the greedy
+// DBS, DBS.py:247-294; the candidate tables of env_group.py:96-119 and the sweeps) are scored B
+// slots at a time.  Inside a bundle every run of candidates of one frame is ONE pass over the
+// image: the thread that owns a quad loads U, I and T once per run and, per candidate, only the
+// shifted impulse response (L2 resident).  HBM traffic per candidate falls from 16 N^2 B towards
+// 16 N^2 / B; the per-quad arithmetic and the 2^-40 fixed-point sums are those of k_eval_t, so
+// both kernels return bit-identical results.  A speculation window (n_tasks <= SORT_WINDOW_MAX,
+// sort_window set) is ordered by frame inside every CTA first; results stay indexed by the
+// caller's task number.
+constexpr int SORT_WINDOW_MAX = 128;
+
+struct BundleTask { int task; long long act; Decoded d; };
+
+__device__ __forceinline__ BundleTask bundle_task(const DeltaArgs& a, int slot, bool sorted,
+                                                  const int* s_order) {
+    BundleTask t;
+    t.task = sorted ? s_order[slot] : slot;
+    t.act = task_action(a, t.task);
+    t.d = decode_action(a, t.task, t.act);
+    return t;
+}
+
+template <int B, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_eval_bundle_t(const DeltaArgs a) {
+    __shared__ long long sh[2 * B][8];
+    __shared__ int s_key[SORT_WINDOW_MAX];
+    __shared__ int s_order[SORT_WINDOW_MAX];
+    pdl_wait_then_release();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = a.N, P = a.P, upt = a.units_per_task, n = a.n_tasks;
+    const size_t n2 = size_t(N) * N;
+    const bool sorted = a.sort_window && n <= SORT_WINDOW_MAX;
+    if (sorted) {
+        if (tid < n) {
+            const long long act = task_action(a, tid);
+            s_key[tid] = act < 0 ? 0x7fffffff : int(act / (long long)n2);     // idle slots last
+        }
+        __syncthreads();
+        if (tid < n) {
+            const int key = s_key[tid];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) {
+                const int kj = s_key[j];
+                rank += (kj < key || (kj == key && j < tid)) ? 1 : 0;
+            }
+            s_order[rank] = tid;
+        }
+        __syncthreads();
+    }
+    const int n_bundles = (n + B - 1) / B;
+    const long long total = (long long)n_bundles * upt;
+    const long long beg = (long long)blockIdx.x * total / gridDim.x;
+    const long long end = (long long)(blockIdx.x + 1) * total / gridDim.x;
+    const float invFg = 1.f / float(a.Fg);
+    const uint64_t pf = policy_evict_first(), pl = policy_evict_last();
+    long long u = beg;
+    while (u < end) {
+        const int j = int(u / upt);
+        const long long t_beg = (long long)j * upt;
+        const long long seg_end = (t_beg + upt < end) ? t_beg + upt : end;
+        const unsigned n_ctas = unsigned(cta_of_unit(t_beg + upt - 1, total, gridDim.x) -
+                                         cta_of_unit(t_beg, total, gridDim.x)) + 1u;
+        const int slots = (n - j * B < B) ? n - j * B : B;
+        int rb = 0;
+        while (rb < slots) {
+            // the run: slots rb .. rb+len-1 of the bundle, all of one environment and frame
+            const BundleTask head = bundle_task(a, j * B + rb, sorted, s_order);
+            if (!head.d.active) {                           // idle slot
+                if (u == t_beg && tid == 0) write_idle_result(a, head.task);
+                rb += 1;
+                continue;
+            }
+            int rr[B], cc[B]; float s2[B]; long long aII[B], aIT[B];
+            int len = 1;
+            rr[0] = head.d.r; cc[0] = head.d.c; s2[0] = 2.f * head.d.sgn * invFg;
+            aII[0] = 0; aIT[0] = 0;
+#pragma unroll
+            for (int i = 1; i < B; ++i) {
+                rr[i] = 0; cc[i] = 0; s2[i] = 0.f; aII[i] = 0; aIT[i] = 0;
+                if (rb + i < slots && len == i) {
+                    const BundleTask t = bundle_task(a, j * B + rb + i, sorted, s_order);
+                    if (t.d.active && t.d.env == head.d.env && t.d.f == head.d.f) {
+                        rr[i] = t.d.r; cc[i] = t.d.c; s2[i] = 2.f * t.d.sgn * invFg;
+                        len = i + 1;
+                    }
+                }
+            }
+            const float2* U = a.U + (size_t(head.d.env) * a.F + head.d.f) * n2;
+            const float* I = a.I + (size_t(head.d.env) * a.G + head.d.g) * n2;
+            const float* T = a.T + (size_t(head.d.env) * a.G + head.d.g) * n2;
+            const float2* h = a.h + size_t(head.d.g) * P * a.HP;
+            if (a.unit_dx == 0) {
+                eval_run_dispatch<1, B>(len, a, U, I, T, h, rr, cc, s2, aII, aIT, int(u - t_beg),
+                                        int(seg_end - t_beg), tid, invFg, pf, pl);
+            } else {
+                Cursor cu; cu.init(int(u - t_beg), tid, N);
+#pragma unroll 1
+                for (long long v = u; v < seg_end; ++v) {
+                    const size_t p = size_t(cu.y) * N + cu.x;
+                    Quad q;
+                    const float4* Up = reinterpret_cast<const float4*>(U + p);
+                    q.ua = ld_stream4(Up, pf);
+                    q.ub = ld_stream4(Up + 1, pf);
+                    q.iv = ld_stream4(reinterpret_cast<const float4*>(I + p), pf);
+                    q.tv = ld_stream4(reinterpret_cast<const float4*>(T + p), pf);
+                    float2 hq[B][4];
+#pragma unroll
+                    for (int i = 0; i < B; ++i) {
+                        if (i < len) {
+                            int hy = cu.y - rr[i]; if (hy < 0) hy += P;
+                            int hx = cu.x - cc[i]; if (hx < 0) hx += P;
+                            const float2* hp = h + size_t(hy) * a.HP + hx;
+                            hq[i][0] = ld_keep2(hp, pl); hq[i][1] = ld_keep2(hp + 1, pl);
+                            hq[i][2] = ld_keep2(hp + 2, pl); hq[i][3] = ld_keep2(hp + 3, pl);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < B; ++i) {
+                        if (i < len) {
+                            q.h0 = hq[i][0]; q.h1 = hq[i][1]; q.h2 = hq[i][2]; q.h3 = hq[i][3];
+                            eval_quad(q, s2[i], invFg, aII[i], aIT[i]);
+                        }
+                    }
+                    cu.next(a);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                if (i < len) {
+                    const long long x = warp_sum_ll(aII[i]), y = warp_sum_ll(aIT[i]);
+                    if (lane == 0) { sh[2 * i][warp] = x; sh[2 * i + 1][warp] = y; }
+                }
+            }
+            __syncthreads();
+            if (tid < len) {                                // one thread per candidate of the run
+                const BundleTask t = bundle_task(a, j * B + rb + tid, sorted, s_order);
+                long long x = 0, y = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { x += sh[2 * tid][w]; y += sh[2 * tid + 1][w]; }
+                contribute_and_finalise(a, t.task, t.d, t.act, x, y, n_ctas, n2);
+            }
+            __syncthreads();
+            rb += len;
+        }
         u = seg_end;
     }
 }
@@ -867,7 +1134,7 @@ k_commit_t(const DeltaArgs a) {
         d.sgn = float(res.sgn);            // the state byte may already be flipped
         float2* U = a.U + (size_t(d.env) * a.F + d.f) * n2;
         float* I = a.I + (size_t(d.env) * a.G + d.g) * n2;
-        const float2* h = a.h + size_t(d.g) * P * P;
+        const float2* h = a.h + size_t(d.g) * P * a.HP;
         const float s2 = 2.f * d.sgn * invFg, sg = d.sgn;
         Cursor cu; cu.init(int(u - t_beg), tid, N);
         long long v = u;
@@ -913,7 +1180,7 @@ k_recon_candidate(const float2* __restrict__ U, const float2* __restrict__ h,
         const int y = int(p / N), x = int(p - size_t(y) * N);
         int hy = y - r; if (hy < 0) hy += P;
         int hx = x - c; if (hx < 0) hx += P;
-        const float2 u = U[p], hv = __ldg(h + size_t(hy) * P + hx);
+        const float2 u = U[p], hv = __ldg(h + size_t(hy) * h_stride(P) + hx);
         out_g[p] += delta_px(u.x, u.y, hv.x, hv.y, s2, invFg);
     }
 }

@@ -36,6 +36,7 @@ struct bh_ctx {
     double* dsums = nullptr;
     double* dloss_partial = nullptr;
     int max_tasks = 0, units_per_task = 0, grid_cap = 0, grid_cap_commit = 0;
+    int grid_cap_bundle = 0, bundle = 0;     // bundle = slots per bundle of k_eval_bundle_t, 0 = off
     int32_t* d_envs = nullptr;
     long long* d_actions = nullptr;
     Result* d_results = nullptr;
@@ -57,6 +58,7 @@ struct bh_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_eval = nullptr;
     cudaStream_t own_stream = nullptr;   // capture needs a real stream when the caller gave none
     void (*k_eval)(const DeltaArgs) = nullptr;
+    void (*k_eval_bundle)(const DeltaArgs) = nullptr;
     void (*k_commit)(const DeltaArgs) = nullptr;
     bool use_pdl = true;
     int64_t launches = 0;
@@ -221,11 +223,26 @@ static eval_fn commit_variant(int v) {
         default: return k_commit_t<3, 2>;
     }
 }
+// k_eval_bundle variants: slots per bundle x CTAs per SM; BHOLO_BUNDLE_VARIANT=9 disables bundling
+// (candidate lists then go through k_eval_t)
+static eval_fn bundle_variant(int v, int* slots) {
+    switch (v) {
+        case 1: *slots = 8; return k_eval_bundle_t<8, 1>;
+        case 2: *slots = 6; return k_eval_bundle_t<6, 1>;
+        case 3: *slots = 3; return k_eval_bundle_t<3, 2>;
+        case 4: *slots = 2; return k_eval_bundle_t<2, 3>;
+        case 9: *slots = 0; return nullptr;
+        default: *slots = 4; return k_eval_bundle_t<4, 2>;
+    }
+}
 static eval_fn eval_variant(int v) {
     switch (v) {
         case 1: return k_eval_t<2, 4>;
         case 2: return k_eval_t<4, 2>;
         case 3: return k_eval_t<2, 3>;
+        case 4: return k_eval_t<3, 3>;
+        case 5: return k_eval_t<6, 1>;
+        case 6: return k_eval_t<5, 2>;
         default: return k_eval_t<3, 2>;
     }
 }
@@ -292,7 +309,7 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
         }                                                                              \
     } while (0)
     BH_TRY(cudaMalloc(&c->dH, size_t(G) * p2 * sizeof(float2)));
-    BH_TRY(cudaMalloc(&c->dh, size_t(G) * p2 * sizeof(float2)));
+    BH_TRY(cudaMalloc(&c->dh, size_t(G) * c->P * h_stride(c->P) * sizeof(float2)));
     BH_TRY(cudaMalloc(&c->dtw, (build_twiddles(c->P).size() / 2 + 1) * sizeof(float2)));
     BH_TRY(cudaMalloc(&c->dU, size_t(n_env) * F * n2 * sizeof(float2)));
     if (pad == 2) BH_TRY(cudaMalloc(&c->dscratch, size_t(c->Fg) * p2 * sizeof(float2)));
@@ -327,10 +344,15 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
         BH_TRY(cudaMemset(c->dstate, 0, size_t(n_env) * F * n2));
         BH_TRY(cudaMemset(c->dU, 0, size_t(n_env) * F * n2 * sizeof(float2)));
         BH_TRY(cudaMemset(c->dI, 0, size_t(n_env) * G * n2 * sizeof(float)));
+        const size_t HP = size_t(h_stride(c->P));
         for (int g = 0; g < G && rc == 0; ++g) {
             auto t = get_tables(c->P, wl[g], dx, z, method);
             BH_TRY(cudaMemcpy(c->dH + size_t(g) * p2, t->H.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
-            BH_TRY(cudaMemcpy(c->dh + size_t(g) * p2, t->h.data(), p2 * sizeof(float2), cudaMemcpyHostToDevice));
+            // rows of h carry H_PAD wrapped columns (bh_kernels.cuh: h_stride)
+            BH_TRY(cudaMemcpy2D(c->dh + size_t(g) * c->P * HP, HP * sizeof(float2), t->h.data(), c->P * sizeof(float2),
+                                c->P * sizeof(float2), c->P, cudaMemcpyHostToDevice));
+            BH_TRY(cudaMemcpy2D(c->dh + size_t(g) * c->P * HP + c->P, HP * sizeof(float2), t->h.data(), c->P * sizeof(float2),
+                                H_PAD * sizeof(float2), c->P, cudaMemcpyHostToDevice));
         }
         auto tw = build_twiddles(c->P);
         BH_TRY(cudaMemcpy(c->dtw, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -344,6 +366,12 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
         c->k_commit = commit_variant(cv ? std::atoi(cv) : 0);
         BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, c->k_commit, 256, 0));
         c->grid_cap_commit = std::max(1, nb) * prop.multiProcessorCount;
+        const char* bv = std::getenv("BHOLO_BUNDLE_VARIANT");
+        c->k_eval_bundle = bundle_variant(bv ? std::atoi(bv) : 0, &c->bundle);
+        if (c->k_eval_bundle) {
+            BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, c->k_eval_bundle, 256, 0));
+            c->grid_cap_bundle = std::max(1, nb) * prop.multiProcessorCount;
+        }
     }
 #undef BH_TRY
     if (rc) { std::string keep = g_err; bh_destroy(c); g_err = keep; return rc; }
@@ -431,12 +459,12 @@ static DeltaArgs make_args(bh_ctx* c, int n, int env_fixed, const int32_t* d_env
     a.U = c->dU; a.I = c->dI; a.T = c->dT; a.state = c->dstate; a.h = c->dh; a.sums = c->dsums;
     a.envs = d_envs; a.actions = d_actions; a.offset_ptr = nullptr; a.n_total = n;
     a.env_fixed = env_fixed;
-    a.n_tasks = n; a.N = c->N; a.P = c->P; a.F = c->F; a.G = c->G; a.Fg = c->Fg;
+    a.n_tasks = n; a.N = c->N; a.P = c->P; a.HP = h_stride(c->P); a.F = c->F; a.G = c->G; a.Fg = c->Fg;
     a.relative = c->relative; a.rule = rule;
     a.units_per_task = c->units_per_task;
     a.unit_dy = UNIT_PX / c->N; a.unit_dx = UNIT_PX % c->N;
     a.acc = c->d_acc; a.tickets = c->d_tickets; a.results = d_results;
-    a.results_host = nullptr; a.n_inline = 0;
+    a.results_host = nullptr; a.n_inline = 0; a.sort_window = 0;
     a.dbs_accepted = nullptr; a.dbs_trace = nullptr; a.dbs_count = nullptr; a.dbs_cursor = nullptr;
     return a;
 }
@@ -459,6 +487,20 @@ static cudaError_t launch_delta(bh_ctx* c, void (*kern)(const DeltaArgs), int gr
 
 static int launch_eval(bh_ctx* c, const DeltaArgs& a) {
     launch_delta(c, c->k_eval, delta_grid(c, a.n_tasks), a);
+    c->launches += 1;
+    return 0;
+}
+// Candidate lists that revisit frames of an environment: bundled evaluation (shared U / I / T
+// loads, k_eval_bundle_t).  It pays once runs of same-frame candidates are likely -- host lists are
+// sorted by frame, windows of one environment are sorted inside the kernel and need about four
+// candidates per frame.  Short windows (the greedy DBS while its accept rate is high) are faster
+// through k_eval_t, which keeps more independent units in flight (scripts/tune_bundle.py).
+static int launch_eval_list(bh_ctx* c, const DeltaArgs& a, bool sorted_by_caller) {
+    const int need = sorted_by_caller ? 2 * c->bundle : 4 * c->F;
+    if (!c->k_eval_bundle || a.n_tasks < need || (!sorted_by_caller && a.n_tasks > SORT_WINDOW_MAX))
+        return launch_eval(c, a);
+    const long long total = (long long)((a.n_tasks + c->bundle - 1) / c->bundle) * c->units_per_task;
+    launch_delta(c, c->k_eval_bundle, int(std::min<long long>(total, c->grid_cap_bundle)), a);
     c->launches += 1;
     return 0;
 }
@@ -493,7 +535,12 @@ extern "C" int bh_eval_flips_device(bh_ctx* c, int env, int n, const int32_t* d_
     if (!d_env_ids) BH_CHECK_ENV(c, env);
     DeltaArgs a = make_args(c, n, env, d_env_ids, reinterpret_cast<const long long*>(d_actions),
                             RULE_NEVER, reinterpret_cast<Result*>(d_results));
-    launch_eval(c, a);
+    if (d_env_ids) {
+        launch_eval(c, a);
+    } else {
+        a.sort_window = 1;              // a window of one environment: frame order inside the CTA
+        launch_eval_list(c, a, false);
+    }
     BH_CUDA(c, cudaGetLastError());
     return 0;
 }
@@ -527,7 +574,7 @@ extern "C" int bh_eval_flips(bh_ctx* c, int env, int64_t n, const int32_t* env_i
         if (env_ids)
             BH_CUDA(c, cudaMemcpyAsync(c->d_envs, c->h_envs, size_t(m) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         DeltaArgs a = make_args(c, m, env, env_ids ? c->d_envs : nullptr, c->d_actions, RULE_NEVER, c->d_results);
-        launch_eval(c, a);
+        launch_eval_list(c, a, true);
         BH_CUDA(c, cudaGetLastError());
         BH_CUDA(c, cudaMemcpyAsync(c->h_results, c->d_results, size_t(m) * sizeof(Result), cudaMemcpyDeviceToHost, c->stream));
         BH_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -687,7 +734,7 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
         BH_DBS(cudaMemcpyAsync(d_order, order, size_t(n) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
         BH_DBS(cudaMemsetAsync(d_acc, 0, size_t(n), c->stream));
         BH_DBS(cudaMemsetAsync(c->d_scalars, 0, 4 * sizeof(long long), c->stream));
-        const int kmax = std::min(64, c->max_tasks);
+        const int kmax = std::min(SORT_WINDOW_MAX, c->max_tasks);
         int K = k_spec > 0 ? std::min(k_spec, c->max_tasks) : 2;
         const int iters_per_sync = 32;
         long long cursor = 0, nacc = 0, last_resync = 0;
@@ -695,6 +742,7 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
             DeltaArgs a = make_args(c, K, env, nullptr, d_order, RULE_DBS, c->d_results);
             a.offset_ptr = c->d_scalars;
             a.n_total = n;
+            a.sort_window = 1;
             DeltaArgs ac = a;                   // the commit kernel also selects and logs
             ac.dbs_cursor = c->d_scalars; ac.dbs_count = c->d_scalars + 1;
             ac.dbs_accepted = d_acc; ac.dbs_trace = d_trace;
@@ -705,7 +753,7 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
                     cudaGraphExec_t ge = nullptr;
                     const int64_t before = c->launches;
                     BH_DBS(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                    for (int i = 0; i < iters_per_sync; ++i) { launch_eval(c, a); launch_commit(c, ac); }
+                    for (int i = 0; i < iters_per_sync; ++i) { launch_eval_list(c, a, false); launch_commit(c, ac); }
                     BH_DBS(cudaStreamEndCapture(c->stream, &g));
                     c->launches = before;       // captured, not launched
                     BH_DBS(cudaGraphInstantiate(&ge, g, 0));
@@ -715,7 +763,7 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
                 BH_DBS(cudaGraphLaunch(it->second, c->stream));
                 c->launches += 2 * iters_per_sync;
             } else {
-                for (int i = 0; i < iters_per_sync; ++i) { launch_eval(c, a); launch_commit(c, ac); }
+                for (int i = 0; i < iters_per_sync; ++i) { launch_eval_list(c, a, false); launch_commit(c, ac); }
             }
             BH_DBS(cudaGetLastError());
             BH_DBS(cudaMemcpyAsync(c->h_scalars, c->d_scalars, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
@@ -928,7 +976,7 @@ extern "C" int bh_get_recon(bh_ctx* c, int env, float* out, int on_host, int64_t
         BH_CUDA(c, cudaStreamSynchronize(c->stream));
         const float sgn = 1.f - 2.f * float(sb);
         k_recon_candidate<<<std::min<size_t>((n2 + 255) / 256, 148 * 8), 256, 0, c->stream>>>(
-            c->dU + (size_t(env) * c->F + f) * n2, c->dh + size_t(g) * c->P * c->P, dst + size_t(g) * n2,
+            c->dU + (size_t(env) * c->F + f) * n2, c->dh + size_t(g) * c->P * h_stride(c->P), dst + size_t(g) * n2,
             c->N, c->P, r, col, sgn, c->Fg);
         BH_CUDA(c, cudaGetLastError());
         c->launches += 1;
@@ -1047,11 +1095,14 @@ extern "C" int bh_time_eval(bh_ctx* c, int n, const int32_t* d_env_ids, const in
     BH_CHECK_CTX(c);
     if (n < 1 || n > c->max_tasks || reps < 1 || n_sets < 1 || !ms_per_launch) BH_FAIL(c, -1, "bad arguments");
     DeltaArgs a = make_args(c, n, 0, d_env_ids, reinterpret_cast<const long long*>(d_actions), RULE_NEVER, c->d_results);
-    for (int i = 0; i < 3; ++i) launch_eval(c, a);          // warm
+    // no env ids: a window of candidates of environment 0, scored like a DBS speculation window
+    a.sort_window = d_env_ids ? 0 : 1;
+    auto launch = [&]() { return d_env_ids ? launch_eval(c, a) : launch_eval_list(c, a, false); };
+    for (int i = 0; i < 3; ++i) launch();                    // warm
     BH_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     for (int i = 0; i < reps; ++i) {
         a.actions = reinterpret_cast<const long long*>(d_actions) + size_t(i % n_sets) * n;
-        launch_eval(c, a);
+        launch();
     }
     BH_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     BH_CUDA(c, cudaEventSynchronize(c->ev1));

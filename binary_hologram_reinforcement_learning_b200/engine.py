@@ -258,6 +258,18 @@ class HoloEngine:
             self._check(rc, "bh_vec_step")
         return out
 
+    def vec_step_ptrs(self, n: int, ptrs, rule: int, book: "VecBook"):
+        """``vec_step`` on cached addresses ``(env_ids, actions, results)`` of persistent host arrays."""
+        rc = self.lib.bh_vec_step(self._h, n, ptrs[0], ptrs[1], rule, ptrs[2], self._book_ref(book))
+        if rc != 0:
+            self._check(rc, "bh_vec_step")
+
+    def _book_ref(self, book: "VecBook"):
+        ref = getattr(book, "_cached_ref", None)
+        if ref is None:
+            ref = book._cached_ref = C.addressof(book)
+        return ref
+
     def step_batch_device(self, n: int, d_env_ids: int, d_actions: int, rule: int, d_results: int):
         self._check(self.lib.bh_step_batch_device(self._h, n, C.c_void_p(d_env_ids),
                                                   C.c_void_p(d_actions), rule, C.c_void_p(d_results)),

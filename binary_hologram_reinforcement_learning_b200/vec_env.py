@@ -46,6 +46,11 @@ class HologramVecEnv:
         self._actions = None
         self._res = np.empty(self.num_envs, dtype=RESULT_DTYPE)
         self._eids = np.arange(self.num_envs, dtype=np.int32)
+        # the step path passes raw addresses: ndarray.ctypes costs more than a microsecond per use
+        self._actions = np.zeros(self.num_envs, dtype=np.int64)
+        self._ptrs = (self._eids.ctypes.data, self._actions.ctypes.data, self._res.ctypes.data)
+        self._psnr_after = self._res["psnr_after"]
+        self._no_event = bytes(self.num_envs)
         self._sim = np.empty(self.num_envs, dtype=np.int64)
         # episode statistics of finished episodes: reward, steps, flips, psnr0, psnr1
         self.episode_stats: List[np.ndarray] = []
@@ -189,8 +194,8 @@ class HologramVecEnv:
         """env.py:154-260 for all envs with numpy; per-env Python only on episode events."""
         acts, envs, E = self._actions, self.envs, self.num_envs
         # scoring on the GPU + mirrors, counters, psnr_change, reward, event mask in one foreign call
-        res = self.engine.vec_step(acts, self._eids, RULE_ENV, self._res, self._book)
-        psnr_after = res["psnr_after"]
+        self.engine.vec_step_ptrs(E, self._ptrs, RULE_ENV, self._book)
+        res, psnr_after = self._res, self._psnr_after
         diff = self._diff
         if self._group:                                              # env_group.py:254-255
             rewards = np.empty(E)
@@ -204,7 +209,7 @@ class HologramVecEnv:
             if acc.any():
                 for i in np.flatnonzero(acc & (self._flips % envs[0].resync_every == 0)):
                     self.engine.resync(int(i))
-        if not self._event.any():
+        if self._event.tobytes() == self._no_event:
             self._ep_reward += rewards
             return self._pack(self._obs_cache), rewards, self._no_done.copy(), infos
         dones = np.zeros(E, dtype=bool)
@@ -235,7 +240,7 @@ class HologramVecEnv:
         return self._pack(self._obs_cache), rewards, dones, infos
 
     def step_async(self, actions):
-        self._actions = np.ascontiguousarray(actions, dtype=np.int64).reshape(self.num_envs)
+        self._actions[:] = np.asarray(actions).reshape(self.num_envs)
 
     def step_wait(self):
         if self._fast:

@@ -19,6 +19,6 @@ if len(sys.argv) > 1:
     print(json.dumps({"variant": os.environ.get("BHOLO_EVAL_VARIANT", "0"), "ms_8": ms,
                       "gbs_8": 16 * N * N * E / ms / 1e6, "ms_1": ms1, "gbs_1": 16 * N * N / ms1 / 1e6}))
 else:
-    for v in [0, 1, 2, 3]:
+    for v in [0, 1, 2, 3, 4, 5, 6]:
         env = dict(os.environ, BHOLO_EVAL_VARIANT=str(v))
         print(subprocess.run([sys.executable, __file__, "run"], env=env, capture_output=True, text=True).stdout.strip())

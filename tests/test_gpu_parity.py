@@ -12,7 +12,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import binary_hologram_reinforcement_learning_b200 as bh
-from binary_hologram_reinforcement_learning_b200.engine import RULE_DBS, RULE_ENV, RULE_NEVER
+from binary_hologram_reinforcement_learning_b200.engine import RESULT_DTYPE, RULE_DBS, RULE_ENV, RULE_NEVER
 from oracle import hologram_oracle as O
 from tests.golden import make_golden as MG
 
@@ -186,7 +186,7 @@ def test_golden_env_trajectory(name, golden_dir):
 
 
 @pytest.mark.parametrize("name", list(MG.CASES))
-@pytest.mark.parametrize("k_spec", [1, 0, 16])
+@pytest.mark.parametrize("k_spec", [1, 0, 16, 128])    # 128: frame-sorted, bundled windows
 def test_golden_dbs_greedy(name, k_spec, golden_dir):
     """DBS.py:247-294: the device loop reproduces the sequential accept sequence for any batch depth."""
     N, F, wl, pad, relative, seed = MG.CASES[name]
@@ -734,3 +734,36 @@ def test_multidiscrete_action_equals_flat_action():
     with pytest.raises(ValueError):
         a.step(np.array([F, 0, 0]))
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("N,F,wl", [(64, 6, O.WL_RGB), (256, 8, O.WL_MONO)])
+def test_bundled_list_evaluation_is_bit_identical_to_single_candidates(N, F, wl):
+    """Candidate lists (host list, single-env device window) run through k_eval_bundle_t, which shares the
+    U / I / T loads between candidates of a frame; its exact fixed-point sums equal k_eval_t's bit for bit."""
+    import torch
+    E = 3
+    eng = _engine(N, F, wl, n_env=E)
+    for e in range(E):
+        pre, tgt, st = _problem(N, F, wl, seed=900 + e)
+        eng.set_target(e, tgt)
+        eng.load_state(e, st)
+    rng = np.random.default_rng(5)
+    n = 301                                                # ragged: not a multiple of any bundle size
+    acts = rng.integers(0, F * N * N, size=n)
+    acts[10:40] = rng.integers(0, N * N, size=30) + 2 * N * N          # a long same-frame run
+    acts[50] = acts[51] = acts[52]                                     # duplicates
+    envs = rng.integers(0, E, size=n).astype(np.int32)
+    single = np.array([eng.eval_flips(acts[i:i + 1], env_ids=envs[i:i + 1])[0] for i in range(n)])
+    listed = eng.eval_flips(acts, env_ids=envs)
+    assert np.array_equal(single, listed)
+    # one environment, device-resident window of K candidates (the DBS speculation window)
+    for K in (2, 7, 64, 128, 300):
+        d_act = torch.from_numpy(acts[:K].astype(np.int64)).cuda()
+        d_res = torch.zeros(K * 40, dtype=torch.uint8, device="cuda")
+        eng.eval_flips_device(K, 0, d_act.data_ptr(), d_res.data_ptr(), env=1)
+        torch.cuda.synchronize()
+        res = d_res.cpu().numpy().view(RESULT_DTYPE)
+        ref = np.array([eng.eval_flips(acts[i:i + 1], env=1)[0] for i in range(K)])
+        assert np.array_equal(res["psnr_after"], ref)
+        assert np.array_equal(res["action"], acts[:K])
+    eng.close()
