@@ -38,13 +38,13 @@ echo "ncu launches rc=$?"
 
 # (2) full capture of the delta kernels (ncu default: caches flushed before every replay)
 timeout 300 $SMALL > gpurun_out/bench_small2.json 2> gpurun_out/bench_small2.err &&
-timeout 600 ncu --set full --clock-control none -k regex:"k_(eval|commit)" -s 20 -c 8 \
+timeout 600 ncu --set full --clock-control none -k regex:"k_(eval_t|commit_t)" -s 20 -c 8 \
     -f -o gpurun_out/prof_hotpath $SMALL > gpurun_out/ncu_full.log 2>&1
 echo "ncu delta kernels rc=$?"; tail -1 gpurun_out/ncu_full.log
 raw_csv prof_hotpath
 
 # (3) k_eval with warm caches: the live L2 residency of the impulse table
-timeout 600 ncu --set full --clock-control none --cache-control none -k regex:"k_eval" -s 20 -c 4 \
+timeout 600 ncu --set full --clock-control none --cache-control none -k regex:"k_eval_t" -s 20 -c 4 \
     -f -o gpurun_out/prof_eval_warm $SMALL > gpurun_out/ncu_warm.log 2>&1
 echo "ncu warm rc=$?"; tail -1 gpurun_out/ncu_warm.log
 raw_csv prof_eval_warm
@@ -56,3 +56,9 @@ timeout 600 ncu --set full --clock-control none \
     -f -o gpurun_out/prof_prop python scripts/prof_prop.py > gpurun_out/ncu_prop.log 2>&1
 echo "ncu prop rc=$?"; cat gpurun_out/prop_plain.log
 raw_csv prof_prop
+
+# (5) bundled candidate-list evaluation (bh_eval_flips inside the bench extras)
+timeout 600 ncu --set full --clock-control none --cache-control none -k regex:"k_eval_bundle" -c 2 \
+    -f -o gpurun_out/prof_bundle $SMALL > gpurun_out/ncu_bundle.log 2>&1
+echo "ncu bundle rc=$?"; tail -1 gpurun_out/ncu_bundle.log
+raw_csv prof_bundle

@@ -55,7 +55,7 @@ if os.path.exists(lp):
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"| {k} | {len(v)} | {sum(v):.1f} | {100 * sum(v) / total:.1f}% | {sum(v) / len(v):.2f} | {min(v):.2f} | {max(v):.2f} |\n")
         # share inside one env step: consecutive k_eval, k_commit pairs
-        ev = [x for k, v in agg.items() if k.startswith("k_eval") for x in v]
+        ev = [x for k, v in agg.items() if k.startswith("k_eval_t") for x in v]
         cm = [x for k, v in agg.items() if k.startswith("k_commit") for x in v]
         if ev and cm:
             f.write(f"\nInside an env step (k_eval + k_commit): k_eval mean {sum(ev) / len(ev):.2f} us, "
@@ -75,7 +75,7 @@ def raw_page(stem):
     return None
 
 
-EXTRA = [("prof_prop", "propagation"), ("prof_eval_warm", "eval_warm_cache")]
+EXTRA = [("prof_prop", "propagation"), ("prof_eval_warm", "eval_warm_cache"), ("prof_bundle", "eval_bundle")]
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -96,7 +96,7 @@ if raw:
         for r in data:
             w.writerow([short(r[ik])] + [r[i] for i in idx.values()])
     # per-launch DRAM traffic of k_eval (steady-state launches)
-    ev = [r for r in data if short(r[ik]).startswith("k_eval")]
+    ev = [r for r in data if short(r[ik]).startswith("k_eval_t")]
     if ev:
         def mb(r, key):
             i = hdr.index(key)
