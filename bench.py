@@ -397,7 +397,7 @@ def run_b200(args):
                          "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "env steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "api": "HologramVecEnv.step (bh_step_batch)",
+                    "d2h_bytes_per_step": d2h, "api": "HologramVecEnv.step (bh_vec_step)",
                     "checksum_reward_env0": reward_sum,
                     "with_eager_recon_obs": {"value": world * E * n_eager / eager_s, "unit": "env steps/s",
                                              "d2h_bytes_per_env_step": 4 * GROUPS * N_SIDE * N_SIDE}},
