@@ -496,8 +496,12 @@ static int launch_eval(bh_ctx* c, const DeltaArgs& a) {
 // candidates per frame.  Short windows (the greedy DBS while its accept rate is high) are faster
 // through k_eval_t, which keeps more independent units in flight (scripts/tune_bundle.py).
 static int launch_eval_list(bh_ctx* c, const DeltaArgs& a, bool sorted_by_caller) {
-    const int need = sorted_by_caller ? 2 * c->bundle : 4 * c->F;
-    if (!c->k_eval_bundle || a.n_tasks < need || (!sorted_by_caller && a.n_tasks > SORT_WINDOW_MAX))
+    // images that are not row-regular (896^2 crop) run the bundled kernel's generic loop, one unit in
+    // flight: it only wins on long lists (896^2 x 24: 128 per call 580 k -> 530 k/s, 65 536 per call
+    // 616 k -> 863 k/s)
+    const bool regular = UNIT_PX % c->N == 0;
+    const int need = !regular ? 512 : (sorted_by_caller ? 2 * c->bundle : 4 * c->F);
+    if (!c->k_eval_bundle || a.n_tasks < need || (!sorted_by_caller && (!regular || a.n_tasks > SORT_WINDOW_MAX)))
         return launch_eval(c, a);
     const long long total = (long long)((a.n_tasks + c->bundle - 1) / c->bundle) * c->units_per_task;
     launch_delta(c, c->k_eval_bundle, int(std::min<long long>(total, c->grid_cap_bundle)), a);

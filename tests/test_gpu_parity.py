@@ -736,8 +736,8 @@ def test_multidiscrete_action_equals_flat_action():
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("N,F,wl", [(64, 6, O.WL_RGB), (256, 8, O.WL_MONO)])
-def test_bundled_list_evaluation_is_bit_identical_to_single_candidates(N, F, wl):
+@pytest.mark.parametrize("N,F,wl,n", [(64, 6, O.WL_RGB, 301), (256, 8, O.WL_MONO, 301), (896, 3, O.WL_RGB, 601)])
+def test_bundled_list_evaluation_is_bit_identical_to_single_candidates(N, F, wl, n):
     """Candidate lists (host list, single-env device window) run through k_eval_bundle_t, which shares the
     U / I / T loads between candidates of a frame; its exact fixed-point sums equal k_eval_t's bit for bit."""
     import torch
@@ -748,7 +748,8 @@ def test_bundled_list_evaluation_is_bit_identical_to_single_candidates(N, F, wl)
         eng.set_target(e, tgt)
         eng.load_state(e, st)
     rng = np.random.default_rng(5)
-    n = 301                                                # ragged: not a multiple of any bundle size
+    # n is ragged (not a multiple of any bundle size); 896 is the one size that is not row-regular: its
+    # lists take the bundled kernel's generic loop from 512 candidates on
     acts = rng.integers(0, F * N * N, size=n)
     acts[10:40] = rng.integers(0, N * N, size=30) + 2 * N * N          # a long same-frame run
     acts[50] = acts[51] = acts[52]                                     # duplicates
