@@ -647,11 +647,11 @@ extern "C" int bh_step_batch(bh_ctx* c, int n, const int32_t* env_ids, const int
     return 0;
 }
 
-extern "C" int bh_vec_step(bh_ctx* c, int n, const int32_t* env_ids, const int64_t* actions, int rule,
-                           bh_result* results, const bh_vec_book* b) {
+extern "C" int bh_vec_book_update(int n, const int32_t* env_ids, const int64_t* actions,
+                                  const bh_result* results, const bh_vec_book* b) {
     if (!b || !b->prev_psnr || !b->init_psnr || !b->steps || !b->flips || !b->rewards)
-        BH_FAIL(c, -1, "incomplete bh_vec_book");
-    if (int rc = bh_step_batch(c, n, env_ids, actions, rule, results)) return rc;
+        BH_FAIL((bh_ctx*)nullptr, -1, "incomplete bh_vec_book");
+    if (n < 0 || (n > 0 && (!actions || !results))) BH_FAIL((bh_ctx*)nullptr, -1, "bad arguments");
     for (int i = 0; i < n; ++i) {
         const int e = env_ids ? env_ids[i] : i;
         const bh_result& r = results[i];
@@ -677,6 +677,14 @@ extern "C" int bh_vec_step(bh_ctx* c, int n, const int32_t* env_ids, const int64
         if (b->event) b->event[i] = ev;
     }
     return 0;
+}
+
+extern "C" int bh_vec_step(bh_ctx* c, int n, const int32_t* env_ids, const int64_t* actions, int rule,
+                           bh_result* results, const bh_vec_book* b) {
+    if (!b || !b->prev_psnr || !b->init_psnr || !b->steps || !b->flips || !b->rewards)
+        BH_FAIL(c, -1, "incomplete bh_vec_book");
+    if (int rc = bh_step_batch(c, n, env_ids, actions, rule, results)) return rc;
+    return bh_vec_book_update(n, env_ids, actions, results, b);
 }
 
 extern "C" int bh_commit_flip(bh_ctx* c, int env, int64_t action) {

@@ -20,7 +20,7 @@ METHOD_ASM, METHOD_FRESNEL = 0, 1
 ABI_SYMBOLS = (
     "bh_abi_version", "bh_last_error", "bh_create", "bh_destroy", "bh_set_stream",
     "bh_set_target", "bh_load_state", "bh_clone_env", "bh_resync", "bh_get_metrics", "bh_eval_flips",
-    "bh_step_batch", "bh_vec_step", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
+    "bh_step_batch", "bh_vec_step", "bh_vec_book_update", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
     "bh_commit_flip", "bh_dbs_run", "bh_sweep_all", "bh_sweep_stats", "bh_get_recon", "bh_get_state", "bh_get_field",
     "bh_device_ptr", "bh_host_alloc", "bh_host_free", "bh_simulate", "bh_time_eval", "bh_time_propagate", "bh_time_propagate_passes", "bh_launch_count",
 )
@@ -85,6 +85,7 @@ def load_library(build_if_missing: bool = True):
         "bh_eval_flips": (i32, [vp, i32, i64, vp, vp, vp]),
         "bh_step_batch": (i32, [vp, i32, vp, vp, i32, vp]),
         "bh_vec_step": (i32, [vp, i32, vp, vp, i32, vp, vp]),
+        "bh_vec_book_update": (i32, [i32, vp, vp, vp, vp]),
         "bh_step_batch_device": (i32, [vp, i32, vp, vp, i32, vp]),
         "bh_eval_flips_device": (i32, [vp, i32, i32, vp, vp, vp]),
         "bh_max_tasks": (i32, [vp]),

@@ -139,6 +139,13 @@ typedef struct bh_vec_book {
 int bh_vec_step(bh_ctx* ctx, int n, const int32_t* env_ids, const int64_t* actions, int rule,
                 bh_result* results, const bh_vec_book* book);
 
+/* The bookkeeping half of bh_vec_step on its own: applies env.py:163-167,184-196,214 to n scored
+ * steps (results from bh_step_batch or read back from bh_step_batch_device).  Host only -- no
+ * CUDA call, usable (and tested) without a GPU.  Returns 0, or -1 for an incomplete book
+ * (message via bh_last_error(NULL)). */
+int bh_vec_book_update(int n, const int32_t* env_ids, const int64_t* actions,
+                       const bh_result* results, const bh_vec_book* book);
+
 /* Same with DEVICE pointers and no synchronisation (inputs resident in HBM). */
 int bh_step_batch_device(bh_ctx* ctx, int n, const int32_t* d_env_ids,
                          const int64_t* d_actions, int rule, bh_result* d_results);

@@ -78,6 +78,60 @@ def test_goal_bonus_constants():
     assert abs(envs.goal_bonus(0.5, -595.24) - O.goal_bonus(0.5, -595.24)) < 1e-12
 
 
+def test_vec_book_update_follows_env_py_without_a_gpu():
+    """bh_vec_book_update (the host half of bh_vec_step): env.py:163-167,184-196,214 and appendix B-1/3/6/7."""
+    lib = engine.load_library()
+    E, stride = 3, 12
+    state = np.zeros((E, stride), np.int8); record = np.zeros((E, stride), np.int8)
+    record[2, 7] = 127                                         # B-7: the int8 attempt counter wraps
+    prev = np.array([10.0, 20.0, 29.95]); init = prev.copy()
+    steps = np.zeros(E, np.int64); flips = np.zeros(E, np.int64)
+    tdiff = np.full(E, 0.1); tpsnr = np.full(E, 30.0); maxs = np.array([100, 3, 100], np.int64)
+    rewards = np.zeros(E); change = np.zeros(E); diff = np.zeros(E)
+    last = np.full(E, -7, np.int64); event = np.zeros(E, np.uint8)
+    b = engine.VecBook()
+    b.state, b.state_record, b.stride = state.ctypes.data, record.ctypes.data, stride
+    b.prev_psnr, b.init_psnr, b.steps, b.flips = prev.ctypes.data, init.ctypes.data, steps.ctypes.data, flips.ctypes.data
+    b.t_psnr_diff, b.t_psnr, b.max_steps, b.reward_scale = tdiff.ctypes.data, tpsnr.ctypes.data, maxs.ctypes.data, 800.0
+    b.rewards, b.psnr_change, b.psnr_diff = rewards.ctypes.data, change.ctypes.data, diff.ctypes.data
+    b.last_candidate, b.event = last.ctypes.data, event.ctypes.data
+
+    def update(env_ids, actions, psnr_after, accept):
+        n = len(actions)
+        res = np.zeros(n, engine.RESULT_DTYPE)
+        res["psnr_after"], res["accept"], res["action"] = psnr_after, accept, actions
+        ids = np.asarray(env_ids, np.int32); act = np.asarray(actions, np.int64)
+        rc = lib.bh_vec_book_update(n, ids.ctypes.data, act.ctypes.data, res.ctypes.data, ctypes.addressof(b))
+        assert rc == 0
+
+    # step 1: env0 kept with a big gain (success event), env1 rejected, env2 kept above T_PSNR with diff < 0.1
+    update([0, 1, 2], [2, 5, 7], [10.5, 19.9, 30.02], [1, 0, 1])
+    np.testing.assert_allclose(rewards, [400.0, -80.0, 0.07 * 800], rtol=0, atol=1e-9)       # env.py:188
+    assert list(steps) == [1, 1, 1] and list(flips) == [1, 0, 1]                            # B-6
+    assert state[0, 2] == 1 and state[1, 5] == 0 and state[2, 7] == 1                       # rejected flip rolled back
+    assert record[0, 2] == 1 and record[1, 5] == 1 and record[2, 7] == -128                 # every attempt counts; wraps
+    np.testing.assert_allclose(prev, [10.5, 20.0, 30.02])                                   # env.py:214 / :196
+    assert list(last) == [-1, 5, -1] and list(event) == [1, 0, 1]
+    np.testing.assert_allclose(diff, [0.5, -0.1, 0.07], atol=1e-12)
+    # step 2: a subset in another order; ties are kept by the env rule (decided on the device), no event for env1
+    update([1, 0], [5, 2], [20.0, 10.5], [1, 1])
+    np.testing.assert_allclose(rewards[:2], [0.0, 0.0], atol=1e-12)
+    assert list(steps) == [2, 2, 1] and list(flips) == [2, 1, 1]
+    assert state[1, 5] == 1 and state[0, 2] == 0 and record[1, 5] == 2 and record[0, 2] == 2
+    assert list(event[:2]) == [0, 1]                           # env0: psnr_diff 0.5 >= T_PSNR_DIFF again
+    # step 3: env1 reaches max_steps on a rejected flip -> no event (B-1) ...
+    update([1], [6], [19.0], [0])
+    assert steps[1] == 3 and event[0] == 0 and last[1] == 6 and prev[1] == 20.0
+    # ... and on the next kept flip the max_steps branch has to run although the gain is tiny
+    update([1], [6], [20.01], [1])
+    assert steps[1] == 4 and event[0] == 1 and flips[1] == 2 and abs(rewards[0] - 8.0) < 1e-9
+    # an incomplete book is refused
+    b2 = engine.VecBook()
+    ids = np.zeros(1, np.int32); act = np.zeros(1, np.int64); res = np.zeros(1, engine.RESULT_DTYPE)
+    assert lib.bh_vec_book_update(1, ids.ctypes.data, act.ctypes.data, res.ctypes.data, ctypes.addressof(b2)) == -1
+    assert b"incomplete" in lib.bh_last_error(None)
+
+
 def test_synthetic_inputs_match_oracle_copy():
     a = bh.synthetic_problem(32, 6, 3, 7)
     b = O.synthetic_problem(32, 6, 3, 7)
