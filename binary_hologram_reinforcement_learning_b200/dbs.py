@@ -38,6 +38,73 @@ def decile_index(pre_values: np.ndarray) -> np.ndarray:
     return idx
 
 
+def _decode(action, N: int):
+    """(channel, row, col) of a flat action on an N x N grid (DBS.py:248-251)."""
+    a = int(action)
+    return a // (N * N), (a % (N * N)) // N, a % N
+
+
+def _accepted_bins(pre, perm, accepted, trace, initial_psnr):
+    """Accepted flips and their PSNR gains per decile of the pre-model output (DBS_1024_24.py:398-416)."""
+    nb = len(OUTPUT_BINS) - 1
+    acc_idx = np.flatnonzero(accepted)
+    if not acc_idx.size:
+        return np.zeros(nb, dtype=np.int64), np.zeros(nb)
+    prev_psnr = np.concatenate([[initial_psnr], trace[acc_idx[:-1]]])
+    d = decile_index(pre.ravel()[perm[acc_idx]])
+    ok = d >= 0
+    return (np.bincount(d[ok], minlength=nb),
+            np.bincount(d[ok], weights=(trace[acc_idx] - prev_psnr)[ok], minlength=nb))
+
+
+def _emit_sweep_log(file_name, initial_psnr, perm, psnr_all, cpre, N, bin_counts, t0, log_every=5000):
+    """The stdout of the reference's score-and-revert sweep, replayed from the per-candidate results.
+
+    dbs-1024-1024-24-6464.py:396-431: every ``log_every`` candidates a step block (the candidate of that
+    step, counters including it, its pre-model value) and the cumulative range lines WITH ``Attempted
+    Pixels`` -- the lines log_py/'dbs 평균.py':25-31 parses; then the summary of :439-447,462-478 (range
+    lines without the attempt counts).  The sweep never accepts, so ``PSNR Before`` is the initial PSNR.
+    """
+    n = int(perm.shape[0])
+    nb = len(OUTPUT_BINS) - 1
+    pre_vals = np.asarray(cpre).ravel()[perm]
+    d = decile_index(pre_vals)
+    better = psnr_all > initial_psnr
+    gain = np.where(better, psnr_all - initial_psnr, 0.0)
+    att, imp, gn = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.int64), np.zeros(nb)
+    flips = 0
+
+    def step_block(k, with_pre):
+        ch, row, col = _decode(perm[k - 1], N)
+        tail = f"\npre_value: {float(pre_vals[k - 1]):.6f}" if with_pre else ""
+        print(f"Step: {k}"
+              f"\nPSNR Before: {initial_psnr:.6f} | PSNR After: {psnr_all[k - 1]:.6f} | Change: {psnr_all[k - 1] - initial_psnr:.6f}"
+              f"\nSuccess Ratio: {flips / k:.6f} | Flip Count: {flips}"
+              f"\nFlip Pixel: Channel={ch}, Row={row}, Col={col}"
+              f"\nTime taken for this data: {time.time() - t0:.2f} seconds{tail}")
+
+    step = max(1, int(log_every))
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        dd, bb = d[lo:hi], better[lo:hi]
+        ok = dd >= 0
+        att += np.bincount(dd[ok], minlength=nb)
+        imp += np.bincount(dd[ok & bb], minlength=nb)
+        gn += np.bincount(dd[ok & bb], weights=gain[lo:hi][ok & bb], minlength=nb)
+        flips += int(np.count_nonzero(bb))
+        if hi - lo == step:                                # ...6464.py:396 `steps % 5000 == 0`
+            step_block(hi, True)
+            _print_bins(bin_counts, imp, gn, att)
+    if n:
+        step_block(n, False)                               # ...6464.py:439-445
+    last = psnr_all[-1] if n else initial_psnr
+    print(f"{file_name}.png Optimization completed. Final PSNR improvement: {last - initial_psnr:.6f}")
+    print(f"Time taken for this data: {time.time() - t0:.2f} seconds\n")
+    print("Pre-model output range statistics:")
+    _print_bins(bin_counts, imp, gn)
+    print("\n")
+
+
 def _file_stem(name) -> str:
     if isinstance(name, (list, tuple)):
         name = name[0]
@@ -127,6 +194,7 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
         thresholds = [initial_psnr + i * step_gain for i in range(1, 21 if env.G == 1 else 101)]
         previous = initial_psnr
         flip_count = 0
+        last_change = last_ratio = None                   # set by the threshold blocks (stale in the summary)
         start = 0
         if checkpoint and os.path.exists(checkpoint):
             ck = np.load(checkpoint)
@@ -158,10 +226,18 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
                         pa = trace[j]
                         prev_acc = hit[hit < j]
                         pb = trace[prev_acc[-1]] if prev_acc.size else previous
-                        print(f"Step: {j + 1}"
-                              f"\nPSNR Before: {pb:.6f} | PSNR After: {pa:.6f} | Change: {pa - pb:.6f} | Diff: {pa - initial_psnr:.6f}"
-                              f"\nSuccess Ratio: {np.count_nonzero(accepted[:j + 1]) / (j + 1):.6f} | Flip Count: {np.count_nonzero(accepted[:j + 1])}"
+                        n_acc = int(np.count_nonzero(accepted[:j + 1]))
+                        last_change, last_ratio = pa - pb, n_acc / (j + 1)
+                        ch, row, col = _decode(perm[j], eng.N)
+                        print(f"Step: {j + 1}"                       # DBS.py:283-289, DBS_1024_24.py:372-378
+                              f"\nPSNR Before: {pb:.6f} | PSNR After: {pa:.6f} | Change: {last_change:.6f} | Diff: {pa - initial_psnr:.6f}"
+                              f"\nSuccess Ratio: {last_ratio:.6f} | Flip Count: {n_acc}"
+                              f"\nFlip Pixel: Channel={ch}, Row={row}, Col={col}"
                               f"\nTime taken for this data: {time.time() - t0:.2f} seconds")
+                        if env.G > 1:                                # DBS_1024_24.py:379-396 (flips before this one)
+                            imp_j, gn_j = _accepted_bins(pre, perm, accepted[:j], trace, initial_psnr)
+                            _print_bins(bin_counts + imp_j, imp_j, gn_j)
+                            print("\n")
                 previous = trace[hit[-1]]
             if checkpoint:
                 tmp = checkpoint + ".tmp.npz"
@@ -174,15 +250,7 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
         final_psnr, _, _ = eng.metrics(e)
         env.previous_psnr = final_psnr
         # decile statistics of the accepted flips (DBS_1024_24.py:390-416)
-        acc_idx = np.flatnonzero(accepted)
-        improved = np.zeros(len(OUTPUT_BINS) - 1, dtype=np.int64)
-        gains = np.zeros(len(OUTPUT_BINS) - 1)
-        if acc_idx.size:
-            prev_psnr = np.concatenate([[initial_psnr], trace[acc_idx[:-1]]])
-            d = decile_index(pre.ravel()[perm[acc_idx]])
-            ok = d >= 0
-            improved = np.bincount(d[ok], minlength=improved.size)
-            gains = np.bincount(d[ok], weights=(trace[acc_idx] - prev_psnr)[ok], minlength=gains.size)
+        improved, gains = _accepted_bins(pre, perm, accepted, trace, initial_psnr)
         steps = int(done_upto)
         accepted, trace = accepted[:steps], trace[:steps]
         dt = time.time() - t0
@@ -195,10 +263,18 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
             np.save(os.path.join(save_dir, f"episode_{file_name}_rgb_after.npy"), eng.recon(e)[None])
             np.save(os.path.join(save_dir, f"episode_{file_name}_state_after.npy"), new_state)
         if verbose:
+            # the reference's summary shows the LAST EVALUATED candidate (possibly rejected) next to the stale
+            # change / ratio of the last threshold block (DBS.py:297-305, appendix B-11)
             last = trace[-1] if steps else initial_psnr
+            ch, row, col = _decode(perm[steps - 1], eng.N) if steps else (0, 0, 0)
+            if last_change is None:                       # no threshold block was printed: the reference raises here
+                last_change, last_ratio = 0.0, (flip_count / steps if steps else 0.0)
+            change = (f"Change: {last_change:.6f} | Diff: {last - initial_psnr:.6f}" if env.G == 1   # DBS.py:301
+                      else f"Change: {last - initial_psnr:.6f}")                                       # DBS_1024_24.py:432
             print(f"Step: {steps}"
-                  f"\nPSNR Before: {final_psnr:.6f} | PSNR After: {last:.6f} | Change: {last - initial_psnr:.6f}"
-                  f"\nSuccess Ratio: {(flip_count / steps if steps else 0):.6f} | Flip Count: {flip_count}"
+                  f"\nPSNR Before: {final_psnr:.6f} | PSNR After: {last:.6f} | {change}"
+                  f"\nSuccess Ratio: {last_ratio:.6f} | Flip Count: {flip_count}"
+                  f"\nFlip Pixel: Channel={ch}, Row={row}, Col={col}"
                   f"\nTime taken for this data: {dt:.2f} seconds")
             print(f"{file_name}.png Optimization completed. Final PSNR improvement: {last - initial_psnr:.6f}")
             print(f"Time taken for this data: {dt:.2f} seconds\n")
@@ -246,7 +322,7 @@ def dbs_sweep(target_function: Callable, trainloader: Iterable, z=2e-3, pixel_pi
               crop_margin=64, *, CH=24, wl=WL_RGB, max_datasets=1, order: Optional[np.ndarray] = None,
               rng=None, device=0, pad=1, relative=True, verbose=True,
               max_candidates: Optional[int] = None, chunk: int = 1 << 18,
-              shard: Optional[tuple] = None) -> List[dict]:
+              shard: Optional[tuple] = None, log_every: int = 5000) -> List[dict]:
     """dbs-1024-1024-24-6464.py:194-478: crop, then score every flip and always revert.
 
     ``shard=(rank, world)`` scores only this rank's contiguous slice of the
@@ -318,15 +394,7 @@ def dbs_sweep(target_function: Callable, trainloader: Iterable, z=2e-3, pixel_pi
                                 attempted=att, improved=imp, gains=gn, bin_counts=bin_counts,
                                 flip_count=flip_count, steps=int(n), seconds=dt))
             if verbose:
-                print(f"Step: {n}"
-                      f"\nPSNR Before: {initial_psnr:.6f} | PSNR After: {psnr_all[-1]:.6f} | Change: {psnr_all[-1] - initial_psnr:.6f}"
-                      f"\nSuccess Ratio: {flip_count / n:.6f} | Flip Count: {flip_count}"
-                      f"\nTime taken for this data: {dt:.2f} seconds")
-                print(f"{file_name}.png Optimization completed.")
-                print(f"Time taken for this data: {dt:.2f} seconds\n")
-                print("Pre-model output range statistics:")
-                _print_bins(bin_counts, imp, gn, att)
-                print("\n")
+                _emit_sweep_log(file_name, initial_psnr, perm, psnr_all, cpre, N, bin_counts, t0, log_every)
             continue
         if eng.Fg % 2 == 0 and (hi_all - lo_all) * 4 >= n:
             psnr_map = eng.sweep_all(0)                    # every candidate in one call
@@ -337,24 +405,13 @@ def dbs_sweep(target_function: Callable, trainloader: Iterable, z=2e-3, pixel_pi
             psnr_all[lo - lo_all:hi - lo_all] = r["psnr_after"]
             attempted += r["attempted"]; improved += r["improved"]; gains += r["gains"]
             flip_count += r["flip_count"]
-            if verbose:                                   # ...6464.py:396-431 (every 5000 steps there)
-                steps = hi - lo_all
-                print(f"Step: {steps}"
-                      f"\nPSNR Before: {initial_psnr:.6f} | PSNR After: {psnr_all[hi - lo_all - 1]:.6f} | Change: {psnr_all[hi - lo_all - 1] - initial_psnr:.6f}"
-                      f"\nSuccess Ratio: {flip_count / steps:.6f} | Flip Count: {flip_count}"
-                      f"\nTime taken for this data: {time.time() - t0:.2f} seconds")
-                _print_bins(bin_counts, improved, gains, attempted)
         dt = time.time() - t0
         results.append(dict(file=file_name, initial_psnr=initial_psnr, psnr_after=psnr_all,
                             order=perm[lo_all:hi_all], attempted=attempted, improved=improved,
                             gains=gains, bin_counts=bin_counts, flip_count=flip_count,
                             steps=int(hi_all - lo_all), seconds=dt))
         if verbose:
-            print(f"{file_name}.png Optimization completed.")
-            print(f"Time taken for this data: {dt:.2f} seconds\n")
-            print("Pre-model output range statistics:")
-            _print_bins(bin_counts, improved, gains)
-            print("\n")
+            _emit_sweep_log(file_name, initial_psnr, perm[lo_all:hi_all], psnr_all, cpre, N, bin_counts, t0, log_every)
     if eng is not None:
         eng.close()
     return results

@@ -22,6 +22,7 @@ class OracleEngine:
                                 relative=bool(relative), method=method)
         self.N, self.F, self.G, self.n_env = int(N), int(F), len(wl), int(n_env)
         self.dx, self.z, self.pad, self.relative = float(dx), float(z), int(pad), bool(relative)
+        self.Fg = self.F // self.G
         self.num_pixels = self.F * self.N * self.N
         self.launch_count = 0
         self._state = [np.zeros((F, N, N), np.int8) for _ in range(n_env)]
@@ -154,6 +155,21 @@ class OracleEngine:
             out[...] = psnr
             return out
         return psnr
+
+    def sweep_stats(self, pre_model, edges, env=0, want_map=False):
+        """dbs-1024-1024-24-6464.py:371-395 over every pixel: (attempted, improved, gains, psnr map)."""
+        pm = self.sweep_all(env)
+        pre = np.asarray(pre_model, dtype=np.float32).reshape(self.F, self.N, self.N)
+        att, imp, gains = np.zeros(10, np.int64), np.zeros(10, np.int64), np.zeros(10)
+        p0 = self._prev[env]
+        for idx in np.ndindex(pre.shape):
+            b = O.decile_of(float(pre[idx]))
+            if b >= 0:
+                att[b] += 1
+                if pm[idx] > p0:
+                    imp[b] += 1
+                    gains[b] += pm[idx] - p0
+        return att, imp, gains, (pm if want_map else None)
 
 
 def pinned_stub(shape, dtype):

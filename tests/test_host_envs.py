@@ -222,9 +222,175 @@ def test_dbs_greedy_driver_checkpoint_and_resume(tmp_path):
     assert np.array_equal(full["accepted"].astype(bool), acc_ref)
     assert np.array_equal(full["state"].reshape(F, N, N), st_ref)
     assert full["final_psnr"] == pytest.approx(tr_ref[acc_ref][-1], abs=1e-12)
+    # decile statistics of the kept flips (DBS_1024_24.py:398-416)
+    assert full["improved_bin_counts"].sum() == full["flip_count"] == acc_ref.sum()
+    assert full["psnr_improvements"].sum() == pytest.approx(full["final_psnr"] - full["initial_psnr"], abs=1e-9)
+    d = dbs.decile_index(pre.ravel()[order[acc_ref]])
+    assert np.array_equal(full["improved_bin_counts"], np.bincount(d, minlength=10))
     ck = str(tmp_path / "dbs.npz")
     part = run(checkpoint=ck, segment=300, max_segments=2)[0]
     assert os.path.exists(ck) and not part.get("complete", True)
     rest = run(checkpoint=ck, segment=300)[0]
     assert np.array_equal(rest["accepted"], full["accepted"]) and np.array_equal(rest["state"], full["state"])
     assert rest["final_psnr"] == full["final_psnr"]
+
+
+def test_dbs_sweep_driver_full_sharded_and_partial():
+    """dbs-1024-1024-24-6464.py:194-478: crop, score every flip against the fixed state, decile statistics;
+    the whole-image path, the rank-sharded path and a candidate subset agree with the oracle."""
+    N, F, m = 16, 4, 2
+    n = F * (N - 2 * m) ** 2
+    ld = bh.SyntheticLoader(N, F, 1, seeds=(61,))
+    pre, tgt = bh.synthetic_problem(N, F, 1, 61)
+    cfg = O.HoloConfig(N=N - 2 * m, F=F)
+    cst, ctg, cpre = (pre >= 0.5).astype(np.int8)[:, m:-m, m:-m], tgt[:, m:-m, m:-m], pre[:, m:-m, m:-m]
+
+    def run(**kw):
+        return bh.optimize_with_random_pixel_flips(ld.target_function, ld, 2e-3, 7.56e-6, m, CH=F, wl=O.WL_MONO,
+                                                   max_datasets=0, rng=np.random.default_rng(1), verbose=False, **kw)[0]
+
+    full = run()
+    ref_psnr, p0, att, imp, gain = O.sweep(cfg, cst, ctg, cpre, full["order"])
+    assert full["steps"] == n and full["initial_psnr"] == p0
+    np.testing.assert_allclose(full["psnr_after"], ref_psnr, rtol=0, atol=1e-12)
+    assert np.array_equal(full["attempted"], att) and np.array_equal(full["improved"], imp)
+    np.testing.assert_allclose(full["gains"], gain, rtol=1e-12, atol=1e-15)
+    assert np.array_equal(full["attempted"], full["bin_counts"]) and full["flip_count"] == imp.sum()
+    parts = [run(shard=(r, 3)) for r in range(3)]
+    assert np.array_equal(np.concatenate([p["order"] for p in parts]), full["order"])
+    np.testing.assert_allclose(np.concatenate([p["psnr_after"] for p in parts]), ref_psnr, rtol=0, atol=1e-12)
+    assert np.array_equal(sum(p["attempted"] for p in parts), att)
+    assert np.array_equal(sum(p["improved"] for p in parts), imp)
+    np.testing.assert_allclose(sum(p["gains"] for p in parts), gain, rtol=1e-12, atol=1e-15)
+    some = run(max_candidates=40)                              # a candidate subset goes through eval_flips
+    assert some["steps"] == 40 and np.array_equal(some["order"], full["order"][:40])
+    np.testing.assert_allclose(some["psnr_after"], ref_psnr[:40], rtol=0, atol=1e-12)
+    r40 = O.sweep(cfg, cst, ctg, cpre, full["order"][:40])
+    assert np.array_equal(some["attempted"], r40[2]) and np.array_equal(some["improved"], r40[3])
+
+
+# the reference's own log parsers, restated: log_py/DBS_psnr_log.py:23-30 and log_py/valid_log.py:24-31
+DBS_STEP_RE = (r"Step: (\d+)\s+"
+               r"PSNR Before: [\d.]+\s+\|\s+PSNR After: [\d.]+\s+\|\s+Change: [\d.e+-]+\s+\|\s+Diff: ([\d.e+-]+)\s+"
+               r"Success Ratio: ([\d.e+-]+)\s+\|\s+Flip Count: (\d+).*?"
+               r"Time taken for this data: ([\d.]+) seconds")
+ENV_STEP_RE = (r"Step: (\d+)\s+\| Initial PSNR: ([\d.]+)\s+"
+               r"PSNR After: ([\d.]+)\s+\|\s+Change: ([\d.e+-]+)\s+\|\s+Diff: ([\d.e+-]+)\s+"
+               r"Reward: ([\d.]+)\s+\|\s+Success Ratio: ([\d.e+-]+)\s+\|\s+Flip Count: (\d+).*?"
+               r"Time taken for this data: ([\d.]+) seconds")
+
+
+def test_reference_log_parsers_read_our_stdout(capsys):
+    """the stdout blocks are the reference's wire format.  The regexes of its log_py/ parsers
+    find the step blocks of the greedy DBS (DBS.py:283-289,299-305) and of the env (env.py:206-212)."""
+    import re
+    N, F = 16, 4
+    ld = bh.SyntheticLoader(N, F, 1, seeds=(7,))
+    env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, verbose=True, max_steps=10 ** 6, T_PSNR_DIFF=1e9)
+    res = bh.optimize_with_random_pixel_flips(env, 2e-3, 7.56e-6, max_datasets=0, rng=np.random.default_rng(2),
+                                              verbose=True)[0]
+    out = capsys.readouterr().out
+    assert re.search(r"Starting pixel flip optimization for file \S+\.png with initial PSNR: \d+\.\d{6}", out)
+    blocks = list(re.finditer(DBS_STEP_RE, out, re.DOTALL))
+    assert len(blocks) >= 2                                    # threshold blocks (+0.5 dB each) and the summary
+    steps = [int(m.group(1)) for m in blocks]
+    assert steps == sorted(steps) and steps[-1] == res["steps"]
+    for m in blocks[:-1]:                                      # threshold block: counters at that accepted flip
+        j = int(m.group(1))
+        assert bool(res["accepted"][j - 1]) and int(m.group(4)) == int(res["accepted"][:j].sum())
+        assert float(m.group(2)) == pytest.approx(res["psnr_trace"][j - 1] - res["initial_psnr"], abs=1e-6)
+    assert int(blocks[-1].group(4)) == res["flip_count"]
+    assert re.search(r"Flip Pixel: Channel=\d+, Row=\d+, Col=\d+\nTime taken for this data: ", out)
+    fin = re.search(r"Optimization completed\. Final PSNR improvement: (-?\d+\.\d{6})", out)
+    assert float(fin.group(1)) == pytest.approx(res["psnr_trace"][-1] - res["initial_psnr"], abs=1e-6)   # B-11
+
+    env.reset()
+    capsys.readouterr()
+    rng = np.random.default_rng(0)
+    n_acc = 0
+    for _ in range(300):
+        _, _, term, trunc, _ = env.step(int(rng.integers(0, F * N * N)))
+    out = capsys.readouterr().out
+    blocks = list(re.finditer(ENV_STEP_RE, out, re.DOTALL))
+    assert blocks, out[:500]
+    for m in blocks:
+        assert float(m.group(2)) == pytest.approx(env.initial_psnr, abs=1e-6)
+        assert float(m.group(5)) == pytest.approx(float(m.group(3)) - env.initial_psnr, abs=2e-6)
+    env.close()
+
+
+# log_py/'dbs 평균.py':25-33 -- the range lines of the sweep's progress blocks
+RANGE_RE = (r"Range\s*([\d\.]+-[\d\.]+):\s*Total Pixels\s*=\s*(\d+),\s*"
+            r"Improved Pixels\s*=\s*(\d+),\s*Attempted Pixels\s*=\s*(\d+),\s*"
+            r"Improvement Ratio\s*=\s*([\d\.]+),\s*"
+            r"Improvement Ratio \(in range\)\s*=\s*([\d\.]+),\s*"
+            r"Improvement Ratio \(to total improved\)\s*=\s*([\d\.]+),\s*"
+            r"Total PSNR Improvement\s*=\s*([\d\.]+),\s*"
+            r"Average PSNR Improvement\s*=\s*([\d\.]+)")
+
+
+def test_sweep_stdout_replays_the_reference_blocks(capsys):
+    """dbs-1024-1024-24-6464.py:396-447,462-478: a step block + cumulative range lines every `log_every`
+    candidates (counters include that candidate), then the summary; parsed with the reference's regex."""
+    import re
+    N, F, m, every = 16, 4, 2, 100
+    ld = bh.SyntheticLoader(N, F, 1, seeds=(61,))
+    res = bh.optimize_with_random_pixel_flips(ld.target_function, ld, 2e-3, 7.56e-6, m, CH=F, wl=O.WL_MONO,
+                                              max_datasets=0, rng=np.random.default_rng(1), verbose=True,
+                                              log_every=every)[0]
+    out = capsys.readouterr().out
+    n = res["steps"]
+    better = res["psnr_after"] > res["initial_psnr"]
+    blocks = list(re.finditer(r"Step: (\d+)\nPSNR Before: ([\d.]+) \| PSNR After: ([\d.]+) \| Change: (-?[\d.]+)\n"
+                              r"Success Ratio: ([\d.]+) \| Flip Count: (\d+)\n"
+                              r"Flip Pixel: Channel=(\d+), Row=(\d+), Col=(\d+)\n"
+                              r"Time taken for this data: [\d.]+ seconds(\npre_value: ([\d.]+))?", out))
+    assert [int(b.group(1)) for b in blocks] == list(range(every, n + 1, every)) + [n]
+    side = N - 2 * m
+    for b in blocks:
+        k = int(b.group(1))
+        assert int(b.group(6)) == int(better[:k].sum())                    # counters include candidate k
+        assert float(b.group(3)) == pytest.approx(res["psnr_after"][k - 1], abs=1e-6)
+        a = int(res["order"][k - 1])
+        assert (int(b.group(7)), int(b.group(8)), int(b.group(9))) == (a // side ** 2, (a % side ** 2) // side, a % side)
+    assert all(b.group(10) for b in blocks[:-1]) and blocks[-1].group(10) is None   # pre_value only in progress blocks
+    lines = [re.search(RANGE_RE, l) for l in out.splitlines()]
+    lines = [l for l in lines if l]
+    assert len(lines) == 10 * (n // every)
+    last10 = lines[-10:]
+    k = (n // every) * every
+    assert sum(int(l.group(4)) for l in last10) == k and sum(int(l.group(3)) for l in last10) == int(better[:k].sum())
+    assert [int(l.group(2)) for l in last10] == list(res["bin_counts"])
+    assert re.search(r"\S+\.png Optimization completed\. Final PSNR improvement: -?\d+\.\d{6}\n"
+                     r"Time taken for this data: [\d.]+ seconds\n\nPre-model output range statistics:\nRange 0\.0-0\.1: "
+                     r"Total Pixels = \d+, Improved Pixels = \d+, Improvement Ratio \(in range\)", out)
+
+
+def test_rgb_greedy_stdout_has_the_range_statistics(capsys):
+    """DBS_1024_24.py:372-396,430-469: threshold blocks every 0.1 dB followed by the cumulative range lines
+    (flips kept BEFORE that step), summary without 'Diff', final 'Pre-model output range statistics'."""
+    import re
+    N, F = 16, 6
+    ld = bh.SyntheticLoader(N, F, 3, seeds=(9,))
+    env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, wl=O.WL_RGB, verbose=False)
+    res = bh.optimize_with_random_pixel_flips(env, 2e-3, 7.56e-6, max_datasets=0, rng=np.random.default_rng(3),
+                                              verbose=True)[0]
+    out = capsys.readouterr().out
+    blocks = list(re.finditer(DBS_STEP_RE, out, re.DOTALL))
+    assert blocks and all(res["accepted"][int(b.group(1)) - 1] for b in blocks)
+    first = int(blocks[0].group(1))
+    rng_lines = re.findall(r"Range \d\.\d-\d\.\d: Total Pixels = (\d+), Improved Pixels = (\d+), Improvement Ratio \(in range\)", out)
+    assert len(rng_lines) == 10 * (len(blocks) + 1)            # one table per threshold block + the final one
+    assert sum(int(i) for _, i in rng_lines[:10]) == int(res["accepted"][:first - 1].sum())
+    assert sum(int(i) for _, i in rng_lines[-10:]) == res["flip_count"]
+    assert re.search(r"PSNR Before: [\d.]+ \| PSNR After: [\d.]+ \| Change: -?[\d.]+\nSuccess Ratio", out)   # :432
+    assert "Pre-model output range statistics:" in out
+    env.close()
+
+
+def test_gpu_suite_driver_tests_also_hold_with_the_oracle_engine(golden_dir, tmp_path):
+    """The DBS-driver tests of the GPU suite, executed here with the oracle engine: the driver code they
+    exercise (checkpoints, mirrors, decile statistics, crop) is host logic and must not depend on the GPU."""
+    from tests import test_gpu_parity as G
+    G.test_dbs_greedy_driver_and_resume(golden_dir, tmp_path)
+    G.test_multidiscrete_action_equals_flat_action()
