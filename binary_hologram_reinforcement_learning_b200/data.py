@@ -2,7 +2,9 @@
 
 The reference reads DIV2K PNGs with ``tt.imread``, centre- or random-crops N x N and
 yields ``(target, path)`` through a torch DataLoader with batch size 1, so an env sees
-``target`` of shape (1, C, N, N) in [0, 1] and ``[path]``.  ``ImageFolderLoader`` yields
+``target`` of shape (1, C, N, N) in [0, 1] and the 1-tuple ``(path,)`` that torch's default collate
+makes of a batch of one string (the reference's logs print it as ``('.../0001.png',)`` and its
+log parsers split on that form, log_py/valid_log.py:12, log_py/comp.py:25).  ``ImageFolderLoader`` yields
 exactly that from a directory of images (PIL is the only dependency); any iterable of
 the same shape -- including the reference's own DataLoader -- works as ``trainloader``.
 """
@@ -38,7 +40,7 @@ def crop_to(img: np.ndarray, N: int, rng: Optional[np.random.Generator] = None) 
 
 
 class ImageFolderLoader:
-    """Iterable of ``(target (1, C, N, N) float32, [path])`` over the images of a directory."""
+    """Iterable of ``(target (1, C, N, N) float32, (path,))`` over the images of a directory."""
 
     def __init__(self, target_dir: str, N: int, gray: bool = False, random_crop: bool = False,
                  shuffle: bool = False, seed: Optional[int] = None,
@@ -60,4 +62,4 @@ class ImageFolderLoader:
         for i in order:
             path = self.target_list[i]
             img = crop_to(load_image(path, self.gray), self.N, self.rng if self.random_crop else None)
-            yield img[None], [path]
+            yield img[None], (path,)

@@ -31,7 +31,7 @@ def synthetic_problem(N: int, F: int, G: int, seed: int = 0):
 
 
 class SyntheticLoader:
-    """Iterable of (target (1,G,N,N) float32, [name]) like the reference's DataLoader."""
+    """Iterable of (target (1,G,N,N) float32, (name,)) like the reference's DataLoader."""
 
     def __init__(self, N: int, F: int, G: int, seeds=(0,)):
         self.N, self.F, self.G, self.seeds = N, F, G, tuple(seeds)
@@ -41,7 +41,7 @@ class SyntheticLoader:
         for s in self.seeds:
             pre, tgt = synthetic_problem(self.N, self.F, self.G, s)
             self._pre[tgt[0, 0, :4].tobytes()] = pre
-            yield tgt[None], [f"synthetic_{s:04d}.png"]
+            yield tgt[None], (f"synthetic_{s:04d}.png",)
 
     def target_function(self, target):
         """Stand-in for BinaryNet: returns the seeded pre-model output of this target."""

@@ -202,7 +202,7 @@ def test_two_rank_gloo_stats_gather(tmp_path):
 
 
 def test_image_folder_loader(tmp_path):
-    """Dataset512-shaped loader (DBS.py:172-199): (1, C, N, N) float32 in [0,1] and [path]."""
+    """Dataset512-shaped loader (DBS.py:172-199): (1, C, N, N) float32 in [0,1] and (path,)."""
     PIL = pytest.importorskip("PIL.Image")
     rng = np.random.default_rng(0)
     for i, shape in enumerate([(80, 100, 3), (40, 50, 3)]):
@@ -212,7 +212,7 @@ def test_image_folder_loader(tmp_path):
     assert len(items) == 2 and len(ld) == 2
     t, p = items[0]
     assert t.shape == (1, 3, 64, 64) and t.dtype == np.float32 and 0 <= t.min() and t.max() <= 1
-    assert isinstance(p, list) and p[0].endswith("0000.png")
+    assert isinstance(p, tuple) and p[0].endswith("0000.png")     # torch default_collate of one string
     assert items[1][0].shape == (1, 3, 64, 64)              # smaller image tiled up, then cropped
     full = bh.load_image(p[0])
     assert np.array_equal(t[0], full[:, 8:72, 18:82])       # centre crop

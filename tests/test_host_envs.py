@@ -305,9 +305,11 @@ def test_reference_log_parsers_read_our_stdout(capsys):
     assert float(fin.group(1)) == pytest.approx(res["psnr_trace"][-1] - res["initial_psnr"], abs=1e-6)   # B-11
 
     env.reset()
-    capsys.readouterr()
+    head = capsys.readouterr().out
+    # log_py/valid_log.py:12 / DBS_psnr_log.py:12 split episodes on this line; comp.py:25 takes the file name
+    assert re.search(r"\[Episode Start\] Currently using dataset file: \((.+?)\), Episode count: \d+", head)
+    assert re.search(r"Currently using dataset file:\s*\('.*?([^/]+\.png)',\)", head).group(1) == "synthetic_0007.png"
     rng = np.random.default_rng(0)
-    n_acc = 0
     for _ in range(300):
         _, _, term, trunc, _ = env.step(int(rng.integers(0, F * N * N)))
     out = capsys.readouterr().out
