@@ -43,12 +43,15 @@ def goal_bonus(success_ratio: float, const: float) -> float:
             + 2800 * success_ratio + const)
 
 
-def importance_reward_table(psnr_changes: Sequence[float]) -> np.ndarray:
+def importance_reward_table(psnr_changes: Sequence[float], verbose: bool = False) -> np.ndarray:
     """env_group.py:121-141: rank of each candidate -> degree-5 polynomial reward."""
     n = len(psnr_changes)
     step_poly = np.array([10000, 9000, 8000, 5000, 2500, 1])
     rewards_poly = np.array([-0.5, -0.48, -0.45, -0.35, 0, 1])
     poly = np.poly1d(np.polyfit(step_poly, rewards_poly, len(step_poly) - 1))
+    if verbose:                                           # env_group.py:128-129
+        print("Polynomial Reward Function Equation:")
+        print(poly)
     order = np.argsort(psnr_changes)
     x_val = 10000 - (10000 - 1) * (np.arange(n) / (n - 1))
     ranks = np.zeros(n)
@@ -278,7 +281,7 @@ class BinaryHologramEnv(spaces.Env):
             psnr[inside] = self._engine.eval_flips(sim_actions[inside], env=self._e)
         changes = psnr - self.initial_psnr
         positive = float(np.sum(changes[changes > 0]))
-        return list(changes), importance_reward_table(changes), positive
+        return list(changes), importance_reward_table(changes, self.verbose), positive
 
     def _map_actions(self, actions: np.ndarray):
         """Full-grid action -> engine (cropped-grid) action; inside = within the window."""

@@ -134,13 +134,20 @@ def test_vec_env_goal_termination_fast_path():
     vec.close()
 
 
-def test_group_env_and_vec_group_rewards_match_oracle():
+def test_group_env_and_vec_group_rewards_match_oracle(capsys):
     """env_group.py:90-143,254-255: rank table at reset, nearest-value reward; vec fast path + clones."""
     N, F, S = 16, 4, 60
     ld = bh.SyntheticLoader(N, F, 1, seeds=(31,))
-    env = bh.BinaryHologramEnvGroup(ld.target_function, ld, IPS=N, CH=F, verbose=False, num_samples=S,
+    env = bh.BinaryHologramEnvGroup(ld.target_function, ld, IPS=N, CH=F, verbose=True, num_samples=S,
                                     rng=np.random.default_rng(9))
     env.reset()
+    head = capsys.readouterr().out                         # env_group.py:128-129,194-199 / log_py/'Dynamic Threshold.py':16-20
+    assert "Polynomial Reward Function Equation:" in head and "Time taken for psnr_change_list:" in head
+    import re
+    assert float(re.search(r"\[Dynamic Threshold\] T_PSNR_DIFF set to: ([0-9.]+)", head).group(1)) == pytest.approx(
+        env.T_PSNR_DIFF, abs=1e-6)
+    assert re.search(r"\[Episode Start\].*dataset file: \('(?:.*/)?(.*?)',\)", head).group(1) == "synthetic_0031.png"
+    env.verbose = False
     pre, tgt = bh.synthetic_problem(N, F, 1, 31)
     ref = O.OracleEnv(O.HoloConfig(N=N, F=F), reward_mode="group")
     ref.reset(pre, tgt, rng=np.random.default_rng(9), num_samples=S)
