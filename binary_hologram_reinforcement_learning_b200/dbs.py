@@ -180,8 +180,10 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
         bin_counts = bin_population(pre)
         if save_dir:                                      # DBS_1024_24.py:282-287
             os.makedirs(save_dir, exist_ok=True)
-            np.save(os.path.join(save_dir, f"episode_{file_name}png_rgb_before.npy"),
-                    eng.recon(e)[None])
+            before_path = os.path.join(save_dir, f"episode_{file_name}png_rgb_before.npy")
+            np.save(before_path, eng.recon(e)[None])
+            if verbose:
+                print(f"RGB data saved to {before_path}")
         if verbose:
             print(f"Starting pixel flip optimization for file {file_name}.png with initial PSNR: {initial_psnr:.6f}")
         n = eng.num_pixels
@@ -259,9 +261,6 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
                    seconds=dt, bin_counts=bin_counts + improved, improved_bin_counts=improved,
                    psnr_improvements=gains, state=new_state)
         results.append(out)
-        if save_dir:                                      # DBS_1024_24.py:446-451 (+ the hologram itself)
-            np.save(os.path.join(save_dir, f"episode_{file_name}_rgb_after.npy"), eng.recon(e)[None])
-            np.save(os.path.join(save_dir, f"episode_{file_name}_state_after.npy"), new_state)
         if verbose:
             # the reference's summary shows the LAST EVALUATED candidate (possibly rejected) next to the stale
             # change / ratio of the last threshold block (DBS.py:297-305, appendix B-11)
@@ -280,8 +279,15 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
             print(f"Time taken for this data: {dt:.2f} seconds\n")
             if env.G > 1:
                 print("Pre-model output range statistics:")
-                _print_bins(out["bin_counts"], improved, gains)
-                print("\n")
+        if save_dir:                                      # DBS_1024_24.py:441-451 (+ the hologram itself)
+            after_path = os.path.join(save_dir, f"episode_{file_name}_rgb_after.npy")
+            np.save(after_path, eng.recon(e)[None])
+            np.save(os.path.join(save_dir, f"episode_{file_name}_state_after.npy"), new_state)
+            if verbose:
+                print(f"RGB data saved to {after_path}")
+        if verbose and env.G > 1:                         # DBS_1024_24.py:453-469
+            _print_bins(out["bin_counts"], improved, gains)
+            print("\n")
     return results
 
 

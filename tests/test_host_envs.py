@@ -375,7 +375,7 @@ def test_sweep_stdout_replays_the_reference_blocks(capsys):
                      r"Total Pixels = \d+, Improved Pixels = \d+, Improvement Ratio \(in range\)", out)
 
 
-def test_rgb_greedy_stdout_has_the_range_statistics(capsys):
+def test_rgb_greedy_stdout_has_the_range_statistics(capsys, tmp_path):
     """DBS_1024_24.py:372-396,430-469: threshold blocks every 0.1 dB followed by the cumulative range lines
     (flips kept BEFORE that step), summary without 'Diff', final 'Pre-model output range statistics'."""
     import re
@@ -383,8 +383,15 @@ def test_rgb_greedy_stdout_has_the_range_statistics(capsys):
     ld = bh.SyntheticLoader(N, F, 3, seeds=(9,))
     env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, wl=O.WL_RGB, verbose=False)
     res = bh.optimize_with_random_pixel_flips(env, 2e-3, 7.56e-6, max_datasets=0, rng=np.random.default_rng(3),
-                                              verbose=True)[0]
+                                              verbose=True, save_dir=str(tmp_path))[0]
     out = capsys.readouterr().out
+    # DBS_1024_24.py:282-287,441-451: before / after reconstructions; log_py/'log dbs.py':16 splits on this line
+    assert out.count("RGB data saved to ") == 2
+    before = np.load(tmp_path / "episode_synthetic_0009png_rgb_before.npy")
+    after = np.load(tmp_path / "episode_synthetic_0009_rgb_after.npy")
+    assert before.shape == after.shape == (1, 3, N, N) and not np.array_equal(before, after)
+    assert np.array_equal(np.load(tmp_path / "episode_synthetic_0009_state_after.npy"), res["state"])
+    assert out.index("Pre-model output range statistics:") < out.rindex("RGB data saved to ") < out.rindex("Range 0.0-0.1")
     blocks = list(re.finditer(DBS_STEP_RE, out, re.DOTALL))
     assert blocks and all(res["accepted"][int(b.group(1)) - 1] for b in blocks)
     first = int(blocks[0].group(1))
