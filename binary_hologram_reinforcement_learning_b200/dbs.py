@@ -147,7 +147,8 @@ def bin_population(pre_model: np.ndarray) -> np.ndarray:
 # ---------------------------------------------------------------------------
 # greedy DBS
 # ---------------------------------------------------------------------------
-def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_datasets=None,
+def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, crop_margin: Optional[int] = None, *,
+                   psnr_diff_threshold: Optional[float] = None, max_datasets=None,
                    order: Optional[np.ndarray] = None, rng=None, k_spec: int = 0,
                    resync_every: int = 1024, segment: int = 1 << 20, verbose: bool = True,
                    max_candidates: Optional[int] = None, save_dir: Optional[str] = None,
@@ -160,6 +161,9 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
     nothing but the before/after reconstructions (DBS_1024_24.py:282-287,446-451).
     ``max_segments`` bounds the work of one call (the result then has ``complete = False``
     and a later call with the same checkpoint continues).
+    ``crop_margin`` (DBS_1024_24-128.py:187): optimise the centre window only; passed to
+    ``env.reset`` (env_1024_24_128.py:100).  ``psnr_diff_threshold`` (DBS_01.py:204,320-325,
+    DBS_ratio_0.5.py:204): leave an image as soon as a candidate lifts the PSNR by that much.
     """
     results = []
     db_num = 0
@@ -167,7 +171,7 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
         max_datasets = 800 if env.G == 1 else 10          # DBS.py:205, DBS_1024_24.py:208
     while db_num <= max_datasets:                         # DBS.py:208 (runs max+1 images)
         try:
-            obs, info = env.reset(z=z, pixel_pitch=pixel_pitch)
+            obs, info = env.reset(z=z, pixel_pitch=pixel_pitch, crop_margin=crop_margin)
             db_num += 1
         except Exception as e:                            # DBS.py:212-214
             print(f"An error occurred during reset: {e}")
@@ -211,13 +215,25 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
                 if verbose:
                     print(f"Resuming {file_name}.png from candidate {start} (PSNR {eng.metrics(e)[0]:.6f})")
         done_upto = start
-        for seg_i, lo in enumerate(range(start, perm.shape[0], segment)):
+        stopped = False
+        seg_len = segment if psnr_diff_threshold is None else min(segment, 4096)
+        for seg_i, lo in enumerate(range(start, perm.shape[0], seg_len)):
             if max_segments is not None and seg_i >= max_segments:
                 break
-            hi = min(perm.shape[0], lo + segment)
-            done_upto = hi
+            hi = min(perm.shape[0], lo + seg_len)
+            state_before = eng.state(e) if psnr_diff_threshold is not None else None
             acc, tr, nacc, psnr_now = eng.dbs_run(perm[lo:hi], env=e, k_spec=k_spec,
                                                   resync_every=resync_every, trace=True)
+            if psnr_diff_threshold is not None:           # DBS_01.py:320-325
+                reach = np.flatnonzero(tr - initial_psnr >= psnr_diff_threshold)
+                if reach.size:
+                    k = int(reach[0]) + 1
+                    if k < hi - lo:                       # later flips were applied: replay the prefix only
+                        eng.load_state(e, state_before)
+                        acc, tr, nacc, psnr_now = eng.dbs_run(perm[lo:lo + k], env=e, k_spec=k_spec,
+                                                              resync_every=resync_every, trace=True)
+                    hi, stopped = lo + k, True
+            done_upto = hi
             accepted[lo:hi], trace[lo:hi] = acc, tr
             flip_count += nacc
             if verbose and nacc:
@@ -241,6 +257,10 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
                             _print_bins(bin_counts + imp_j, imp_j, gn_j)
                             print("\n")
                 previous = trace[hit[-1]]
+            if stopped:
+                if verbose:
+                    print(f"PSNR diff threshold {psnr_diff_threshold} reached at step {hi}. Moving to next dataset.")
+                break
             if checkpoint:
                 tmp = checkpoint + ".tmp.npz"
                 np.savez_compressed(tmp, fname=np.array(file_name), order=perm, cursor=np.array(hi),
@@ -256,7 +276,7 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, *, max_d
         steps = int(done_upto)
         accepted, trace = accepted[:steps], trace[:steps]
         dt = time.time() - t0
-        out = dict(complete=steps == perm.shape[0], file=file_name, initial_psnr=initial_psnr, final_psnr=final_psnr, steps=steps,
+        out = dict(complete=steps == perm.shape[0], stopped_on_threshold=stopped, file=file_name, initial_psnr=initial_psnr, final_psnr=final_psnr, steps=steps,
                    flip_count=int(flip_count), accepted=accepted, psnr_trace=trace, order=perm,
                    seconds=dt, bin_counts=bin_counts + improved, improved_bin_counts=improved,
                    psnr_improvements=gains, state=new_state)

@@ -170,7 +170,17 @@ class BinaryHologramEnv(spaces.Env):
     # -- env.py:90-152 ---------------------------------------------------
     def reset(self, seed=None, options=None, z=2e-3, pixel_pitch=7.56e-6, crop_margin=None):
         if crop_margin is not None and int(crop_margin) != self.crop_margin:
-            raise ValueError("crop_margin is fixed at construction (it sets the FFT side)")
+            # env_1024_24_128.py:100 takes the margin at reset; a new margin is a new FFT side, i.e. a new engine
+            if not self._own_engine:
+                raise ValueError("crop_margin of a shared engine is fixed at construction (it sets the FFT side)")
+            if self._engine is not None:
+                self._engine.close()
+                self._engine = None
+            self.crop_margin = int(crop_margin)
+            self.Nsim = self.IPS - 2 * self.crop_margin
+            self._recon_buf = None
+            self.observation_space.spaces["recon_image"] = spaces.Box(
+                low=0, high=1, shape=(1, self.G, self.Nsim, self.Nsim), dtype=np.float32)
         if seed is not None:
             self.rng = np.random.default_rng(seed)
         self._ensure_engine(float(z), float(pixel_pitch))

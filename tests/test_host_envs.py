@@ -410,3 +410,59 @@ def test_gpu_suite_driver_tests_also_hold_with_the_oracle_engine(golden_dir, tmp
     from tests import test_gpu_parity as G
     G.test_dbs_greedy_driver_and_resume(golden_dir, tmp_path)
     G.test_multidiscrete_action_equals_flat_action()
+
+
+def test_dbs_psnr_diff_threshold_stops_at_the_first_candidate_that_reaches_it(capsys):
+    """DBS_01.py:204,320-325 / DBS_ratio_0.5.py:204: leave the image once a candidate lifts the PSNR by the
+    threshold; state and decisions are those of the sequential loop cut at that candidate."""
+    N, F, thr = 16, 4, 0.3
+    ld = bh.SyntheticLoader(N, F, 1, seeds=(21,))
+    pre, tgt = bh.synthetic_problem(N, F, 1, 21)
+    cfg = O.HoloConfig(N=N, F=F)
+    order = np.random.default_rng(6).permutation(F * N * N)
+    st0 = (pre >= 0.5).astype(np.int8)
+    _, acc_ref, tr_ref = O.dbs_greedy(cfg, st0, tgt, order)
+    p0 = O.score(cfg, O.reconstruct(cfg, st0), tgt)[0]
+    stop = int(np.flatnonzero(tr_ref - p0 >= thr)[0]) + 1
+    assert 1 < stop < order.size
+    st_ref, _, _ = O.dbs_greedy(cfg, st0, tgt, order[:stop])
+    env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, verbose=False)
+    res = bh.optimize_with_random_pixel_flips(env, 2e-3, 7.56e-6, max_datasets=0, rng=np.random.default_rng(6),
+                                              verbose=True, psnr_diff_threshold=thr)[0]
+    out = capsys.readouterr().out
+    assert res["stopped_on_threshold"] and not res["complete"] and res["steps"] == stop
+    assert np.array_equal(res["accepted"].astype(bool), acc_ref[:stop]) and res["accepted"][-1]
+    assert np.array_equal(res["state"].reshape(F, N, N), st_ref) and np.array_equal(env.state[0], st_ref)
+    assert res["final_psnr"] - res["initial_psnr"] >= thr
+    assert f"PSNR diff threshold {thr} reached at step {stop}. Moving to next dataset." in out
+    env.close()
+
+
+def test_crop_margin_as_a_reset_argument_and_as_dbs_argument():
+    """env_1024_24_128.py:100 takes crop_margin at reset, DBS_1024_24-128.py:187 as 4th argument of the DBS."""
+    N, F, m = 24, 4, 4
+    ld = bh.SyntheticLoader(N, F, 1, seeds=(5,))
+    env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, verbose=False, T_PSNR_DIFF=1e9)
+    obs, _ = env.reset()
+    assert env.engine.N == N and obs["recon_image"].shape == (1, 1, N, N)
+    first = env.engine
+    obs, _ = env.reset(crop_margin=m)                          # new FFT side -> new engine
+    assert first.closed and env.engine.N == N - 2 * m and obs["recon_image"].shape == (1, 1, N - 2 * m, N - 2 * m)
+    assert env.observation_space["recon_image"].shape == (1, 1, N - 2 * m, N - 2 * m)
+    pre, tgt = bh.synthetic_problem(N, F, 1, 5)
+    cfg = O.HoloConfig(N=N - 2 * m, F=F)
+    cst, ctg = (pre >= 0.5).astype(np.int8)[:, m:-m, m:-m], tgt[:, m:-m, m:-m]
+    assert env.initial_psnr == O.score(cfg, O.reconstruct(cfg, cst), ctg)[0]
+    env.close()
+    env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, verbose=False)
+    res = bh.optimize_with_random_pixel_flips(env, 2e-3, 7.56e-6, m, max_datasets=0, rng=np.random.default_rng(2),
+                                              max_candidates=150, verbose=False)[0]
+    st_ref, acc_ref, _ = O.dbs_greedy(cfg, cst, ctg, res["order"])
+    assert res["order"].max() < F * (N - 2 * m) ** 2 and np.array_equal(res["accepted"].astype(bool), acc_ref)
+    assert np.array_equal(env.state[0][:, m:-m, m:-m], st_ref)          # the window of the full-size mirror
+    assert np.array_equal(env.state[0][:, :m], (pre >= 0.5).astype(np.int8)[:, :m])    # margin untouched
+    shared = OracleEngine(N, F, O.WL_MONO, n_env=2)
+    env2 = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, verbose=False, engine=shared, env_index=1)
+    with pytest.raises(ValueError):
+        env2.reset(crop_margin=m)
+    env.close()
