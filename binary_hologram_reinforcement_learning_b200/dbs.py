@@ -148,7 +148,8 @@ def bin_population(pre_model: np.ndarray) -> np.ndarray:
 # greedy DBS
 # ---------------------------------------------------------------------------
 def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, crop_margin: Optional[int] = None, *,
-                   psnr_diff_threshold: Optional[float] = None, max_datasets=None,
+                   psnr_diff_threshold: Optional[float] = None, range_stats: Optional[bool] = None,
+                   max_datasets=None,
                    order: Optional[np.ndarray] = None, rng=None, k_spec: int = 0,
                    resync_every: int = 1024, segment: int = 1 << 20, verbose: bool = True,
                    max_candidates: Optional[int] = None, save_dir: Optional[str] = None,
@@ -164,9 +165,12 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, crop_mar
     ``crop_margin`` (DBS_1024_24-128.py:187): optimise the centre window only; passed to
     ``env.reset`` (env_1024_24_128.py:100).  ``psnr_diff_threshold`` (DBS_01.py:204,320-325,
     DBS_ratio_0.5.py:204): leave an image as soon as a candidate lifts the PSNR by that much.
+    ``range_stats``: print the per-decile tables of the kept flips (DBS_ratio.py, DBS_1024_24.py:379-396,
+    453-469); default: for colour holograms only, as in the reference's scripts.
     """
     results = []
     db_num = 0
+    stats = (env.G > 1) if range_stats is None else bool(range_stats)
     if max_datasets is None:
         max_datasets = 800 if env.G == 1 else 10          # DBS.py:205, DBS_1024_24.py:208
     while db_num <= max_datasets:                         # DBS.py:208 (runs max+1 images)
@@ -252,7 +256,7 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, crop_mar
                               f"\nSuccess Ratio: {last_ratio:.6f} | Flip Count: {n_acc}"
                               f"\nFlip Pixel: Channel={ch}, Row={row}, Col={col}"
                               f"\nTime taken for this data: {time.time() - t0:.2f} seconds")
-                        if env.G > 1:                                # DBS_1024_24.py:379-396 (flips before this one)
+                        if stats:                                    # DBS_1024_24.py:379-396 (flips before this one)
                             imp_j, gn_j = _accepted_bins(pre, perm, accepted[:j], trace, initial_psnr)
                             _print_bins(bin_counts + imp_j, imp_j, gn_j)
                             print("\n")
@@ -297,7 +301,7 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, crop_mar
                   f"\nTime taken for this data: {dt:.2f} seconds")
             print(f"{file_name}.png Optimization completed. Final PSNR improvement: {last - initial_psnr:.6f}")
             print(f"Time taken for this data: {dt:.2f} seconds\n")
-            if env.G > 1:
+            if stats:
                 print("Pre-model output range statistics:")
         if save_dir:                                      # DBS_1024_24.py:441-451 (+ the hologram itself)
             after_path = os.path.join(save_dir, f"episode_{file_name}_rgb_after.npy")
@@ -305,7 +309,7 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, crop_mar
             np.save(os.path.join(save_dir, f"episode_{file_name}_state_after.npy"), new_state)
             if verbose:
                 print(f"RGB data saved to {after_path}")
-        if verbose and env.G > 1:                         # DBS_1024_24.py:453-469
+        if verbose and stats:                             # DBS_1024_24.py:453-469
             _print_bins(out["bin_counts"], improved, gains)
             print("\n")
     return results
