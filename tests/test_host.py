@@ -182,6 +182,25 @@ assert list(h) == [3, 6, 9]
 assert dist.max_over_ranks(float(rank)) == 1.0
 lo, hi = dist.shard_range(10, rank, world)
 assert (lo, hi) == ((0, 5) if rank == 0 else (5, 10))
+# the sharded score-and-revert sweep of SURVEY 8e, with the oracle-backed engine stand-in: every rank scores
+# its contiguous slice of the globally defined order, the decile histograms are all-reduced, and the result
+# equals the unsharded sweep
+import binary_hologram_reinforcement_learning_b200 as bh
+from binary_hologram_reinforcement_learning_b200 import dbs
+from tests.oracle_engine import OracleEngine
+dbs.HoloEngine = OracleEngine
+N, F, m = 16, 4, 2
+def sweep(shard):
+    ld = bh.SyntheticLoader(N, F, 1, seeds=(61,))
+    return bh.dbs_sweep(ld.target_function, ld, 2e-3, 7.56e-6, m, CH=F, wl=bh.WL_MONO, max_datasets=0,
+                        rng=np.random.default_rng(1), verbose=False, shard=shard)[0]
+mine, full = sweep((rank, world)), sweep(None)
+att, imp, gn = dist.reduce_histograms(mine["attempted"], mine["improved"], mine["gains"])
+assert np.array_equal(att, full["attempted"]) and np.array_equal(imp, full["improved"])
+assert np.allclose(gn, full["gains"], rtol=1e-12, atol=1e-15)
+lo, hi = dist.shard_range(full["order"].size, rank, world)
+assert np.array_equal(mine["order"], full["order"][lo:hi])
+assert np.array_equal(mine["psnr_after"], full["psnr_after"][lo:hi])
 dist.barrier()
 print("GLOO_OK", rank)
 """
