@@ -593,6 +593,27 @@ def test_large_golden_dbs64_exhaustive(golden_dir):
     eng.close()
 
 
+@pytest.mark.skipif(not os.environ.get("BHOLO_LONG_TESTS"), reason="long run: set BHOLO_LONG_TESTS=1")
+def test_large_golden_dbs256_first_50k(golden_dir):
+    """first 50 000 candidates of the greedy DBS of a 256^2 x 8 stack (DBS.py:243-294).
+    Opt-in (BHOLO_LONG_TESTS=1): generated after the last GPU session of round 1, not yet run on a B200."""
+    g = _need(golden_dir, "large_dbs256_50k")
+    N, F, seed = 256, 8, 61
+    pre, tgt, st = _problem(N, F, O.WL_MONO, seed)
+    eng = _engine(N, F, O.WL_MONO)
+    eng.set_target(0, tgt)
+    eng.load_state(0, st)
+    acc, _, nacc, fin = eng.dbs_run(g["order"], resync_every=1024)
+    ref = np.unpackbits(g["accepted"])[:int(g["n"])]
+    mism = int(np.count_nonzero(acc != ref))
+    assert mism <= 0.002 * ref.size, mism                   # near-tie divergences only
+    assert abs(fin - float(g["final_psnr"])) < 5e-3
+    assert abs(nacc - int(g["n_accepted"])) <= 0.002 * ref.size
+    if mism == 0:
+        assert np.array_equal(np.packbits(eng.state(0).astype(np.uint8)), g["final_state"])
+    eng.close()
+
+
 def test_large_golden_group256(golden_dir):
     """env_group.py:90-143 at 256^2 x 8 with the reference's 10 000 candidates."""
     g = _need(golden_dir, "large_group256")
