@@ -51,6 +51,8 @@ class HologramVecEnv:
         self._ptrs = (self._eids.ctypes.data, self._actions.ctypes.data, self._res.ctypes.data)
         self._psnr_after = self._res["psnr_after"]
         self._no_event = bytes(self.num_envs)
+        self._resync_every = int(resync_every)
+        self._resync_wait = 0                  # steps until a re-propagation can be due (see _step_fast)
         self._sim = np.empty(self.num_envs, dtype=np.int64)
         # episode statistics of finished episodes: reward, steps, flips, psnr0, psnr1
         self.episode_stats: List[np.ndarray] = []
@@ -113,6 +115,7 @@ class HologramVecEnv:
         env.state, env.state_record = self._state[i], self._record[i]
         self._steps[i] = env.steps
         self._flips[i] = env.flip_count
+        self._resync_wait = 0
         self._prev[i] = env.previous_psnr
         self._init[i] = env.initial_psnr
         self._sustained[i] = env.psnr_sustained_steps
@@ -204,11 +207,16 @@ class HologramVecEnv:
         else:
             rewards = self._rewards.copy()                           # env.py:188
         infos = [{} for _ in range(E)]
-        if envs[0].resync_every > 0:
-            acc = res["accept"] != 0
-            if acc.any():
-                for i in np.flatnonzero(acc & (self._flips % envs[0].resync_every == 0)):
+        if self._resync_every > 0:
+            # an env is re-propagated when its kept-flip count reaches a multiple of resync_every.  Counts
+            # grow by at most one per step, so nothing can be due before `_resync_wait` more steps:
+            # the (numpy) test runs only then, not on every step
+            self._resync_wait -= 1
+            if self._resync_wait <= 0:
+                due = (res["accept"] != 0) & (self._flips % self._resync_every == 0)
+                for i in np.flatnonzero(due):
                     self.engine.resync(int(i))
+                self._resync_wait = int((self._resync_every - self._flips % self._resync_every).min())
         if self._event.tobytes() == self._no_event:
             self._ep_reward += rewards
             return self._pack(self._obs_cache), rewards, self._no_done.copy(), infos

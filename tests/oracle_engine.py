@@ -48,11 +48,14 @@ class OracleEngine:
 
     def load_state(self, env, state):
         self._state[env] = np.asarray(state, dtype=np.int8).reshape(self.F, self.N, self.N).copy()
-        self.resync(env)
+        self._repropagate(env)
 
-    def resync(self, env):
+    def _repropagate(self, env):
         self._means[env] = O.reconstruct(self.cfg, self._state[env])
         self._prev[env] = O.score(self.cfg, self._means[env], self._target[env])[0]
+
+    def resync(self, env):
+        self._repropagate(env)
 
     def clone_env(self, src, dst):
         self._state[dst] = self._state[src].copy()
@@ -146,7 +149,7 @@ class OracleEngine:
         o = np.asarray(order, dtype=np.int64).ravel()
         st, acc, tr = O.dbs_greedy(self.cfg, self._state[env], self._target[env], o)
         self._state[env] = st.astype(np.int8)
-        self.resync(env)
+        self._repropagate(env)
         return acc.astype(np.uint8), (tr if trace else None), int(acc.sum()), self._prev[env]
 
     def sweep_all(self, env=0, out=None):

@@ -466,3 +466,35 @@ def test_crop_margin_as_a_reset_argument_and_as_dbs_argument():
     with pytest.raises(ValueError):
         env2.reset(crop_margin=m)
     env.close()
+
+
+@pytest.mark.parametrize("R", [1, 3, 7])
+def test_vec_env_repropagates_exactly_when_a_flip_count_reaches_a_multiple(R):
+    """resync_every: the incremental fields are re-propagated every R kept flips of an env.  The fast path
+    only looks at the counters when a multiple can have been reached; the calls must be exactly the due ones."""
+    N, F, E = 16, 4, 3
+    loaders = [bh.SyntheticLoader(N, F, 1, seeds=(500 + i,)) for i in range(E)]
+    vec = bh.HologramVecEnv(E, _loader_fn(loaders), loaders, max_steps=25, T_PSNR_DIFF=1e9, IPS=N, CH=F,
+                            resync_every=R)
+    assert vec._fast
+    vec.reset()
+    calls, expected = [], []
+    real_resync = vec.engine.resync
+    step_no = [0]
+
+    def spy(env):
+        calls.append((step_no[0], int(env)))
+        real_resync(env)
+    vec.engine.resync = spy
+    rng = np.random.default_rng(12)
+    for step in range(90):                                  # crosses several auto-resets (max_steps = 25)
+        step_no[0] = step
+        flips_before = vec._flips.copy()
+        vec.step(rng.integers(0, F * N * N, size=E))
+        acc = vec._res["accept"] != 0
+        for i in range(E):
+            if acc[i] and (flips_before[i] + 1) % R == 0:
+                expected.append((step, i))
+    # auto-reset calls env.reset -> load_state, not resync, so the spy only sees the periodic ones
+    assert calls == expected and len(calls) > 0
+    vec.close()
