@@ -259,6 +259,13 @@ class HoloEngine:
             self._check(rc, "bh_vec_step")
         return out
 
+    def step_batch_ptrs(self, n: int, ptrs, rule: int):
+        """``step_batch`` on cached addresses ``(env_ids, actions, results)`` of persistent host arrays
+        (``ndarray.ctypes`` costs more than a microsecond per use; this is the per-step path of an env)."""
+        rc = self.lib.bh_step_batch(self._h, n, ptrs[0], ptrs[1], rule, ptrs[2])
+        if rc != 0:
+            self._check(rc, "bh_step_batch")
+
     def vec_step_ptrs(self, n: int, ptrs, rule: int, book: "VecBook"):
         """``vec_step`` on cached addresses ``(env_ids, actions, results)`` of persistent host arrays."""
         rc = self.lib.bh_vec_step(self._h, n, ptrs[0], ptrs[1], rule, ptrs[2], self._book_ref(book))

@@ -136,6 +136,7 @@ class BinaryHologramEnv(spaces.Env):
         self._res = np.empty(1, dtype=RESULT_DTYPE)
         self._act = np.empty(1, dtype=np.int64)
         self._eid = np.array([self._e], dtype=np.int32)
+        self._ptrs = (self._eid.ctypes.data, self._act.ctypes.data, self._res.ctypes.data)
         self._recon_buf = None                            # pinned, allocated with the engine
 
     # ------------------------------------------------------------------
@@ -314,15 +315,17 @@ class BinaryHologramEnv(spaces.Env):
         action = int(action)
         if not 0 <= action < self.num_pixels:
             raise ValueError(f"action {action} outside Discrete({self.num_pixels})")
-        sim_action, inside = self._map_actions(np.array([action]))
-        if inside[0]:
-            self._act[0] = sim_action[0]
-            self._engine.step_batch(self._act, self._eid, RULE_ENV, out=self._res)
-            res = self._res[0]
-            return self._finish_step(action, float(res["psnr_after"]), bool(res["accept"]),
-                                     int(sim_action[0]))
-        # a pixel outside the simulated window leaves the reconstruction unchanged
-        return self._finish_step(action, self.previous_psnr, True, -1)
+        sim_action = action
+        if self.crop_margin:
+            sim, inside = self._map_actions(np.array([action]))
+            if not inside[0]:
+                # a pixel outside the simulated window leaves the reconstruction unchanged
+                return self._finish_step(action, self.previous_psnr, True, -1)
+            sim_action = int(sim[0])
+        self._act[0] = sim_action
+        self._engine.step_batch_ptrs(1, self._ptrs, RULE_ENV)
+        res = self._res[0]
+        return self._finish_step(action, float(res["psnr_after"]), bool(res["accept"]), sim_action)
 
     def _finish_step(self, action: int, psnr_after: float, accepted: bool, sim_action: int):
         IPS = self.IPS

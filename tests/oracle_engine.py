@@ -117,12 +117,20 @@ class OracleEngine:
         self.launch_count += 2
         return res
 
-    def vec_step_ptrs(self, n, ptrs, rule, book):
-        """Same contract as HoloEngine.vec_step_ptrs; the bookkeeping runs in the real C library."""
+    def _views(self, n, ptrs):
         ids = np.ctypeslib.as_array((C.c_int32 * n).from_address(ptrs[0]))
         acts = np.ctypeslib.as_array((C.c_int64 * n).from_address(ptrs[1]))
         res = np.frombuffer((C.c_char * (n * real.RESULT_DTYPE.itemsize)).from_address(ptrs[2]),
                             dtype=real.RESULT_DTYPE)
+        return ids, acts, res
+
+    def step_batch_ptrs(self, n, ptrs, rule):
+        ids, acts, res = self._views(n, ptrs)
+        self.step_batch(acts, ids, rule, out=res)
+
+    def vec_step_ptrs(self, n, ptrs, rule, book):
+        """Same contract as HoloEngine.vec_step_ptrs; the bookkeeping runs in the real C library."""
+        ids, acts, res = self._views(n, ptrs)
         self.step_batch(acts, ids, rule, out=res)
         rc = real.load_library().bh_vec_book_update(n, ptrs[0], ptrs[1], ptrs[2], C.addressof(book))
         assert rc == 0

@@ -498,3 +498,11 @@ def test_vec_env_repropagates_exactly_when_a_flip_count_reaches_a_multiple(R):
     # auto-reset calls env.reset -> load_state, not resync, so the spy only sees the periodic ones
     assert calls == expected and len(calls) > 0
     vec.close()
+
+
+@pytest.mark.parametrize("name", ["mono64", "rgb64", "mono32_pad2", "mono64_abs"])
+def test_golden_env_trajectories_through_the_env_with_the_oracle_engine(name, golden_dir):
+    """The golden env trajectories (tests/golden/*.npz) replayed through BinaryHologramEnv.step on the CPU:
+    same test body as the GPU suite, scoring by the oracle engine -- pins the env's host logic to the fixtures."""
+    from tests import test_gpu_parity as G
+    G.test_golden_env_trajectory(name, golden_dir)
