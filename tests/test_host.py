@@ -209,10 +209,14 @@ print("GLOO_OK", rank)
 def test_two_rank_gloo_stats_gather(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER)
+    import socket
+    with socket.socket() as sk:                       # a free rendezvous port
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     procs = []
     for r in range(2):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r),
-                   MASTER_ADDR="127.0.0.1", MASTER_PORT="29641")
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=240)[0] for p in procs]
