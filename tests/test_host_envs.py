@@ -506,3 +506,26 @@ def test_golden_env_trajectories_through_the_env_with_the_oracle_engine(name, go
     same test body as the GPU suite, scoring by the oracle engine -- pins the env's host logic to the fixtures."""
     from tests import test_gpu_parity as G
     G.test_golden_env_trajectory(name, golden_dir)
+
+
+def test_dataset_iterator_restart_and_image_count_quirks(capsys):
+    """Appendix B-8: the env restarts its loader silently (one INFO line) at exhaustion, env.py:96-102.
+    B-9: `while db_num <= max_datasets` processes max_datasets + 1 images, DBS.py:208."""
+    N, F = 16, 4
+    ld = bh.SyntheticLoader(N, F, 1, seeds=(1, 2))
+    env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, verbose=True)
+    names = []
+    for _ in range(3):
+        env.reset()
+        names.append(env.current_file[0])
+    out = capsys.readouterr().out
+    assert names == ["synthetic_0001.png", "synthetic_0002.png", "synthetic_0001.png"]
+    assert out.count("[INFO] Reached the end of dataset. Restarting from the beginning.") == 1
+    assert "Episode count: 3" in out and env.episode_num_count == 3
+    env.close()
+    ld = bh.SyntheticLoader(N, F, 1, seeds=(1, 2, 3))
+    env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, verbose=False)
+    res = bh.optimize_with_random_pixel_flips(env, max_datasets=1, rng=np.random.default_rng(0), max_candidates=30,
+                                              verbose=False)
+    assert [r["file"] for r in res] == ["synthetic_0001", "synthetic_0002"]     # B-9 (and B-10 fixed: own names)
+    env.close()
