@@ -1,5 +1,6 @@
 """Seconds-long GPU sanity run of the Python step paths (single env, vectorised env with periodic
-re-propagation, greedy DBS with the early stop) against the CPU oracle.  No torch, no pytest."""
+re-propagation, greedy DBS with the early stop) against the CPU oracle.  No torch, no pytest:
+`python tests/gpu_sanity.py` on a B200.  Lives under tests/ because it uses the oracle as checker."""
 import os
 import sys
 import time
