@@ -26,17 +26,6 @@ namespace bh {
 //   h     float2 [G][P][P]      impulse response ifft2(H)
 // ---------------------------------------------------------------------------
 
-struct Result {            // mirrored by bh_result in include/bholo.h (40 bytes)
-    double psnr_after;
-    double d_sii;
-    double d_sit;
-    long long action;
-    int32_t accept;
-    int32_t sgn;
-};
-
-enum { RULE_ENV = 0, RULE_DBS = 1, RULE_NEVER = 2 };
-
 // Tile shape knobs (sequences per tile, CTAs per SM the compiler must allow).  Tuned on B200 at
 // P = 1024 (profiles/r1_notes.md): narrow tiles with a large register budget beat wide tiles at
 // the 64-register cap -- the passes are latency bound, and independent small CTAs overlap their
@@ -513,677 +502,11 @@ k_loss_final(const double* __restrict__ partial, int n_partial, double n_elems,
     }
 }
 
-// ---------------------------------------------------------------------------
-// incremental path
-// ---------------------------------------------------------------------------
-// Work decomposition.  A "unit" is UNIT_PX = 1024 consecutive pixels of one
-// candidate's N x N image (one pass of a 256-thread CTA at 4 px per thread).
-// The n_tasks * units_per_task units of a launch are split into gridDim.x
-// contiguous, balanced ranges (CTA b owns [b*total/grid, (b+1)*total/grid)), so
-// every resident CTA streams the same number of bytes (+-1 unit) and a CTA
-// crosses at most a few task boundaries.
-//
-// Reduction.  Per-thread fp32 partials of one quad are converted to 2^-40
-// fixed point and summed as 64-bit integers (registers -> warp shuffles ->
-// shared -> one global atomic per CTA and task).  Integer addition is
-// associative, so sum(dI*(2I+dI)) and sum(dI*T) are bit-identical for every
-// grid size, batch composition, speculation depth and GPU count.
-constexpr int UNIT_PX = 1024;
-// Rows of the impulse-response table carry H_PAD wrapped columns (h[y][P + j] = h[y][j]), so the
-// four taps of a pixel quad are always contiguous: one address, no per-tap wrap.
-constexpr int H_PAD = 4;
-__host__ __device__ constexpr int h_stride(int P) { return P + H_PAD; }
-constexpr float FIX_SCALE = 1099511627776.0f;          // 2^40
-constexpr double FIX_INV = 1.0 / 1099511627776.0;
+}  // namespace bh
 
-struct DeltaArgs {
-    float2* U; float* I; const float* T; int8_t* state; const float2* h;
-    double* sums;                  // [E][4]
-    const int32_t* envs;           // [n_tasks] or nullptr (then env_fixed)
-    const long long* actions;      // device
-    const long long* offset_ptr;   // speculative DBS: actions[*offset_ptr + k]; nullptr otherwise
-    long long n_total;             // valid entries of actions
-    int env_fixed;
-    int n_tasks, N, P, F, G, Fg, relative, rule;
-    int HP;                        // row stride of h: P + H_PAD (h_stride)
-    int units_per_task;            // N*N / UNIT_PX
-    int unit_dy, unit_dx;          // UNIT_PX / N, UNIT_PX % N
-    unsigned long long* acc;       // [n_tasks][2] fixed-point accumulators (zero between launches)
-    unsigned* tickets;             // [n_tasks]
-    Result* results;               // [n_tasks]
-    Result* results_host;          // optional mapped pinned mirror written by the finaliser
-    // speculative greedy DBS (k_commit does the selection): decision log, PSNR trace, counter
-    uint8_t* dbs_accepted; double* dbs_trace; long long* dbs_count; long long* dbs_cursor;
-    // small batches (one env step of <= INLINE_MAX envs) carry their tasks in the
-    // kernel parameters: no host-to-device copy on the step path
-    int n_inline;
-    long long inl_actions[32];
-    int inl_envs[32];
-    // bundled evaluation (k_eval_bundle_t): order a speculation window by frame inside the CTA
-    int sort_window;
-};
-constexpr int INLINE_MAX = 32;
+#include "bh_delta.cuh"      // incremental path: k_eval / k_eval_bundle / k_commit / k_recon_*
 
-struct Decoded {
-    int env, f, g, r, c; float sgn; bool active;
-};
-
-// decode (env.py:158-161) and read the sign of the flip from the resident state
-__device__ __forceinline__ Decoded decode_action(const DeltaArgs& a, int k, long long act) {
-    Decoded d;
-    d.env = a.n_inline ? a.inl_envs[k] : (a.envs ? a.envs[k] : a.env_fixed);
-    d.f = d.g = d.r = d.c = 0; d.sgn = 0.f;
-    d.active = act >= 0;
-    if (!d.active) return d;
-    const int n2 = a.N * a.N;
-    d.f = int(act / n2);
-    const int pix = int(act - (long long)d.f * n2);
-    d.r = pix / a.N;
-    d.c = pix - d.r * a.N;
-    d.g = d.f / a.Fg;
-    d.sgn = 1.f - 2.f * float(a.state[(size_t(d.env) * a.F + d.f) * n2 + pix]);
-    return d;
-}
-
-// per-pixel delta:  dI = (2 s Re(conj(U) h) + |h|^2) / Fg
-__device__ __forceinline__ float delta_px(float ur, float ui, float hr, float hi, float s2,
-                                          float invFg) {
-    const float a = fmaf(ur, hr, ui * hi);
-    const float m = fmaf(hr, hr, hi * hi);
-    return fmaf(s2, a, m * invFg);
-}
-
-// L2 cache-policy loads: the streamed operands (U, I, T) are read once per
-// candidate and marked evict-first; the impulse response is re-read by every
-// candidate and marked evict-last so it stays L2 resident (25 MB for 3 colours).
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-__device__ __forceinline__ uint64_t policy_evict_last() {
-    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-__device__ __forceinline__ float4 ld_stream4(const float4* p, uint64_t pol) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float2 ld_keep2(const float2* p, uint64_t pol) {
-    float2 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
-                 : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
-    return v;
-}
-
-// Programmatic dependent launch: the step path is a chain eval -> commit -> eval ... of grids
-// that each fill the machine in one wave.  Every kernel waits for its predecessor's memory
-// (griddepcontrol.wait) and immediately lets its successor be scheduled, so the successor's
-// CTAs land on SMs as this grid's tail drains and the launch latency disappears from the chain.
-__device__ __forceinline__ void pdl_wait_then_release() {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-
-struct Quad {                      // operands of 4 consecutive pixels
-    float4 ua, ub, iv, tv;
-    float2 h0, h1, h2, h3;
-};
-
-// position of the thread's quad inside the image, advanced unit by unit
-struct Cursor {
-    int y, x;
-    __device__ __forceinline__ void init(int unit, int tid, int N) {
-        const int p = unit * UNIT_PX + tid * 4;
-        y = p / N; x = p - y * N;
-    }
-    __device__ __forceinline__ void next(const DeltaArgs& a) {
-        y += a.unit_dy; x += a.unit_dx;
-        if (x >= a.N) { x -= a.N; ++y; }
-    }
-};
-
-template <bool WITH_T>
-__device__ __forceinline__ void load_quad(Quad& q, const float2* U, const float* I, const float* T,
-                                          const float2* h, const Cursor& cu, int N, int P, int r, int c,
-                                          uint64_t pf, uint64_t pl) {
-    const size_t p = size_t(cu.y) * N + cu.x;
-    const float4* Up = reinterpret_cast<const float4*>(U + p);
-    q.ua = ld_stream4(Up, pf);
-    q.ub = ld_stream4(Up + 1, pf);
-    q.iv = ld_stream4(reinterpret_cast<const float4*>(I + p), pf);
-    if (WITH_T) q.tv = ld_stream4(reinterpret_cast<const float4*>(T + p), pf);
-    int hy = cu.y - r; if (hy < 0) hy += P;
-    int hx = cu.x - c; if (hx < 0) hx += P;
-    const float2* hq = h + size_t(hy) * h_stride(P) + hx;
-    q.h0 = ld_keep2(hq, pl); q.h1 = ld_keep2(hq + 1, pl);
-    q.h2 = ld_keep2(hq + 2, pl); q.h3 = ld_keep2(hq + 3, pl);
-}
-
-__device__ __forceinline__ void eval_quad(const Quad& q, float s2, float invFg, long long& aII,
-                                          long long& aIT) {
-    const float d0 = delta_px(q.ua.x, q.ua.y, q.h0.x, q.h0.y, s2, invFg);
-    const float d1 = delta_px(q.ua.z, q.ua.w, q.h1.x, q.h1.y, s2, invFg);
-    const float d2 = delta_px(q.ub.x, q.ub.y, q.h2.x, q.h2.y, s2, invFg);
-    const float d3 = delta_px(q.ub.z, q.ub.w, q.h3.x, q.h3.y, s2, invFg);
-    float ii = d0 * fmaf(2.f, q.iv.x, d0);
-    ii = fmaf(d1, fmaf(2.f, q.iv.y, d1), ii);
-    ii = fmaf(d2, fmaf(2.f, q.iv.z, d2), ii);
-    ii = fmaf(d3, fmaf(2.f, q.iv.w, d3), ii);
-    float it = d0 * q.tv.x;
-    it = fmaf(d1, q.tv.y, it);
-    it = fmaf(d2, q.tv.z, it);
-    it = fmaf(d3, q.tv.w, it);
-    aII += __float2ll_rn(ii * FIX_SCALE);
-    aIT += __float2ll_rn(it * FIX_SCALE);
-}
-
-__device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// CTA that owns unit u under the balanced partition of `total` units over `grid` CTAs
-__device__ __forceinline__ int cta_of_unit(long long u, long long total, int grid) {
-    return int(((u + 1) * grid - 1) / total);
-}
-
-// One CTA's exact partial sums of task k go to the task's accumulators; the last of the n_ctas
-// contributors turns the totals into the PSNR and the accept decision and re-arms the slot.
-__device__ __forceinline__ void contribute_and_finalise(const DeltaArgs& a, int k, const Decoded& d,
-                                                        long long act, long long x, long long y,
-                                                        unsigned n_ctas, size_t n2) {
-    atomicAdd(a.acc + 2 * k, (unsigned long long)x);
-    atomicAdd(a.acc + 2 * k + 1, (unsigned long long)y);
-    __threadfence();
-    const unsigned ticket = atomicAdd(a.tickets + k, 1u);
-    if (ticket != n_ctas - 1u) return;
-    __threadfence();                                         // every contribution has landed
-    const long long sII = (long long)__ldcg(a.acc + 2 * k);
-    const long long sIT = (long long)__ldcg(a.acc + 2 * k + 1);
-    const double dII = double(sII) * FIX_INV, dIT = double(sIT) * FIX_INV;
-    const double* S = a.sums + size_t(d.env) * 4;
-    const double sii = S[0] + dII, sit = S[1] + dIT, stt = S[2];
-    const double n = double(a.G) * double(n2);
-    const double mse = a.relative ? (stt - sit * sit / sii) / n
-                                  : (sii - 2.0 * sit + stt) / n;
-    const double psnr = -10.0 * log10(mse);
-    const double prev = S[3];
-    int acc = 0;
-    if (a.rule == RULE_ENV) acc = !(psnr - prev < 0.0);     // env.py:191
-    else if (a.rule == RULE_DBS) acc = (psnr > prev);       // DBS.py:273
-    Result r; r.psnr_after = psnr; r.d_sii = dII; r.d_sit = dIT;
-    r.action = act; r.accept = acc; r.sgn = int(d.sgn);
-    a.results[k] = r;
-    if (a.results_host) a.results_host[k] = r;
-    a.acc[2 * k] = 0ull; a.acc[2 * k + 1] = 0ull;
-    a.tickets[k] = 0;
-}
-
-__device__ __forceinline__ void write_idle_result(const DeltaArgs& a, int k) {
-    Result r; r.psnr_after = 0.0; r.d_sii = 0.0; r.d_sit = 0.0;
-    r.action = -1; r.accept = 0; r.sgn = 0;
-    a.results[k] = r;
-}
-
-// the action of task k: kernel parameters, or the (cursor-relative) device list; -1 = idle slot
-__device__ __forceinline__ long long task_action(const DeltaArgs& a, int k) {
-    if (a.n_inline) return a.inl_actions[k];
-    long long idx = k;
-    if (a.offset_ptr) idx += *a.offset_ptr;
-    return (idx < a.n_total) ? a.actions[idx] : -1;
-}
-
-// Row-regular images (N divides UNIT_PX, so a unit is UNIT_PX / N whole rows): a thread keeps its
-// column for the whole pass, the pixel offset advances by UNIT_PX per unit, and the impulse
-// response of a candidate is ONE table offset that advances by unit_dy rows (modulo P).  That
-// removes the per-quad decode of (y, x) and the tap addressing of the generic path -- about half
-// of its instructions.  Scores L candidates of one frame per pass over units [w0, w1) of the task,
-// UF units in flight; pixels, per-quad arithmetic and fixed-point sums are those of the generic
-// path, so the results are bit-identical.
-template <int L, int UF>
-__device__ __forceinline__ void eval_run_rows(const DeltaArgs& a, const float2* U, const float* I,
-                                              const float* T, const float2* h, const int* rr,
-                                              const int* cc, const float* s2, long long* aII,
-                                              long long* aIT, int w0, int w1, int tid, float invFg,
-                                              uint64_t pf, uint64_t pl) {
-    const int N = a.N, P = a.P, HP = a.HP, dy = a.unit_dy;
-    const int y0 = (tid * 4) / N, x = tid * 4 - y0 * N;
-    const int y = w0 * dy + y0;
-    size_t p = size_t(y) * N + x;
-    const int hstep = dy * HP, hwrap = P * HP;
-    int ho[L];                                     // offset of the quad's first tap in the table
-#pragma unroll
-    for (int i = 0; i < L; ++i) {
-        int hx = x - cc[i]; if (hx < 0) hx += P;
-        int hy = y - rr[i]; if (hy < 0) hy += P;
-        ho[i] = hy * HP + hx;
-    }
-    int w = w0;
-#pragma unroll 1
-    for (; w + UF <= w1; w += UF) {
-        float4 ua[UF], ub[UF], iv[UF], tv[UF];
-        float2 hq[UF][L][4];
-#pragma unroll
-        for (int k = 0; k < UF; ++k) {
-            const float4* Up = reinterpret_cast<const float4*>(U + p);
-            ua[k] = ld_stream4(Up, pf);
-            ub[k] = ld_stream4(Up + 1, pf);
-            iv[k] = ld_stream4(reinterpret_cast<const float4*>(I + p), pf);
-            tv[k] = ld_stream4(reinterpret_cast<const float4*>(T + p), pf);
-            p += UNIT_PX;
-#pragma unroll
-            for (int i = 0; i < L; ++i) {
-                const float2* hp = h + ho[i];
-                hq[k][i][0] = ld_keep2(hp, pl); hq[k][i][1] = ld_keep2(hp + 1, pl);
-                hq[k][i][2] = ld_keep2(hp + 2, pl); hq[k][i][3] = ld_keep2(hp + 3, pl);
-                ho[i] += hstep; if (ho[i] >= hwrap) ho[i] -= hwrap;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < UF; ++k) {
-            Quad q; q.ua = ua[k]; q.ub = ub[k]; q.iv = iv[k]; q.tv = tv[k];
-#pragma unroll
-            for (int i = 0; i < L; ++i) {
-                q.h0 = hq[k][i][0]; q.h1 = hq[k][i][1]; q.h2 = hq[k][i][2]; q.h3 = hq[k][i][3];
-                eval_quad(q, s2[i], invFg, aII[i], aIT[i]);
-            }
-        }
-    }
-#pragma unroll 1
-    for (; w < w1; ++w) {
-        Quad q;
-        const float4* Up = reinterpret_cast<const float4*>(U + p);
-        q.ua = ld_stream4(Up, pf);
-        q.ub = ld_stream4(Up + 1, pf);
-        q.iv = ld_stream4(reinterpret_cast<const float4*>(I + p), pf);
-        q.tv = ld_stream4(reinterpret_cast<const float4*>(T + p), pf);
-        p += UNIT_PX;
-        float2 hq[L][4];
-#pragma unroll
-        for (int i = 0; i < L; ++i) {
-            const float2* hp = h + ho[i];
-            hq[i][0] = ld_keep2(hp, pl); hq[i][1] = ld_keep2(hp + 1, pl);
-            hq[i][2] = ld_keep2(hp + 2, pl); hq[i][3] = ld_keep2(hp + 3, pl);
-            ho[i] += hstep; if (ho[i] >= hwrap) ho[i] -= hwrap;
-        }
-#pragma unroll
-        for (int i = 0; i < L; ++i) {
-            q.h0 = hq[i][0]; q.h1 = hq[i][1]; q.h2 = hq[i][2]; q.h3 = hq[i][3];
-            eval_quad(q, s2[i], invFg, aII[i], aIT[i]);
-        }
-    }
-}
-
-// units in flight for a run of L candidates: about four quads of taps per thread
-__host__ __device__ constexpr int run_uf(int L) { return L == 1 ? 3 : (L == 2 ? 2 : 1); }
-
-template <int L, int B>
-__device__ __forceinline__ void eval_run_dispatch(int len, const DeltaArgs& a, const float2* U,
-                                                  const float* I, const float* T, const float2* h,
-                                                  const int* rr, const int* cc, const float* s2,
-                                                  long long* aII, long long* aIT, int w0, int w1,
-                                                  int tid, float invFg, uint64_t pf, uint64_t pl) {
-    if (len == L || L == B)
-        eval_run_rows<L, run_uf(L)>(a, U, I, T, h, rr, cc, s2, aII, aIT, w0, w1, tid, invFg, pf, pl);
-    else if constexpr (L < B)
-        eval_run_dispatch<L + 1, B>(len, a, U, I, T, h, rr, cc, s2, aII, aIT, w0, w1, tid, invFg, pf, pl);
-}
-
-// k_eval: streams U (8 B/px), I and T (4 B/px each) once per candidate and the
-// shifted impulse response from L2: 16 N^2 algorithmic HBM bytes per candidate.
-// The last CTA to contribute to a task turns the exact sums into the PSNR and
-// the accept decision.
-template <int UF, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-k_eval_t(const DeltaArgs a) {
-    __shared__ long long sh[2][8];
-    pdl_wait_then_release();
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int N = a.N, P = a.P, upt = a.units_per_task;
-    const long long total = (long long)a.n_tasks * upt;
-    const long long beg = (long long)blockIdx.x * total / gridDim.x;
-    const long long end = (long long)(blockIdx.x + 1) * total / gridDim.x;
-    const float invFg = 1.f / float(a.Fg);
-    const uint64_t pf = policy_evict_first(), pl = policy_evict_last();
-    const size_t n2 = size_t(N) * N;
-    long long u = beg;
-    while (u < end) {
-        const int k = int(u / upt);
-        const long long t_beg = (long long)k * upt;
-        const long long seg_end = (t_beg + upt < end) ? t_beg + upt : end;
-        const long long act = task_action(a, k);
-        const Decoded d = decode_action(a, k, act);
-        if (!d.active) {
-            if (u == t_beg && tid == 0) write_idle_result(a, k);
-            u = seg_end;
-            continue;
-        }
-        const float2* U = a.U + (size_t(d.env) * a.F + d.f) * n2;
-        const float* I = a.I + (size_t(d.env) * a.G + d.g) * n2;
-        const float* T = a.T + (size_t(d.env) * a.G + d.g) * n2;
-        const float2* h = a.h + size_t(d.g) * P * a.HP;
-        const float s2 = 2.f * d.sgn * invFg;
-        long long aII = 0, aIT = 0;
-        if (a.unit_dx == 0) {
-            eval_run_rows<1, UF>(a, U, I, T, h, &d.r, &d.c, &s2, &aII, &aIT, int(u - t_beg),
-                                 int(seg_end - t_beg), tid, invFg, pf, pl);
-        } else {
-            Cursor cu; cu.init(int(u - t_beg), tid, N);
-            long long v = u;
-            for (; v + UF <= seg_end; v += UF) {         // UF units in flight per thread
-                Quad q[UF];
-#pragma unroll
-                for (int i = 0; i < UF; ++i) {
-                    load_quad<true>(q[i], U, I, T, h, cu, N, P, d.r, d.c, pf, pl); cu.next(a);
-                }
-#pragma unroll
-                for (int i = 0; i < UF; ++i) eval_quad(q[i], s2, invFg, aII, aIT);
-            }
-            for (; v < seg_end; ++v) {
-                Quad q0;
-                load_quad<true>(q0, U, I, T, h, cu, N, P, d.r, d.c, pf, pl); cu.next(a);
-                eval_quad(q0, s2, invFg, aII, aIT);
-            }
-        }
-        aII = warp_sum_ll(aII); aIT = warp_sum_ll(aIT);
-        if (lane == 0) { sh[0][warp] = aII; sh[1][warp] = aIT; }
-        __syncthreads();
-        if (tid == 0) {
-            long long x = 0, y = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { x += sh[0][i]; y += sh[1][i]; }
-            const int first = cta_of_unit(t_beg, total, gridDim.x);
-            const int last = cta_of_unit(t_beg + upt - 1, total, gridDim.x);
-            contribute_and_finalise(a, k, d, act, x, y, unsigned(last - first) + 1u, n2);
-        }
-        __syncthreads();
-        u = seg_end;
-    }
-}
-
-// k_eval_bundle: candidate lists that revisit an environment (speculation windows of the greedy
-// DBS, DBS.py:247-294; the candidate tables of env_group.py:96-119 and the sweeps) are scored B
-// slots at a time.  Inside a bundle every run of candidates of one frame is ONE pass over the
-// image: the thread that owns a quad loads U, I and T once per run and, per candidate, only the
-// shifted impulse response (L2 resident).  HBM traffic per candidate falls from 16 N^2 B towards
-// 16 N^2 / B; the per-quad arithmetic and the 2^-40 fixed-point sums are those of k_eval_t, so
-// both kernels return bit-identical results.  A speculation window (n_tasks <= SORT_WINDOW_MAX,
-// sort_window set) is ordered by frame inside every CTA first; results stay indexed by the
-// caller's task number.
-constexpr int SORT_WINDOW_MAX = 128;
-
-struct BundleTask { int task; long long act; Decoded d; };
-
-__device__ __forceinline__ BundleTask bundle_task(const DeltaArgs& a, int slot, bool sorted,
-                                                  const int* s_order) {
-    BundleTask t;
-    t.task = sorted ? s_order[slot] : slot;
-    t.act = task_action(a, t.task);
-    t.d = decode_action(a, t.task, t.act);
-    return t;
-}
-
-template <int B, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-k_eval_bundle_t(const DeltaArgs a) {
-    __shared__ long long sh[2 * B][8];
-    __shared__ int s_key[SORT_WINDOW_MAX];
-    __shared__ int s_order[SORT_WINDOW_MAX];
-    pdl_wait_then_release();
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int N = a.N, P = a.P, upt = a.units_per_task, n = a.n_tasks;
-    const size_t n2 = size_t(N) * N;
-    const bool sorted = a.sort_window && n <= SORT_WINDOW_MAX;
-    if (sorted) {
-        if (tid < n) {
-            const long long act = task_action(a, tid);
-            s_key[tid] = act < 0 ? 0x7fffffff : int(act / (long long)n2);     // idle slots last
-        }
-        __syncthreads();
-        if (tid < n) {
-            const int key = s_key[tid];
-            int rank = 0;
-            for (int j = 0; j < n; ++j) {
-                const int kj = s_key[j];
-                rank += (kj < key || (kj == key && j < tid)) ? 1 : 0;
-            }
-            s_order[rank] = tid;
-        }
-        __syncthreads();
-    }
-    const int n_bundles = (n + B - 1) / B;
-    const long long total = (long long)n_bundles * upt;
-    const long long beg = (long long)blockIdx.x * total / gridDim.x;
-    const long long end = (long long)(blockIdx.x + 1) * total / gridDim.x;
-    const float invFg = 1.f / float(a.Fg);
-    const uint64_t pf = policy_evict_first(), pl = policy_evict_last();
-    long long u = beg;
-    while (u < end) {
-        const int j = int(u / upt);
-        const long long t_beg = (long long)j * upt;
-        const long long seg_end = (t_beg + upt < end) ? t_beg + upt : end;
-        const unsigned n_ctas = unsigned(cta_of_unit(t_beg + upt - 1, total, gridDim.x) -
-                                         cta_of_unit(t_beg, total, gridDim.x)) + 1u;
-        const int slots = (n - j * B < B) ? n - j * B : B;
-        int rb = 0;
-        while (rb < slots) {
-            // the run: slots rb .. rb+len-1 of the bundle, all of one environment and frame
-            const BundleTask head = bundle_task(a, j * B + rb, sorted, s_order);
-            if (!head.d.active) {                           // idle slot
-                if (u == t_beg && tid == 0) write_idle_result(a, head.task);
-                rb += 1;
-                continue;
-            }
-            int rr[B], cc[B]; float s2[B]; long long aII[B], aIT[B];
-            int len = 1;
-            rr[0] = head.d.r; cc[0] = head.d.c; s2[0] = 2.f * head.d.sgn * invFg;
-            aII[0] = 0; aIT[0] = 0;
-#pragma unroll
-            for (int i = 1; i < B; ++i) {
-                rr[i] = 0; cc[i] = 0; s2[i] = 0.f; aII[i] = 0; aIT[i] = 0;
-                if (rb + i < slots && len == i) {
-                    const BundleTask t = bundle_task(a, j * B + rb + i, sorted, s_order);
-                    if (t.d.active && t.d.env == head.d.env && t.d.f == head.d.f) {
-                        rr[i] = t.d.r; cc[i] = t.d.c; s2[i] = 2.f * t.d.sgn * invFg;
-                        len = i + 1;
-                    }
-                }
-            }
-            const float2* U = a.U + (size_t(head.d.env) * a.F + head.d.f) * n2;
-            const float* I = a.I + (size_t(head.d.env) * a.G + head.d.g) * n2;
-            const float* T = a.T + (size_t(head.d.env) * a.G + head.d.g) * n2;
-            const float2* h = a.h + size_t(head.d.g) * P * a.HP;
-            if (a.unit_dx == 0) {
-                eval_run_dispatch<1, B>(len, a, U, I, T, h, rr, cc, s2, aII, aIT, int(u - t_beg),
-                                        int(seg_end - t_beg), tid, invFg, pf, pl);
-            } else {
-                Cursor cu; cu.init(int(u - t_beg), tid, N);
-#pragma unroll 1
-                for (long long v = u; v < seg_end; ++v) {
-                    const size_t p = size_t(cu.y) * N + cu.x;
-                    Quad q;
-                    const float4* Up = reinterpret_cast<const float4*>(U + p);
-                    q.ua = ld_stream4(Up, pf);
-                    q.ub = ld_stream4(Up + 1, pf);
-                    q.iv = ld_stream4(reinterpret_cast<const float4*>(I + p), pf);
-                    q.tv = ld_stream4(reinterpret_cast<const float4*>(T + p), pf);
-                    float2 hq[B][4];
-#pragma unroll
-                    for (int i = 0; i < B; ++i) {
-                        if (i < len) {
-                            int hy = cu.y - rr[i]; if (hy < 0) hy += P;
-                            int hx = cu.x - cc[i]; if (hx < 0) hx += P;
-                            const float2* hp = h + size_t(hy) * a.HP + hx;
-                            hq[i][0] = ld_keep2(hp, pl); hq[i][1] = ld_keep2(hp + 1, pl);
-                            hq[i][2] = ld_keep2(hp + 2, pl); hq[i][3] = ld_keep2(hp + 3, pl);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < B; ++i) {
-                        if (i < len) {
-                            q.h0 = hq[i][0]; q.h1 = hq[i][1]; q.h2 = hq[i][2]; q.h3 = hq[i][3];
-                            eval_quad(q, s2[i], invFg, aII[i], aIT[i]);
-                        }
-                    }
-                    cu.next(a);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < B; ++i) {
-                if (i < len) {
-                    const long long x = warp_sum_ll(aII[i]), y = warp_sum_ll(aIT[i]);
-                    if (lane == 0) { sh[2 * i][warp] = x; sh[2 * i + 1][warp] = y; }
-                }
-            }
-            __syncthreads();
-            if (tid < len) {                                // one thread per candidate of the run
-                const BundleTask t = bundle_task(a, j * B + rb + tid, sorted, s_order);
-                long long x = 0, y = 0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) { x += sh[2 * tid][w]; y += sh[2 * tid + 1][w]; }
-                contribute_and_finalise(a, t.task, t.d, t.act, x, y, n_ctas, n2);
-            }
-            __syncthreads();
-            rb += len;
-        }
-        u = seg_end;
-    }
-}
-
-// k_commit: applies every accepted task: U_f += s*shift(h), I_g += dI, flips the
-// state byte and advances the running sums.  24 N^2 algorithmic HBM bytes per
-// accepted flip.  Tasks of one launch must target distinct environments
-// (n_tasks <= COMMIT_MAX_TASKS).  Every CTA first compacts the accepted tasks,
-// then the balanced unit partition runs over the accepted ones only, so a
-// launch with one accepted flip out of K still uses the whole chip.
-constexpr int COMMIT_MAX_TASKS = 256;
-
-__device__ __forceinline__ void commit_quad(const Quad& q, float2* U, float* I, size_t p, float s2,
-                                            float sg, float invFg) {
-    float4 iv = q.iv, ua = q.ua, ub = q.ub;
-    iv.x += delta_px(ua.x, ua.y, q.h0.x, q.h0.y, s2, invFg);
-    iv.y += delta_px(ua.z, ua.w, q.h1.x, q.h1.y, s2, invFg);
-    iv.z += delta_px(ub.x, ub.y, q.h2.x, q.h2.y, s2, invFg);
-    iv.w += delta_px(ub.z, ub.w, q.h3.x, q.h3.y, s2, invFg);
-    ua.x = fmaf(sg, q.h0.x, ua.x); ua.y = fmaf(sg, q.h0.y, ua.y);
-    ua.z = fmaf(sg, q.h1.x, ua.z); ua.w = fmaf(sg, q.h1.y, ua.w);
-    ub.x = fmaf(sg, q.h2.x, ub.x); ub.y = fmaf(sg, q.h2.y, ub.y);
-    ub.z = fmaf(sg, q.h3.x, ub.z); ub.w = fmaf(sg, q.h3.y, ub.w);
-    float4* Up = reinterpret_cast<float4*>(U + p);
-    Up[0] = ua; Up[1] = ub;
-    *reinterpret_cast<float4*>(I + p) = iv;
-}
-
-template <int UF, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-k_commit_t(const DeltaArgs a) {
-    __shared__ int s_list[COMMIT_MAX_TASKS];
-    __shared__ int s_cnt;
-    const int tid = threadIdx.x;
-    pdl_wait_then_release();
-    if (tid == 0) {
-        int n = 0;
-        if (a.dbs_cursor) {
-            // speculative greedy DBS (DBS.py:247-294 order): all K candidates were scored against
-            // the same state; keep the first accepted one, the candidates after it are scored
-            // again by the next batch.  Block 0 logs the decisions and advances the cursor
-            // (idle slots carry accept = 0, so no other block needs the cursor).
-            int first = -1;
-            for (int k = 0; k < a.n_tasks; ++k)
-                if (a.results[k].accept) { first = k; break; }
-            if (first >= 0) s_list[n++] = first;
-            if (blockIdx.x == 0) {
-                const long long off = *a.dbs_cursor;
-                long long cnt = a.n_total - off;
-                if (cnt > a.n_tasks) cnt = a.n_tasks;
-                if (cnt > 0) {
-                    const int used = first >= 0 ? first + 1 : int(cnt);
-                    for (int k = 0; k < used; ++k) {
-                        a.dbs_accepted[off + k] = (k == first) ? 1 : 0;
-                        if (a.dbs_trace) a.dbs_trace[off + k] = a.results[k].psnr_after;
-                    }
-                    if (first >= 0) *a.dbs_count += 1;
-                    *a.dbs_cursor = off + used;
-                }
-            }
-        } else {
-            for (int k = 0; k < a.n_tasks; ++k)
-                if (a.results[k].accept) s_list[n++] = k;
-        }
-        s_cnt = n;
-    }
-    __syncthreads();
-    const int n_acc = s_cnt;
-    if (n_acc == 0) return;
-    const int N = a.N, P = a.P, upt = a.units_per_task;
-    const long long total = (long long)n_acc * upt;
-    const long long beg = (long long)blockIdx.x * total / gridDim.x;
-    const long long end = (long long)(blockIdx.x + 1) * total / gridDim.x;
-    const float invFg = 1.f / float(a.Fg);
-    const uint64_t pf = policy_evict_first(), pl = policy_evict_last();
-    const size_t n2 = size_t(N) * N;
-    long long u = beg;
-    while (u < end) {
-        const int slot = int(u / upt);
-        const int k = s_list[slot];
-        const long long t_beg = (long long)slot * upt;
-        const long long seg_end = (t_beg + upt < end) ? t_beg + upt : end;
-        const Result res = a.results[k];
-        Decoded d = decode_action(a, k, res.action);
-        d.sgn = float(res.sgn);            // the state byte may already be flipped
-        float2* U = a.U + (size_t(d.env) * a.F + d.f) * n2;
-        float* I = a.I + (size_t(d.env) * a.G + d.g) * n2;
-        const float2* h = a.h + size_t(d.g) * P * a.HP;
-        const float s2 = 2.f * d.sgn * invFg, sg = d.sgn;
-        Cursor cu; cu.init(int(u - t_beg), tid, N);
-        long long v = u;
-        for (; v + UF <= seg_end; v += UF) {
-            Quad q[UF];
-            size_t p[UF];
-#pragma unroll
-            for (int i = 0; i < UF; ++i) {
-                load_quad<false>(q[i], U, I, nullptr, h, cu, N, P, d.r, d.c, pf, pl);
-                p[i] = size_t(cu.y) * N + cu.x;
-                cu.next(a);
-            }
-#pragma unroll
-            for (int i = 0; i < UF; ++i) commit_quad(q[i], U, I, p[i], s2, sg, invFg);
-        }
-        for (; v < seg_end; ++v) {
-            Quad q;
-            load_quad<false>(q, U, I, nullptr, h, cu, N, P, d.r, d.c, pf, pl);
-            commit_quad(q, U, I, size_t(cu.y) * N + cu.x, s2, sg, invFg);
-            cu.next(a);
-        }
-        if (u == t_beg && tid == 0) {
-            int8_t* st = a.state + (size_t(d.env) * a.F + d.f) * n2 + size_t(d.r) * N + d.c;
-            *st = int8_t(1 - *st);
-            double* S = a.sums + size_t(d.env) * 4;
-            S[0] += res.d_sii;
-            S[1] += res.d_sit;
-            S[3] = res.psnr_after;
-        }
-        u = seg_end;
-    }
-}
-
-// k_recon_candidate: out_g += dI of one (uncommitted) candidate flip; used to
-// materialise obs["recon_image"] of a rejected step (env.py:176-181, appendix B-2).
-__global__ void __launch_bounds__(256)
-k_recon_candidate(const float2* __restrict__ U, const float2* __restrict__ h,
-                  float* __restrict__ out_g, int N, int P, int r, int c, float sgn, int Fg) {
-    const float invFg = 1.f / float(Fg), s2 = 2.f * sgn * invFg;
-    const size_t n2 = size_t(N) * N;
-    for (size_t p = size_t(blockIdx.x) * blockDim.x + threadIdx.x; p < n2;
-         p += size_t(gridDim.x) * blockDim.x) {
-        const int y = int(p / N), x = int(p - size_t(y) * N);
-        int hy = y - r; if (hy < 0) hy += P;
-        int hx = x - c; if (hx < 0) hx += P;
-        const float2 u = U[p], hv = __ldg(h + size_t(hy) * h_stride(P) + hx);
-        out_g[p] += delta_px(u.x, u.y, hv.x, hv.y, s2, invFg);
-    }
-}
+namespace bh {
 
 // ---------------------------------------------------------------------------
 // exhaustive sweep by correlation (score EVERY pixel of every frame against the

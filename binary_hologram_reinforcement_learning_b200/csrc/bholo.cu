@@ -61,6 +61,14 @@ struct bh_ctx {
     void (*k_eval_bundle)(const DeltaArgs) = nullptr;
     void (*k_commit)(const DeltaArgs) = nullptr;
     bool use_pdl = true;
+    bool fp64_eval = true;               // per-quad arithmetic of the delta evaluation in double
+    // observation path (bh_recon_batch)
+    uint8_t* d_recon_stale = nullptr;    // [E][RECON_MAX_BUFFERS]
+    ReconPlan* d_recon_plan = nullptr;   // [max_tasks]
+    float* d_recon_obs[RECON_MAX_BUFFERS] = {nullptr, nullptr, nullptr, nullptr};   // device observation blocks
+    cudaEvent_t ev_recon = nullptr;
+    // scratch of bh_sweep_stats, kept between calls
+    double* d_stat_map = nullptr; float* d_stat_pre = nullptr; unsigned long long* d_stat_out = nullptr;
     int64_t launches = 0;
     std::string err;
 };
@@ -206,12 +214,14 @@ static int propagate_env(bh_ctx* c, int env, float* pass_ms = nullptr) {
                                           c->dsums + size_t(env) * 4, c->relative);
     BH_CUDA(c, cudaGetLastError());
     c->launches += 1;
+    // every observation buffer has to re-read all planes of this environment
+    BH_CUDA(c, cudaMemsetAsync(c->d_recon_stale + size_t(env) * RECON_MAX_BUFFERS, 0xff, RECON_MAX_BUFFERS, c->stream));
     return 0;
 }
 
-// k_eval variants: units in flight per thread x CTAs per SM.  Measured at 1024^2 x 24, 8 candidates
-// per launch (scripts/tune_eval.py, profiles/r1_notes.md): <2,4> 28.6 us, <4,2> 27.4, <2,3> 27.9,
-// <3,2> 27.3 (default), 1 CTA/SM variants 33-35 us.  BHOLO_EVAL_VARIANT selects another one.
+// k_eval variants: units in flight per thread x CTAs per SM x arithmetic type of the per-quad sums.
+// Measured at 1024^2 x 24, 8 candidates per launch (scripts/tune_eval.py, profiles/r2_notes.md).
+// BHOLO_EVAL_VARIANT selects another shape, BHOLO_EVAL_FP32=1 the float arithmetic of round 1.
 typedef void (*eval_fn)(const DeltaArgs);
 static eval_fn commit_variant(int v) {
     switch (v) {
@@ -220,30 +230,34 @@ static eval_fn commit_variant(int v) {
         case 3: return k_commit_t<3, 2>;
         case 4: return k_commit_t<4, 2>;
         case 5: return k_commit_t<2, 3>;
+        case 6: return k_commit_t<3, 3>;
         default: return k_commit_t<3, 2>;
     }
 }
 // k_eval_bundle variants: slots per bundle x CTAs per SM; BHOLO_BUNDLE_VARIANT=9 disables bundling
 // (candidate lists then go through k_eval_t)
+template <typename R>
 static eval_fn bundle_variant(int v, int* slots) {
     switch (v) {
-        case 1: *slots = 8; return k_eval_bundle_t<8, 1>;
-        case 2: *slots = 6; return k_eval_bundle_t<6, 1>;
-        case 3: *slots = 3; return k_eval_bundle_t<3, 2>;
-        case 4: *slots = 2; return k_eval_bundle_t<2, 3>;
+        case 1: *slots = 8; return k_eval_bundle_t<8, 1, R>;
+        case 2: *slots = 6; return k_eval_bundle_t<6, 1, R>;
+        case 3: *slots = 3; return k_eval_bundle_t<3, 2, R>;
+        case 4: *slots = 2; return k_eval_bundle_t<2, 3, R>;
         case 9: *slots = 0; return nullptr;
-        default: *slots = 4; return k_eval_bundle_t<4, 2>;
+        default: *slots = 4; return k_eval_bundle_t<4, 2, R>;
     }
 }
+template <typename R>
 static eval_fn eval_variant(int v) {
     switch (v) {
-        case 1: return k_eval_t<2, 4>;
-        case 2: return k_eval_t<4, 2>;
-        case 3: return k_eval_t<2, 3>;
-        case 4: return k_eval_t<3, 3>;
-        case 5: return k_eval_t<6, 1>;
-        case 6: return k_eval_t<5, 2>;
-        default: return k_eval_t<3, 2>;
+        case 1: return k_eval_t<2, 4, R>;
+        case 2: return k_eval_t<4, 2, R>;
+        case 3: return k_eval_t<2, 3, R>;
+        case 4: return k_eval_t<3, 3, R>;
+        case 5: return k_eval_t<6, 1, R>;
+        case 6: return k_eval_t<5, 2, R>;
+        case 7: return k_eval_t<2, 2, R>;
+        default: return k_eval_t<3, 2, R>;
     }
 }
 
@@ -262,6 +276,10 @@ extern "C" int bh_destroy(bh_ctx* c) {
     cudaFree(c->dK3); cudaFree(c->dK4); cudaFree(c->dK5); cudaFree(c->dK6); cudaFree(c->dsw_in); cudaFree(c->dsw_out);
     cudaFree(c->dsw_buf);
     cudaFree(c->dsw_it); cudaFree(c->dsw_ii); cudaFree(c->dsw_psnr);
+    cudaFree(c->d_recon_stale); cudaFree(c->d_recon_plan);
+    for (auto& b : c->d_recon_obs) cudaFree(b);
+    cudaFree(c->d_stat_map); cudaFree(c->d_stat_pre); cudaFree(c->d_stat_out);
+    if (c->ev_recon) cudaEventDestroy(c->ev_recon);
     cudaFreeHost(c->h_envs); cudaFreeHost(c->h_actions); cudaFreeHost(c->h_results);
     cudaFreeHost(c->h_scalars); cudaFreeHost(c->h_sums);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -327,6 +345,9 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
     BH_TRY(cudaMalloc(&c->d_acc, size_t(c->max_tasks) * 2 * sizeof(unsigned long long)));
     BH_TRY(cudaMalloc(&c->d_tickets, size_t(c->max_tasks) * sizeof(unsigned)));
     BH_TRY(cudaMalloc(&c->d_scalars, 4 * sizeof(long long)));
+    BH_TRY(cudaMalloc(&c->d_recon_stale, size_t(n_env) * RECON_MAX_BUFFERS));
+    BH_TRY(cudaMalloc(&c->d_recon_plan, size_t(c->max_tasks) * sizeof(ReconPlan)));
+    BH_TRY(cudaEventCreateWithFlags(&c->ev_recon, cudaEventDisableTiming));
     BH_TRY(cudaMallocHost(&c->h_envs, size_t(c->max_tasks) * sizeof(int32_t)));
     BH_TRY(cudaMallocHost(&c->h_actions, size_t(c->max_tasks) * sizeof(long long)));
     BH_TRY(cudaHostAlloc(&c->h_results, size_t(c->max_tasks) * sizeof(Result), cudaHostAllocMapped));
@@ -344,6 +365,7 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
         BH_TRY(cudaMemset(c->dstate, 0, size_t(n_env) * F * n2));
         BH_TRY(cudaMemset(c->dU, 0, size_t(n_env) * F * n2 * sizeof(float2)));
         BH_TRY(cudaMemset(c->dI, 0, size_t(n_env) * G * n2 * sizeof(float)));
+        BH_TRY(cudaMemset(c->d_recon_stale, 0xff, size_t(n_env) * RECON_MAX_BUFFERS));
         const size_t HP = size_t(h_stride(c->P));
         for (int g = 0; g < G && rc == 0; ++g) {
             auto t = get_tables(c->P, wl[g], dx, z, method);
@@ -359,18 +381,20 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
         int nb = 0;
         c->use_pdl = !std::getenv("BHOLO_NO_PDL");
         const char* ev = std::getenv("BHOLO_EVAL_VARIANT");
-        c->k_eval = eval_variant(ev ? std::atoi(ev) : 0);
+        c->fp64_eval = !std::getenv("BHOLO_EVAL_FP32");
+        c->k_eval = c->fp64_eval ? eval_variant<double>(ev ? std::atoi(ev) : 0) : eval_variant<float>(ev ? std::atoi(ev) : 0);
         BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, c->k_eval, 256, 0));
-        c->grid_cap = std::max(1, nb) * prop.multiProcessorCount;
+        c->grid_cap = std::min(MAX_DELTA_GRID, std::max(1, nb) * prop.multiProcessorCount);
         const char* cv = std::getenv("BHOLO_COMMIT_VARIANT");
         c->k_commit = commit_variant(cv ? std::atoi(cv) : 0);
         BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, c->k_commit, 256, 0));
         c->grid_cap_commit = std::max(1, nb) * prop.multiProcessorCount;
         const char* bv = std::getenv("BHOLO_BUNDLE_VARIANT");
-        c->k_eval_bundle = bundle_variant(bv ? std::atoi(bv) : 0, &c->bundle);
+        c->k_eval_bundle = c->fp64_eval ? bundle_variant<double>(bv ? std::atoi(bv) : 0, &c->bundle)
+                                        : bundle_variant<float>(bv ? std::atoi(bv) : 0, &c->bundle);
         if (c->k_eval_bundle) {
             BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, c->k_eval_bundle, 256, 0));
-            c->grid_cap_bundle = std::max(1, nb) * prop.multiProcessorCount;
+            c->grid_cap_bundle = std::min(MAX_DELTA_GRID, std::max(1, nb) * prop.multiProcessorCount);
         }
     }
 #undef BH_TRY
@@ -429,6 +453,7 @@ extern "C" int bh_clone_env(bh_ctx* c, int src, int dst) {
     BH_CUDA(c, cudaMemcpyAsync(c->dT + size_t(dst) * c->G * n2, c->dT + size_t(src) * c->G * n2, size_t(c->G) * n2 * sizeof(float), k, c->stream));
     BH_CUDA(c, cudaMemcpyAsync(c->dstate + size_t(dst) * c->F * n2, c->dstate + size_t(src) * c->F * n2, size_t(c->F) * n2, k, c->stream));
     BH_CUDA(c, cudaMemcpyAsync(c->dsums + size_t(dst) * 4, c->dsums + size_t(src) * 4, 4 * sizeof(double), k, c->stream));
+    BH_CUDA(c, cudaMemsetAsync(c->d_recon_stale + size_t(dst) * RECON_MAX_BUFFERS, 0xff, RECON_MAX_BUFFERS, c->stream));
     return 0;
 }
 
@@ -465,6 +490,7 @@ static DeltaArgs make_args(bh_ctx* c, int n, int env_fixed, const int32_t* d_env
     a.unit_dy = UNIT_PX / c->N; a.unit_dx = UNIT_PX % c->N;
     a.acc = c->d_acc; a.tickets = c->d_tickets; a.results = d_results;
     a.results_host = nullptr; a.n_inline = 0; a.sort_window = 0;
+    a.recon_stale = c->d_recon_stale;
     a.dbs_accepted = nullptr; a.dbs_trace = nullptr; a.dbs_count = nullptr; a.dbs_cursor = nullptr;
     return a;
 }
@@ -591,7 +617,7 @@ extern "C" int bh_step_batch_device(bh_ctx* c, int n, const int32_t* d_env_ids, 
                                     int rule, bh_result* d_results) {
     BH_CHECK_CTX(c);
     if (n < 0 || n > c->max_tasks) BH_FAIL(c, -3, "n=%d exceeds max_tasks=%d", n, c->max_tasks);
-    if (rule < 0 || rule > 2) BH_FAIL(c, -1, "bad rule %d", rule);
+    if (rule < 0 || rule > 3) BH_FAIL(c, -1, "bad rule %d", rule);
     if (n == 0) return 0;
     if (!d_env_ids && n > 1) BH_FAIL(c, -1, "a batch step needs one distinct env per task");
     DeltaArgs a = make_args(c, n, 0, d_env_ids, reinterpret_cast<const long long*>(d_actions), rule,
@@ -606,7 +632,7 @@ extern "C" int bh_step_batch(bh_ctx* c, int n, const int32_t* env_ids, const int
                              bh_result* results) {
     BH_CHECK_CTX(c);
     if (n < 0 || n > c->max_tasks || !actions || !results) BH_FAIL(c, -1, "bad arguments");
-    if (rule < 0 || rule > 2) BH_FAIL(c, -1, "bad rule %d", rule);
+    if (rule < 0 || rule > 3) BH_FAIL(c, -1, "bad rule %d", rule);
     if (n == 0) return 0;
     if (int rc = check_actions(c, actions, n)) return rc;
     if (n > c->E) BH_FAIL(c, -3, "n=%d tasks but only %d environments", n, c->E);
@@ -690,18 +716,10 @@ extern "C" int bh_vec_step(bh_ctx* c, int n, const int32_t* env_ids, const int64
 extern "C" int bh_commit_flip(bh_ctx* c, int env, int64_t action) {
     BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
     if (int rc = check_actions(c, &action, 1)) return rc;
-    c->h_actions[0] = action;
-    BH_CUDA(c, cudaMemcpyAsync(c->d_actions, c->h_actions, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-    DeltaArgs a = make_args(c, 1, env, nullptr, c->d_actions, RULE_NEVER, c->d_results);
+    // score with the "always keep" rule, then apply: no host round trip in between
+    DeltaArgs a = make_args(c, 1, env, nullptr, c->d_actions, RULE_ALWAYS, c->d_results);
+    a.n_inline = 1; a.inl_actions[0] = action; a.inl_envs[0] = env;
     launch_eval(c, a);
-    // force the decision, then apply
-    Result r;
-    BH_CUDA(c, cudaMemcpyAsync(c->h_results, c->d_results, sizeof(Result), cudaMemcpyDeviceToHost, c->stream));
-    BH_CUDA(c, cudaStreamSynchronize(c->stream));
-    r = c->h_results[0];
-    r.accept = 1;
-    c->h_results[0] = r;
-    BH_CUDA(c, cudaMemcpyAsync(c->d_results, c->h_results, sizeof(Result), cudaMemcpyHostToDevice, c->stream));
     launch_commit(c, a);
     BH_CUDA(c, cudaGetLastError());
     BH_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -766,7 +784,10 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
                     const int64_t before = c->launches;
                     BH_DBS(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
                     for (int i = 0; i < iters_per_sync; ++i) { launch_eval_list(c, a, false); launch_commit(c, ac); }
-                    BH_DBS(cudaStreamEndCapture(c->stream, &g));
+                    // always leave capture mode, also when a captured launch failed
+                    const cudaError_t cap_err = cudaStreamEndCapture(c->stream, &g);
+                    if (cap_err != cudaSuccess && g) { cudaGraphDestroy(g); g = nullptr; }
+                    BH_DBS(cap_err);
                     c->launches = before;       // captured, not launched
                     BH_DBS(cudaGraphInstantiate(&ge, g, 0));
                     cudaGraphDestroy(g);
@@ -915,8 +936,9 @@ extern "C" int bh_sweep_stats(bh_ctx* c, int env, const float* pre_model, const 
     BH_CHECK_CTX(c); BH_CHECK_ENV(c, env);
     if (!pre_model || !edges || !attempted || !improved || !gains) BH_FAIL(c, -1, "bad arguments");
     const size_t count = size_t(c->F) * c->n2;
-    double* d_map = nullptr; float* d_pre = nullptr; unsigned long long* d_out = nullptr;
-    auto cleanup = [&]() { cudaFree(d_map); cudaFree(d_pre); cudaFree(d_out); };
+    // scratch (~450 MB at 1024^2 x 24) is allocated on first use and kept for the life of the context
+    double*& d_map = c->d_stat_map; float*& d_pre = c->d_stat_pre; unsigned long long*& d_out = c->d_stat_out;
+    auto cleanup = [&]() {};
 #define BH_ST(expr)                                                          \
     do {                                                                     \
         cudaError_t _e = (expr);                                             \
@@ -925,9 +947,9 @@ extern "C" int bh_sweep_stats(bh_ctx* c, int env, const float* pre_model, const 
             BH_FAIL(c, -2, "%s failed: %s", #expr, cudaGetErrorString(_e));  \
         }                                                                    \
     } while (0)
-    BH_ST(cudaMalloc(&d_map, count * sizeof(double)));
-    BH_ST(cudaMalloc(&d_pre, count * sizeof(float)));
-    BH_ST(cudaMalloc(&d_out, 3 * N_BINS * sizeof(unsigned long long)));
+    if (!d_map) BH_ST(cudaMalloc(&d_map, count * sizeof(double)));
+    if (!d_pre) BH_ST(cudaMalloc(&d_pre, count * sizeof(float)));
+    if (!d_out) BH_ST(cudaMalloc(&d_out, 3 * N_BINS * sizeof(unsigned long long)));
     BH_ST(cudaMemcpyAsync(d_pre, pre_model, count * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     BH_ST(cudaMemsetAsync(d_out, 0, 3 * N_BINS * sizeof(unsigned long long), c->stream));
     double previous = 0.0;
@@ -954,7 +976,7 @@ extern "C" int bh_sweep_stats(bh_ctx* c, int env, const float* pre_model, const 
 
 extern "C" void* bh_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
         g_err = "cudaHostAlloc failed";
         return nullptr;
     }
@@ -976,27 +998,101 @@ extern "C" int bh_get_recon(bh_ctx* c, int env, float* out, int on_host, int64_t
         if (on_host) BH_CUDA(c, cudaStreamSynchronize(c->stream));
         return 0;
     }
+    if (int rc = check_actions(c, &cand, 1)) return rc;
     float* dst = on_host ? c->drecon : out;
     BH_CUDA(c, cudaMemcpyAsync(dst, I, bytes, cudaMemcpyDeviceToDevice, c->stream));
-    if (cand >= 0) {
-        if (int rc = check_actions(c, &cand, 1)) return rc;
-        const int f = int(cand / (long long)n2);
-        const int pix = int(cand - (long long)f * (long long)n2);
-        const int r = pix / c->N, col = pix % c->N, g = f / c->Fg;
-        int8_t sb = 0;
-        BH_CUDA(c, cudaMemcpyAsync(&sb, c->dstate + (size_t(env) * c->F + f) * n2 + pix, 1, cudaMemcpyDeviceToHost, c->stream));
-        BH_CUDA(c, cudaStreamSynchronize(c->stream));
-        const float sgn = 1.f - 2.f * float(sb);
-        k_recon_candidate<<<std::min<size_t>((n2 + 255) / 256, 148 * 8), 256, 0, c->stream>>>(
-            c->dU + (size_t(env) * c->F + f) * n2, c->dh + size_t(g) * c->P * h_stride(c->P), dst + size_t(g) * n2,
-            c->N, c->P, r, col, sgn, c->Fg);
-        BH_CUDA(c, cudaGetLastError());
-        c->launches += 1;
-    }
+    const int f = int(cand / (long long)n2);
+    const int pix = int(cand - (long long)f * (long long)n2);
+    const int r = pix / c->N, col = pix % c->N, g = f / c->Fg;
+    // the sign of the flip is read from the resident state by the kernel (no host round trip)
+    k_recon_candidate<<<std::min<size_t>((n2 + 255) / 256, 148 * 8), 256, 0, c->stream>>>(
+        c->dU + (size_t(env) * c->F + f) * n2, c->dh + size_t(g) * c->P * h_stride(c->P),
+        c->dstate + (size_t(env) * c->F + f) * n2 + pix, dst + size_t(g) * n2, c->N, c->P, r, col, c->Fg);
+    BH_CUDA(c, cudaGetLastError());
+    c->launches += 1;
     if (on_host) {
         BH_CUDA(c, cudaMemcpyAsync(out, c->drecon, bytes, cudaMemcpyDeviceToHost, c->stream));
         BH_CUDA(c, cudaStreamSynchronize(c->stream));
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// batched observation path
+// ---------------------------------------------------------------------------
+extern "C" void* bh_recon_device_block(bh_ctx* c, int buffer) {
+    if (!c || buffer < 0 || buffer >= RECON_MAX_BUFFERS) return nullptr;
+    if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
+    if (!c->d_recon_obs[buffer]) {
+        const size_t bytes = size_t(c->E) * c->G * c->n2 * sizeof(float);
+        if (cudaMalloc(&c->d_recon_obs[buffer], bytes) != cudaSuccess) { c->err = "cudaMalloc of the observation block failed"; return nullptr; }
+        cudaMemsetAsync(c->d_recon_obs[buffer], 0, bytes, c->stream);
+        // a new block holds nothing: every plane of every environment is stale in it
+        std::vector<uint8_t> ones(size_t(c->E) * RECON_MAX_BUFFERS);
+        cudaMemcpyAsync(ones.data(), c->d_recon_stale, ones.size(), cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        for (int e = 0; e < c->E; ++e) ones[size_t(e) * RECON_MAX_BUFFERS + buffer] = 0xff;
+        cudaMemcpyAsync(c->d_recon_stale, ones.data(), ones.size(), cudaMemcpyHostToDevice, c->stream);
+        cudaStreamSynchronize(c->stream);
+    }
+    return c->d_recon_obs[buffer];
+}
+
+extern "C" int bh_recon_batch(bh_ctx* c, int n, const int32_t* env_ids, const bh_result* d_results,
+                              float* out, int out_kind, int buffer, int flags) {
+    BH_CHECK_CTX(c);
+    if (n < 0 || n > c->max_tasks) BH_FAIL(c, -3, "n=%d exceeds max_tasks=%d", n, c->max_tasks);
+    if (buffer < 0 || buffer >= RECON_MAX_BUFFERS) BH_FAIL(c, -1, "buffer %d outside [0,%d)", buffer, RECON_MAX_BUFFERS);
+    if (n == 0) return 0;
+    float* dst = nullptr;
+    if (out_kind == BH_OBS_DEVICE) {
+        dst = out;
+    } else if (out_kind == BH_OBS_PINNED_HOST) {
+        if (!out) BH_FAIL(c, -1, "out is null");
+        BH_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&dst), out, 0));
+    } else if (out_kind == BH_OBS_CONTEXT) {
+        dst = static_cast<float*>(bh_recon_device_block(c, buffer));
+    } else {
+        BH_FAIL(c, -1, "bad out_kind %d", out_kind);
+    }
+    if (!dst) BH_FAIL(c, -1, "no observation block");
+    ReconArgs a;
+    a.U = c->dU; a.I = c->dI; a.h = c->dh; a.state = c->dstate;
+    a.results = (flags & BH_OBS_COMMITTED_ONLY) ? nullptr
+              : (d_results ? reinterpret_cast<const Result*>(d_results) : c->d_results);
+    a.envs = nullptr; a.n_inline = 0;
+    if (env_ids) {
+        for (int i = 0; i < n; ++i) BH_CHECK_ENV(c, env_ids[i]);
+        if (n <= INLINE_MAX) {
+            a.n_inline = n;
+            for (int i = 0; i < n; ++i) a.inl_envs[i] = env_ids[i];
+        } else {
+            // the staging arrays are free here: every host-array entry point synchronises before returning
+            std::memcpy(c->h_envs, env_ids, size_t(n) * sizeof(int32_t));
+            BH_CUDA(c, cudaMemcpyAsync(c->d_envs, c->h_envs, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            a.envs = c->d_envs;
+        }
+    } else if (n > c->E) {
+        BH_FAIL(c, -3, "n=%d tasks but only %d environments", n, c->E);
+    }
+    a.stale = c->d_recon_stale; a.plan = c->d_recon_plan; a.out = dst;
+    a.n_tasks = n; a.E = c->E; a.N = c->N; a.P = c->P; a.HP = h_stride(c->P); a.F = c->F; a.G = c->G; a.Fg = c->Fg;
+    a.buffer = buffer; a.full = (flags & BH_OBS_FULL) ? 1 : 0;
+    k_recon_plan<<<1, 256, 0, c->stream>>>(a);
+    const int chunks = int(std::min<size_t>((c->n2 + 1023) / 1024, 96));
+    k_recon_batch<<<dim3(chunks, c->G, n), 256, 0, c->stream>>>(a);
+    BH_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    if (flags & BH_OBS_SYNC) {
+        BH_CUDA(c, cudaEventRecord(c->ev_recon, c->stream));
+        BH_CUDA(c, cudaEventSynchronize(c->ev_recon));
+    }
+    return 0;
+}
+
+extern "C" int bh_stream_sync(bh_ctx* c) {
+    BH_CHECK_CTX(c);
+    BH_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -1053,6 +1149,26 @@ static int sim_tables(int device, int P, double wl, double dx, double z, int met
     return 0;
 }
 
+// Work buffers of the stand-alone operator, per device, grown on demand and kept: a script that
+// calls tt.simulate every step must not pay cudaMalloc / cudaFree (each a device synchronisation).
+struct SimPool {
+    void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t cap[4] = {0, 0, 0, 0};
+};
+static cudaError_t sim_pool_get(int device, int slot, size_t bytes, void** out) {
+    static std::map<int, SimPool> pools;          // guarded by the caller's lock
+    SimPool& sp = pools[device];
+    if (sp.cap[slot] < bytes) {
+        if (sp.p[slot]) cudaFree(sp.p[slot]);
+        sp.p[slot] = nullptr; sp.cap[slot] = 0;
+        cudaError_t e = cudaMalloc(&sp.p[slot], bytes);
+        if (e != cudaSuccess) return e;
+        sp.cap[slot] = bytes;
+    }
+    *out = sp.p[slot];
+    return cudaSuccess;
+}
+
 extern "C" int bh_simulate(int device, void* stream_, const float* in, int is_complex, int C, int N,
                            double wl, double dx, double z, int pad, int method, float* out, int on_host) {
     bh_ctx* nul = nullptr;
@@ -1063,39 +1179,30 @@ extern "C" int bh_simulate(int device, void* stream_, const float* in, int is_co
     BH_CUDA(nul, cudaSetDevice(device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
     const size_t n2 = size_t(N) * N, p2 = size_t(P) * P, cnt = size_t(C) * n2;
-    float2 *din = nullptr, *dbuf = nullptr, *dout = nullptr;
-    float* draw = nullptr;
     SimTables tabs;
     if (int rc = sim_tables(device, P, wl, dx, z, method, &tabs)) return rc;
     float2 *dH = tabs.dH, *dtw = tabs.dtw;
-    auto cleanup = [&]() { cudaFree(din); cudaFree(dbuf); cudaFree(dout); cudaFree(draw); };
-#define BH_SIM(expr)                                                          \
-    do {                                                                      \
-        cudaError_t _e = (expr);                                              \
-        if (_e != cudaSuccess) {                                              \
-            cleanup();                                                        \
-            BH_FAIL(nul, -2, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
-        }                                                                     \
-    } while (0)
-    BH_SIM(cudaMalloc(&din, cnt * sizeof(float2)));
+    static std::mutex pool_mu;                     // the call synchronises before it returns, so one
+    std::lock_guard<std::mutex> lk(pool_mu);       // caller at a time owns the pooled buffers
+    float2 *din = nullptr, *dbuf = nullptr, *dout = nullptr;
+    float* draw = nullptr;
+    BH_CUDA(nul, sim_pool_get(device, 0, cnt * sizeof(float2), reinterpret_cast<void**>(&din)));
     const cudaMemcpyKind kin = on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     if (is_complex) {
-        BH_SIM(cudaMemcpyAsync(din, in, cnt * sizeof(float2), kin, st));
+        BH_CUDA(nul, cudaMemcpyAsync(din, in, cnt * sizeof(float2), kin, st));
     } else {
-        BH_SIM(cudaMalloc(&draw, cnt * sizeof(float)));
-        BH_SIM(cudaMemcpyAsync(draw, in, cnt * sizeof(float), kin, st));
+        BH_CUDA(nul, sim_pool_get(device, 1, cnt * sizeof(float), reinterpret_cast<void**>(&draw)));
+        BH_CUDA(nul, cudaMemcpyAsync(draw, in, cnt * sizeof(float), kin, st));
         k_real_to_complex<<<std::min<size_t>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(draw, din, cnt);
     }
     float2* U = reinterpret_cast<float2*>(out);
-    if (on_host) { BH_SIM(cudaMalloc(&dout, cnt * sizeof(float2))); U = dout; }
+    if (on_host) { BH_CUDA(nul, sim_pool_get(device, 2, cnt * sizeof(float2), reinterpret_cast<void**>(&dout))); U = dout; }
     float2* buf = U;
-    if (pad == 2) { BH_SIM(cudaMalloc(&dbuf, size_t(C) * p2 * sizeof(float2))); buf = dbuf; }
+    if (pad == 2) { BH_CUDA(nul, sim_pool_get(device, 3, size_t(C) * p2 * sizeof(float2), reinterpret_cast<void**>(&dbuf))); buf = dbuf; }
     bool ok = false;
-    BH_SIM((dispatch_prop<float2, true>(P, pad, din, buf, U, dH, dtw, C, C, st, &ok)));
-    if (on_host) BH_SIM(cudaMemcpyAsync(out, dout, cnt * sizeof(float2), cudaMemcpyDeviceToHost, st));
-    BH_SIM(cudaStreamSynchronize(st));
-#undef BH_SIM
-    cleanup();
+    BH_CUDA(nul, (dispatch_prop<float2, true>(P, pad, din, buf, U, dH, dtw, C, C, st, &ok)));
+    if (on_host) BH_CUDA(nul, cudaMemcpyAsync(out, dout, cnt * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    BH_CUDA(nul, cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -1122,6 +1229,68 @@ extern "C" int bh_time_eval(bh_ctx* c, int n, const int32_t* d_env_ids, const in
     float ms = 0.f;
     BH_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     *ms_per_launch = ms / float(reps);
+    return 0;
+}
+
+// eval (+ commit) chains as the step path launches them: `reps` vectorised steps over n_sets action
+// sets, device-resident inputs; with_commit = 0 times the evaluation alone under the same rule.
+extern "C" int bh_time_step(bh_ctx* c, int n, const int32_t* d_env_ids, const int64_t* d_actions,
+                            int n_sets, int reps, int rule, int with_commit, float* ms_per_step) {
+    BH_CHECK_CTX(c);
+    if (n < 1 || n > c->max_tasks || reps < 1 || n_sets < 1 || !ms_per_step || !d_env_ids) BH_FAIL(c, -1, "bad arguments");
+    if (rule < 0 || rule > 3) BH_FAIL(c, -1, "bad rule %d", rule);
+    DeltaArgs a = make_args(c, n, 0, d_env_ids, reinterpret_cast<const long long*>(d_actions), rule, c->d_results);
+    auto step = [&](int i) {
+        a.actions = reinterpret_cast<const long long*>(d_actions) + size_t(i % n_sets) * n;
+        launch_eval(c, a);
+        if (with_commit) launch_commit(c, a);
+    };
+    for (int i = 0; i < 3; ++i) step(i);
+    BH_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i) step(i);
+    BH_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    BH_CUDA(c, cudaEventSynchronize(c->ev1));
+    BH_CUDA(c, cudaGetLastError());
+    float ms = 0.f;
+    BH_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *ms_per_step = ms / float(reps);
+    return 0;
+}
+
+// k_commit alone: n_sets result sets are prepared once (every flip marked "keep"), then `reps`
+// commit launches run back to back, launch i applying set i % n_sets (n accepted flips, 24 N^2 B
+// each).  The fields drift by the repeated additions; the environments are re-propagated from
+// their (consistent) state afterwards.
+extern "C" int bh_time_commit(bh_ctx* c, int n, const int32_t* d_env_ids, const int64_t* d_actions,
+                              int n_sets, int reps, float* ms_per_launch) {
+    BH_CHECK_CTX(c);
+    if (n < 1 || n > COMMIT_MAX_TASKS || reps < 1 || n_sets < 1 || !ms_per_launch || !d_env_ids) BH_FAIL(c, -1, "bad arguments");
+    if (size_t(n) * n_sets > size_t(c->max_tasks)) BH_FAIL(c, -1, "n * n_sets exceeds max_tasks");
+    DeltaArgs a = make_args(c, n, 0, d_env_ids, reinterpret_cast<const long long*>(d_actions), RULE_ALWAYS, c->d_results);
+    for (int i = 0; i < n_sets; ++i) {
+        DeltaArgs e = a;
+        e.actions = reinterpret_cast<const long long*>(d_actions) + size_t(i) * n;
+        e.results = c->d_results + size_t(i) * n;
+        e.acc = c->d_acc + size_t(i) * n * 2; e.tickets = c->d_tickets + size_t(i) * n;
+        launch_eval(c, e);
+    }
+    auto commit = [&](int i) {
+        DeltaArgs k = a;
+        k.results = c->d_results + size_t(i % n_sets) * n;
+        launch_commit(c, k);
+    };
+    for (int i = 0; i < 3; ++i) commit(i);
+    BH_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i) commit(i);
+    BH_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    BH_CUDA(c, cudaEventSynchronize(c->ev1));
+    BH_CUDA(c, cudaGetLastError());
+    float ms = 0.f;
+    BH_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *ms_per_launch = ms / float(reps);
+    for (int e = 0; e < c->E; ++e)
+        if (int rc = propagate_env(c, e)) return rc;
+    BH_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 

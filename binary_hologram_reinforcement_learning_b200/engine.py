@@ -13,7 +13,9 @@ import numpy as np
 
 from . import _build
 
-RULE_ENV, RULE_DBS, RULE_NEVER = 0, 1, 2
+RULE_ENV, RULE_DBS, RULE_NEVER, RULE_ALWAYS = 0, 1, 2, 3
+OBS_DEVICE, OBS_PINNED_HOST, OBS_CONTEXT = 0, 1, 2
+OBS_COMMITTED_ONLY, OBS_FULL, OBS_SYNC = 1, 2, 4
 METHOD_ASM, METHOD_FRESNEL = 0, 1
 
 # every symbol include/bholo.h declares
@@ -22,7 +24,9 @@ ABI_SYMBOLS = (
     "bh_set_target", "bh_load_state", "bh_clone_env", "bh_resync", "bh_get_metrics", "bh_eval_flips",
     "bh_step_batch", "bh_vec_step", "bh_vec_book_update", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
     "bh_commit_flip", "bh_dbs_run", "bh_sweep_all", "bh_sweep_stats", "bh_get_recon", "bh_get_state", "bh_get_field",
-    "bh_device_ptr", "bh_host_alloc", "bh_host_free", "bh_simulate", "bh_time_eval", "bh_time_propagate", "bh_time_propagate_passes", "bh_launch_count",
+    "bh_recon_batch", "bh_recon_device_block", "bh_stream_sync",
+    "bh_device_ptr", "bh_host_alloc", "bh_host_free", "bh_simulate", "bh_time_eval", "bh_time_step", "bh_time_commit",
+    "bh_time_propagate", "bh_time_propagate_passes", "bh_launch_count",
 )
 
 
@@ -95,6 +99,11 @@ def load_library(build_if_missing: bool = True):
         "bh_sweep_stats": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
         "bh_get_recon": (i32, [vp, i32, vp, i32, i64]),
         "bh_get_state": (i32, [vp, i32, vp, i32]),
+        "bh_recon_batch": (i32, [vp, i32, vp, vp, vp, i32, i32, i32]),
+        "bh_recon_device_block": (vp, [vp, i32]),
+        "bh_stream_sync": (i32, [vp]),
+        "bh_time_step": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, P(C.c_float)]),
+        "bh_time_commit": (i32, [vp, i32, vp, vp, i32, i32, P(C.c_float)]),
         "bh_get_field": (i32, [vp, i32, i32, vp, i32]),
         "bh_device_ptr": (vp, [vp, i32]),
         "bh_host_alloc": (vp, [C.c_size_t]),
@@ -140,6 +149,36 @@ def pinned_empty(shape, dtype) -> np.ndarray:
     buf = (C.c_char * max(n, 1)).from_address(blk.ptr)
     buf._pinned_owner = blk                      # keeps the block alive with the view
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+class DeviceArray:
+    """Zero-copy view of device memory owned by an engine (``__cuda_array_interface__`` v3):
+    ``torch.as_tensor(view, device="cuda")`` / ``cupy.asarray(view)`` alias it without a copy."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner=None):
+        self.ptr, self.shape, self.typestr, self._owner = int(ptr), tuple(int(v) for v in shape), typestr, owner
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": self.typestr, "data": (self.ptr, False), "version": 3,
+                "strides": None}
+
+    @property
+    def dtype(self):
+        return np.dtype(self.typestr)
+
+    def __getitem__(self, i: int) -> "DeviceArray":
+        """Sub-view along the first axis."""
+        i = int(i)
+        if not 0 <= i < self.shape[0]:
+            raise IndexError(i)
+        step = int(np.prod(self.shape[1:])) * self.dtype.itemsize
+        return DeviceArray(self.ptr + i * step, self.shape[1:], self.typestr, self._owner)
+
+    def numpy(self) -> np.ndarray:
+        """Copy to the host (debugging / tests)."""
+        import torch
+        return torch.as_tensor(self, device="cuda").cpu().numpy()
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -337,6 +376,25 @@ class HoloEngine:
                     "bh_get_recon")
         return out
 
+    def recon_batch(self, n: int, out: int, kind: int = OBS_PINNED_HOST, buffer: int = 0, flags: int = OBS_SYNC,
+                    env_ids_ptr: int = 0, d_results: int = 0):
+        """obs["recon_image"] of the ``n`` envs of the step just enqueued, written plane by plane into the
+        observation block at address ``out`` (see ``bh_recon_batch`` in include/bholo.h)."""
+        rc = self.lib.bh_recon_batch(self._h, n, env_ids_ptr or None, d_results or None, out or None,
+                                     kind, buffer, flags)
+        if rc != 0:
+            self._check(rc, "bh_recon_batch")
+
+    def recon_device_block(self, buffer: int = 0) -> "DeviceArray":
+        """Context-owned device observation block ``buffer`` as a zero-copy (E, 1, G, N, N) float32 view."""
+        ptr = self.lib.bh_recon_device_block(self._h, buffer)
+        if not ptr:
+            raise HoloError("bh_recon_device_block failed: " + self.lib.bh_last_error(self._h).decode())
+        return DeviceArray(int(ptr), (self.n_env, 1, self.G, self.N, self.N), "<f4", owner=self)
+
+    def stream_sync(self):
+        self._check(self.lib.bh_stream_sync(self._h), "bh_stream_sync")
+
     def state(self, env: int = 0) -> np.ndarray:
         out = np.empty((self.F, self.N, self.N), dtype=np.int8)
         self._check(self.lib.bh_get_state(self._h, env, _ptr(out), 1), "bh_get_state")
@@ -353,6 +411,19 @@ class HoloEngine:
         self._check(self.lib.bh_time_eval(self._h, n, C.c_void_p(d_env_ids or None),
                                           C.c_void_p(d_actions), n_sets, reps, C.byref(ms)),
                     "bh_time_eval")
+        return float(ms.value)
+
+    def time_step(self, n: int, d_env_ids: int, d_actions: int, n_sets: int, reps: int, rule: int = RULE_ENV,
+                  with_commit: bool = True) -> float:
+        ms = C.c_float(0.0)
+        self._check(self.lib.bh_time_step(self._h, n, C.c_void_p(d_env_ids), C.c_void_p(d_actions), n_sets,
+                                          reps, rule, int(with_commit), C.byref(ms)), "bh_time_step")
+        return float(ms.value)
+
+    def time_commit(self, n: int, d_env_ids: int, d_actions: int, n_sets: int, reps: int) -> float:
+        ms = C.c_float(0.0)
+        self._check(self.lib.bh_time_commit(self._h, n, C.c_void_p(d_env_ids), C.c_void_p(d_actions), n_sets,
+                                            reps, C.byref(ms)), "bh_time_commit")
         return float(ms.value)
 
     def time_propagate_passes(self, env: int, reps: int):

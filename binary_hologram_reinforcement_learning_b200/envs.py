@@ -22,7 +22,8 @@ from typing import Callable, Iterable, Optional, Sequence
 import numpy as np
 
 from . import spaces
-from .engine import HoloEngine, RULE_ENV, RESULT_DTYPE, pinned_empty
+from .engine import (HoloEngine, RULE_ENV, RESULT_DTYPE, pinned_empty, OBS_PINNED_HOST, OBS_CONTEXT,
+                     OBS_COMMITTED_ONLY, OBS_SYNC)
 
 RW = 800                                   # env.py:29
 WL_MONO = (515e-9,)                        # env.py:124
@@ -69,8 +70,11 @@ class BinaryHologramEnv(spaces.Env):
     wl             one wavelength per colour group (env_1024_24.py:135-147)
     crop_margin    env_1024_24_128.py: simulate the centre (IPS-2m)^2 window
     reward_mode    "psnr" (env.py:188) or "group" (env_group.py:254-255)
-    recon_obs      "eager": copy recon_image to the host every step (reference
-                   behaviour); "lazy": only on ``refresh_recon()``
+    recon_obs      "eager" (default, the reference's behaviour, env.py:176-181): obs["recon_image"]
+                   is current after every step -- the changed colour plane is written into a pinned
+                   host buffer by one kernel (bh_recon_batch); "device": the same, but the
+                   observation is a zero-copy view of device memory (``__cuda_array_interface__``)
+                   for a policy on the same GPU; "lazy": only on ``refresh_recon()``
     engine/env_index  share one multi-environment engine (vectorised envs)
     """
 
@@ -138,6 +142,9 @@ class BinaryHologramEnv(spaces.Env):
         self._eid = np.array([self._e], dtype=np.int32)
         self._ptrs = (self._eid.ctypes.data, self._act.ctypes.data, self._res.ctypes.data)
         self._recon_buf = None                            # pinned, allocated with the engine
+        self._vec = None                                  # set by HologramVecEnv: it refreshes all envs at once
+        if recon_obs not in ("eager", "lazy", "device"):
+            raise ValueError(f"recon_obs must be 'eager', 'lazy' or 'device', not {recon_obs!r}")
 
     # ------------------------------------------------------------------
     def _ensure_engine(self, z: float, dx: float):
@@ -153,6 +160,33 @@ class BinaryHologramEnv(spaces.Env):
     @property
     def engine(self) -> HoloEngine:
         return self._engine
+
+    # -- observation buffer ---------------------------------------------
+    def _attach_obs(self):
+        """Make ``_recon_buf`` the (1, G, Nsim, Nsim) block obs["recon_image"] aliases."""
+        if self._vec is not None:
+            self._vec._attach_env_obs(self)
+        elif self.recon_obs == "device":
+            self._recon_buf = self._engine.recon_device_block(0)[self._e]
+        elif not isinstance(self._recon_buf, np.ndarray):
+            self._recon_buf = pinned_empty((1, self.G, self.Nsim, self.Nsim), np.float32)
+
+    def _publish_recon(self, stepped: bool, reset: bool = False):
+        """Bring obs["recon_image"] up to date after a step (env.py:176-181) or a reset."""
+        if self._vec is not None:
+            if reset:
+                self._vec._env_was_reset(self)
+            return
+        if self.recon_obs == "lazy":
+            if not stepped:
+                self._engine.recon(self._e, -1, out=self._recon_buf[0])
+            return
+        flags = OBS_SYNC | (0 if stepped else OBS_COMMITTED_ONLY)
+        if self.recon_obs == "device":
+            self._engine.recon_batch(1, 0, OBS_CONTEXT, 0, flags, env_ids_ptr=self._ptrs[0])
+        else:
+            self._engine.recon_batch(1, self._recon_buf.ctypes.data, OBS_PINNED_HOST, 0, flags,
+                                     env_ids_ptr=self._ptrs[0])
 
     def _crop(self, a: np.ndarray) -> np.ndarray:
         m = self.crop_margin
@@ -180,13 +214,14 @@ class BinaryHologramEnv(spaces.Env):
             self.crop_margin = int(crop_margin)
             self.Nsim = self.IPS - 2 * self.crop_margin
             self._recon_buf = None
+            if self._vec is not None:
+                raise ValueError("crop_margin of a vectorised env is fixed at construction")
             self.observation_space.spaces["recon_image"] = spaces.Box(
                 low=0, high=1, shape=(1, self.G, self.Nsim, self.Nsim), dtype=np.float32)
         if seed is not None:
             self.rng = np.random.default_rng(seed)
         self._ensure_engine(float(z), float(pixel_pitch))
-        if self._recon_buf is None:
-            self._recon_buf = pinned_empty((1, self.G, self.Nsim, self.Nsim), np.float32)
+        self._attach_obs()
         self.episode_num_count += 1
 
         self.target_image, self.current_file = self._next_target()
@@ -218,7 +253,7 @@ class BinaryHologramEnv(spaces.Env):
         self.previous_psnr = self.initial_psnr
         self._commits = 0
         self._last_candidate = -1
-        eng.recon(e, -1, out=self._recon_buf[0])
+        self._publish_recon(False, reset=True)
 
         if self.reward_mode == "group":                               # env_group.py:190-199
             t0 = time.time()
@@ -256,9 +291,8 @@ class BinaryHologramEnv(spaces.Env):
         self.initial_psnr = self.previous_psnr = leader.initial_psnr
         self._commits, self._last_candidate = 0, -1
         self._engine.clone_env(leader._e, self._e)
-        if self._recon_buf is None:
-            self._recon_buf = pinned_empty((1, self.G, self.Nsim, self.Nsim), np.float32)
-        self._recon_buf[...] = leader._recon_buf
+        self._attach_obs()
+        self._publish_recon(False, reset=True)
         if self.reward_mode == "group":
             self.psnr_change_list, self.importance_ranks = leader.psnr_change_list, leader.importance_ranks
             self._psnr_change_arr, self.T_PSNR_DIFF = leader._psnr_change_arr, leader.T_PSNR_DIFF
@@ -274,8 +308,10 @@ class BinaryHologramEnv(spaces.Env):
                 "target_image": self.target_image_np}
 
     def refresh_recon(self) -> np.ndarray:
-        """Materialise obs["recon_image"] (the last evaluated flip included, env.py:176-181)."""
-        self._engine.recon(self._e, self._last_candidate, out=self._recon_buf[0])
+        """Materialise obs["recon_image"] (the last evaluated flip included, env.py:176-181).
+        Only needed with ``recon_obs="lazy"``; the other modes keep the observation current."""
+        if self.recon_obs == "lazy":
+            self._engine.recon(self._e, self._last_candidate, out=self._recon_buf[0])
         return self._recon_buf
 
     # -- env_group.py:90-143 --------------------------------------------
@@ -336,8 +372,7 @@ class BinaryHologramEnv(spaces.Env):
         self.state_record[0, channel, row, col] += 1                  # env.py:165
         self.flip_count += 1
         self._last_candidate = -1 if accepted else sim_action
-        if self.recon_obs == "eager":                                 # env.py:176-181
-            self.refresh_recon()
+        self._publish_recon(sim_action >= 0)                          # env.py:176-181
         obs = self._obs()
 
         psnr_change = psnr_after - self.previous_psnr                 # env.py:184-185
@@ -353,8 +388,12 @@ class BinaryHologramEnv(spaces.Env):
             return obs, reward, False, False, {}
         self.state[0, channel, row, col] = 1 - self.state[0, channel, row, col]   # env.py:164
         self._commits += 1
+        resynced_psnr = None
         if self.resync_every > 0 and self._commits % self.resync_every == 0:
+            # the device decides the next flips against the re-propagated PSNR: follow it on the host
+            # (env.py:184-196: a kept flip never has a negative change)
             self._engine.resync(self._e)
+            resynced_psnr = self._engine.metrics(self._e)[0]
 
         self.max_psnr_diff = max(self.max_psnr_diff, psnr_diff)
         success_ratio = self.flip_count / self.steps if self.steps > 0 else 0
@@ -371,7 +410,7 @@ class BinaryHologramEnv(spaces.Env):
             self.next_print_thresholds.pop(0)                         # env.py:203-212
             if self.verbose:
                 _block()
-        self.previous_psnr = psnr_after                               # env.py:214
+        self.previous_psnr = psnr_after if resynced_psnr is None else resynced_psnr   # env.py:214
 
         if psnr_diff >= self.T_PSNR_DIFF or (psnr_after >= self.T_PSNR and psnr_diff < 0.1):
             if self.verbose:
@@ -408,7 +447,6 @@ class BinaryHologramEnvRGB(BinaryHologramEnv):
     def __init__(self, target_function, trainloader, max_steps=10000, T_PSNR=30, T_steps=1,
                  T_PSNR_DIFF=0.1, **kw):
         kw.setdefault("IPS", 1024); kw.setdefault("CH", 24); kw.setdefault("wl", WL_RGB)
-        kw.setdefault("recon_obs", "lazy")
         super().__init__(target_function, trainloader, max_steps, T_PSNR, T_steps, T_PSNR_DIFF, **kw)
 
 

@@ -14,16 +14,44 @@ from typing import Callable, Iterable, List, Optional, Sequence
 
 import numpy as np
 
-from .engine import HoloEngine, RULE_ENV, RESULT_DTYPE, VecBook
+from .engine import (HoloEngine, RULE_ENV, RESULT_DTYPE, VecBook, pinned_empty, DeviceArray, OBS_PINNED_HOST,
+                     OBS_CONTEXT, OBS_COMMITTED_ONLY, OBS_SYNC)
 from .envs import BinaryHologramEnv, WL_MONO, RW, goal_bonus
+
+
+class ShardedLoader:
+    """Items ``index, index + count, ...`` of a shared, re-iterable loader: E environments built on
+    one ``trainloader`` walk disjoint images instead of E copies of the same episode."""
+
+    def __init__(self, loader, index: int, count: int):
+        self.loader, self.index, self.count = loader, int(index), int(count)
+
+    def __iter__(self):
+        n = 0
+        for k, item in enumerate(self.loader):
+            if k % self.count == self.index:
+                n += 1
+                yield item
+        if n == 0:                       # fewer images than environments: share them
+            yield from self.loader
+
+    def __getattr__(self, name):         # e.g. target_function helpers hung on the loader
+        return getattr(self.loader, name)
 
 
 class HologramVecEnv:
     def __init__(self, n_envs: int, target_function: Callable, trainloaders, max_steps=10000,
                  T_PSNR=30, T_steps=1, T_PSNR_DIFF=0.1, *, IPS=256, CH=8, wl: Sequence[float] = WL_MONO,
                  crop_margin=0, reward_mode="psnr", device=0, pad=1, relative=True, method="asm",
-                 z=2e-3, pixel_pitch=7.56e-6, obs_mode="views", recon_obs="lazy", verbose=False,
-                 seed: Optional[int] = None, resync_every: int = 1024, num_samples: int = 10000):
+                 z=2e-3, pixel_pitch=7.56e-6, obs_mode="views", recon_obs="eager", verbose=False,
+                 seed: Optional[int] = None, resync_every: int = 1024, num_samples: int = 10000,
+                 obs_buffers: int = 2):
+        """``recon_obs``: "eager" (default; the reference returns the reconstruction of the evaluated
+        flip on every step, env.py:176-181): after each step one kernel writes the changed colour
+        planes of all E envs into a pinned host block, double buffered (``obs_buffers``) so the
+        observation of step k stays valid while step k+1 runs; "device": same, zero-copy device
+        views; "lazy": only ``refresh_recon(i)`` moves data.  One ``trainloader`` is sharded over the
+        envs (env i sees items i, i+E, ...); pass a list for one loader per env."""
         self.num_envs = int(n_envs)
         self.obs_mode = obs_mode
         self.z, self.pixel_pitch = float(z), float(pixel_pitch)
@@ -31,7 +59,8 @@ class HologramVecEnv:
         self.engine = HoloEngine(nsim, CH, wl, n_env=self.num_envs, device=device, dx=pixel_pitch,
                                  z=z, pad=pad, relative=relative, method=method)
         if not isinstance(trainloaders, (list, tuple)):
-            trainloaders = [trainloaders] * self.num_envs
+            trainloaders = ([trainloaders] if self.num_envs == 1 else
+                            [ShardedLoader(trainloaders, i, self.num_envs) for i in range(self.num_envs)])
         ss = np.random.SeedSequence(seed)
         self.envs: List[BinaryHologramEnv] = [
             BinaryHologramEnv(target_function, trainloaders[i], max_steps, T_PSNR, T_steps,
@@ -59,8 +88,26 @@ class HologramVecEnv:
         self._ep_reward = np.zeros(self.num_envs)
         # vectorised bookkeeping (env.py:154-260 evaluated for all envs at once); used when no
         # per-step printing, cropping or rank-table reward is involved
-        self._fast = (crop_margin == 0 and reward_mode in ("psnr", "group") and not verbose
-                      and recon_obs != "eager")
+        self._fast = (crop_margin == 0 and reward_mode in ("psnr", "group") and not verbose)
+        # observation blocks of obs["recon_image"]: [E][1][G][nsim][nsim], written by bh_recon_batch
+        self.recon_obs = recon_obs
+        self._obs_live = recon_obs in ("eager", "device")
+        self._cur = 0
+        if self._obs_live:
+            self._n_obs = max(1, min(int(obs_buffers), 4))
+            shape = (self.num_envs, 1, len(wl), nsim, nsim)
+            if recon_obs == "device":
+                self._obs_kind = OBS_CONTEXT
+                self._blocks = [self.engine.recon_device_block(b) for b in range(self._n_obs)]
+                self._block_ptrs = [0] * self._n_obs
+            else:
+                self._obs_kind = OBS_PINNED_HOST
+                self._blocks = [pinned_empty(shape, np.float32) for _ in range(self._n_obs)]
+                self._block_ptrs = [b.ctypes.data for b in self._blocks]
+            self._views = [[blk[i] for i in range(self.num_envs)] for blk in self._blocks]
+            for env in self.envs:
+                env._vec = self
+        self._sub_eids = np.zeros(self.num_envs, dtype=np.int32)
         self._group = reward_mode == "group"
         self._changes = self._ranks = None      # (E, num_samples) tables of env_group.py:90-143
         self._sorted = [None] * self.num_envs
@@ -134,6 +181,43 @@ class HologramVecEnv:
             sv = env._psnr_change_arr[order]
             self._sorted[i] = (sv, order, np.searchsorted(sv, sv, side="left"))
 
+    # -- observation blocks ------------------------------------------------
+    def _attach_env_obs(self, env: BinaryHologramEnv):
+        env._recon_buf = self._views[self._cur][env._e]
+
+    def _env_was_reset(self, env: BinaryHologramEnv):
+        """A reset / clone re-propagated env: write its committed reconstruction into the current block."""
+        self._attach_env_obs(env)
+        self.engine.recon_batch(1, self._block_ptrs[self._cur], self._obs_kind, self._cur,
+                                OBS_SYNC | OBS_COMMITTED_ONLY, env_ids_ptr=env._ptrs[0])
+
+    def _publish_step(self, n: int, eids_ptr: int = 0, rest: Optional[np.ndarray] = None):
+        """After a step of n envs: advance to the next block and bring it up to date for every env."""
+        b = self._cur = (self._cur + 1) % self._n_obs
+        eng, ptr, kind = self.engine, self._block_ptrs[b], self._obs_kind
+        if rest is not None and rest.size:            # envs without an engine step this time (cropped-out pixels)
+            self._rest_eids = np.ascontiguousarray(rest, dtype=np.int32)
+            if n:
+                eng.recon_batch(n, ptr, kind, b, 0, env_ids_ptr=eids_ptr)
+            eng.recon_batch(int(rest.size), ptr, kind, b, OBS_SYNC | OBS_COMMITTED_ONLY,
+                            env_ids_ptr=self._rest_eids.ctypes.data)
+        else:
+            eng.recon_batch(n, ptr, kind, b, OBS_SYNC, env_ids_ptr=eids_ptr)
+        views = self._views[b]
+        for i, env in enumerate(self.envs):
+            env._recon_buf = views[i]
+            oc = self._obs_cache[i]
+            if oc is not None:
+                oc["recon_image"] = views[i]
+
+    def _terminal_obs(self, env: BinaryHologramEnv):
+        out = {}
+        for k, v in env._obs().items():
+            if isinstance(v, DeviceArray):            # host copy of the final reconstruction
+                v = self.engine.recon(env._e, env._last_candidate)[None]
+            out[k] = np.array(v)
+        return out
+
     def sync_envs(self):
         """Push the vectorised counters back into the per-env objects."""
         if not self._fast:
@@ -198,6 +282,8 @@ class HologramVecEnv:
         acts, envs, E = self._actions, self.envs, self.num_envs
         # scoring on the GPU + mirrors, counters, psnr_change, reward, event mask in one foreign call
         self.engine.vec_step_ptrs(E, self._ptrs, RULE_ENV, self._book)
+        if self._obs_live:                                           # env.py:176-181
+            self._publish_step(E, self._ptrs[0])
         res, psnr_after = self._res, self._psnr_after
         diff = self._diff
         if self._group:                                              # env_group.py:254-255
@@ -215,7 +301,9 @@ class HologramVecEnv:
             if self._resync_wait <= 0:
                 due = (res["accept"] != 0) & (self._flips % self._resync_every == 0)
                 for i in np.flatnonzero(due):
+                    # the device now decides against the re-propagated PSNR: follow it on the host
                     self.engine.resync(int(i))
+                    self._prev[i] = self.engine.metrics(int(i))[0]
                 self._resync_wait = int((self._resync_every - self._flips % self._resync_every).min())
         if self._event.tobytes() == self._no_event:
             self._ep_reward += rewards
@@ -237,7 +325,7 @@ class HologramVecEnv:
             if term or trunc:
                 dones[i] = True
                 self.sync_envs()
-                infos[i] = {"terminal_observation": {k: np.array(v) for k, v in env._obs().items()},
+                infos[i] = {"terminal_observation": self._terminal_obs(env),
                             "TimeLimit.truncated": bool(trunc and not term)}
                 self.episode_stats.append(np.array(
                     [self._ep_reward[i] + rewards[i], self._steps[i], self._flips[i], self._init[i],
@@ -258,13 +346,22 @@ class HologramVecEnv:
         if envs[0].crop_margin == 0:
             self.engine.step_batch(acts, self._eids, RULE_ENV, out=self._res)
             inside = None
+            if self._obs_live:
+                self._publish_step(self.num_envs, self._eids.ctypes.data)
         else:
             sim, inside = envs[0]._map_actions(acts)
             if inside.all():
                 self.engine.step_batch(sim, self._eids, RULE_ENV, out=self._res)
                 inside = None
-            elif inside.any():
-                self._res[inside] = self.engine.step_batch(sim[inside], self._eids[inside], RULE_ENV)
+                if self._obs_live:
+                    self._publish_step(self.num_envs, self._eids.ctypes.data)
+            else:
+                m = int(inside.sum())
+                if m:
+                    self._sub_eids[:m] = self._eids[inside]
+                    self._res[inside] = self.engine.step_batch(sim[inside], self._sub_eids[:m], RULE_ENV)
+                if self._obs_live:
+                    self._publish_step(m, self._sub_eids.ctypes.data, rest=self._eids[~inside])
             self._sim[:] = sim
         obs_list, infos = [], []
         rewards = np.empty(self.num_envs, dtype=np.float64)
@@ -282,7 +379,7 @@ class HologramVecEnv:
             if term or trunc:
                 dones[i] = True
                 info = dict(info)
-                info["terminal_observation"] = {k: np.array(v) for k, v in obs.items()}
+                info["terminal_observation"] = self._terminal_obs(env)
                 info["TimeLimit.truncated"] = bool(trunc and not term)
                 self.episode_stats.append(np.array(
                     [self._ep_reward[i], env.steps, env.flip_count, env.initial_psnr, env.previous_psnr]))

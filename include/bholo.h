@@ -32,6 +32,7 @@ typedef struct bh_ctx bh_ctx;
 #define BH_RULE_ENV   0   /* keep iff psnr_after - previous >= 0   (env.py:191)   */
 #define BH_RULE_DBS   1   /* keep iff psnr_after > previous        (DBS.py:273)   */
 #define BH_RULE_NEVER 2   /* score and revert    (dbs-1024-1024-24-6464.py:371)   */
+#define BH_RULE_ALWAYS 3  /* keep unconditionally (the "keep" branch itself, DBS.py:273-291) */
 
 /* propagation method */
 #define BH_METHOD_ASM     0
@@ -174,6 +175,35 @@ int bh_dbs_run(bh_ctx* ctx, int env, const int64_t* order, int64_t n, int k_spec
  * (env.py:176-181). */
 int bh_get_recon(bh_ctx* ctx, int env, float* out, int on_host, int64_t candidate_action);
 int bh_get_state(bh_ctx* ctx, int env, int8_t* out, int on_host);
+
+/* obs["recon_image"] of the n environments of a step in one call (env.py:176-181: the
+ * reference returns result_after.cpu().numpy() on every step; appendix B-2: a rejected step
+ * shows the reconstruction WITH the rejected flip).  out is an observation block float
+ * [E][G][N][N] indexed by ENV ID that the caller keeps between calls:
+ *   out_kind BH_OBS_PINNED_HOST  host block from bh_host_alloc; the kernel writes it over PCIe
+ *            BH_OBS_DEVICE       device block of the caller (zero-copy observation on the GPU)
+ *            BH_OBS_CONTEXT      device block `buffer` owned by the context (bh_recon_device_block)
+ * The block is kept current plane by plane: a step changes one colour plane per environment, so
+ * only that plane is rewritten, plus planes that went stale since this block was last written
+ * (a rejected flip it still shows, flips kept while another block was current, a reset).  The
+ * context tracks staleness for up to 4 blocks; `buffer` in [0,4) names the block, a caller that
+ * alternates two blocks (double buffering) passes 0,1,0,1...
+ * d_results: DEVICE records of the step that was just enqueued (NULL: the records of the last
+ * bh_step_batch / bh_vec_step).  env_ids: host, NULL = 0..n-1.
+ * flags: BH_OBS_COMMITTED_ONLY ignore the records (committed reconstruction, e.g. after a reset),
+ *        BH_OBS_FULL rewrite every plane, BH_OBS_SYNC return when the block is written. */
+#define BH_OBS_DEVICE       0
+#define BH_OBS_PINNED_HOST  1
+#define BH_OBS_CONTEXT      2
+#define BH_OBS_COMMITTED_ONLY 1
+#define BH_OBS_FULL           2
+#define BH_OBS_SYNC           4
+int bh_recon_batch(bh_ctx* ctx, int n, const int32_t* env_ids, const bh_result* d_results,
+                   float* out, int out_kind, int buffer, int flags);
+/* Device observation block `buffer` of the context, float [E][G][N][N] (allocated on first use). */
+void* bh_recon_device_block(bh_ctx* ctx, int buffer);
+/* Wait for everything enqueued on the context's stream. */
+int bh_stream_sync(bh_ctx* ctx);
 /* Field of one frame, complex64 [N][N] as interleaved floats (test hook). */
 int bh_get_field(bh_ctx* ctx, int env, int frame, float* out, int on_host);
 
@@ -199,6 +229,14 @@ int bh_simulate(int device, void* cuda_stream, const float* in, int is_complex, 
  * consecutive launches stream different frames (working set >> L2). */
 int bh_time_eval(bh_ctx* ctx, int n, const int32_t* d_env_ids, const int64_t* d_actions,
                  int n_sets, int reps, float* ms_per_launch);
+/* The step chain as bh_step_batch_device launches it (k_eval -> k_commit) for `reps` steps;
+ * with_commit = 0 times the evaluations alone under the same rule. */
+int bh_time_step(bh_ctx* ctx, int n, const int32_t* d_env_ids, const int64_t* d_actions,
+                 int n_sets, int reps, int rule, int with_commit, float* ms_per_step);
+/* k_commit alone with n kept flips per launch (24 N^2 algorithmic bytes each); re-propagates
+ * every environment afterwards. */
+int bh_time_commit(bh_ctx* ctx, int n, const int32_t* d_env_ids, const int64_t* d_actions,
+                   int n_sets, int reps, float* ms_per_launch);
 int bh_time_propagate(bh_ctx* ctx, int env, int reps, float* ms_per_launch);
 /* Per-pass split of one propagation (summed over the colour groups), ms4 =
  * {row FFT, column FFT * H * inverse column FFT, inverse row FFT, intensity + loss sums}. */

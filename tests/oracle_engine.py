@@ -29,6 +29,7 @@ class OracleEngine:
         self._target = [np.zeros((self.G, N, N)) for _ in range(n_env)]
         self._means = [None] * n_env
         self._prev = [0.0] * n_env
+        self._last = {}                      # env -> (group, mean_after) of its last REJECTED flip
         self.closed = False
 
     # -- context ---------------------------------------------------------------------------
@@ -51,6 +52,7 @@ class OracleEngine:
         self._repropagate(env)
 
     def _repropagate(self, env):
+        self._last[env] = None
         self._means[env] = O.reconstruct(self.cfg, self._state[env])
         self._prev[env] = O.score(self.cfg, self._means[env], self._target[env])[0]
 
@@ -62,6 +64,7 @@ class OracleEngine:
         self._target[dst] = self._target[src].copy()
         self._means[dst] = self._means[src].copy()
         self._prev[dst] = self._prev[src]
+        self._last[dst] = None
 
     def metrics(self, env):
         psnr, mse = O.score(self.cfg, self._means[env], self._target[env])
@@ -110,12 +113,34 @@ class OracleEngine:
             ch, r, c = self.cfg.decode(x)
             res["psnr_after"][i], res["accept"][i], res["action"][i] = psnr, int(acc), x
             res["sgn"][i] = 1 - 2 * int(self._state[e][ch, r, c])
+            self._last[e] = None if acc else (g, mean_after)
             if acc:
                 self._state[e][ch, r, c] = 1 - self._state[e][ch, r, c]
                 self._means[e][g] = mean_after
                 self._prev[e] = psnr
         self.launch_count += 2
         return res
+
+    def recon_batch(self, n, out, kind=real.OBS_PINNED_HOST, buffer=0, flags=real.OBS_SYNC, env_ids_ptr=0,
+                    d_results=0):
+        """bh_recon_batch on host memory: every plane of the listed envs is rewritten (the plane-wise
+        staleness bookkeeping is a device-side optimisation with the same visible result)."""
+        assert kind == real.OBS_PINNED_HOST and out
+        ids = (np.ctypeslib.as_array((C.c_int32 * n).from_address(env_ids_ptr)) if env_ids_ptr
+               else np.arange(n))
+        G, N = self.G, self.N
+        blk = np.ctypeslib.as_array((C.c_float * (self.n_env * G * N * N)).from_address(out))
+        blk = blk.reshape(self.n_env, G, N, N)
+        for e in ids:
+            e = int(e)
+            rec = self._means[e].copy()
+            last = self._last.get(e)
+            if last is not None and not (flags & real.OBS_COMMITTED_ONLY):
+                rec[last[0]] = last[1]
+            blk[e] = rec
+
+    def stream_sync(self):
+        pass
 
     def _views(self, n, ptrs):
         ids = np.ctypeslib.as_array((C.c_int32 * n).from_address(ptrs[0]))

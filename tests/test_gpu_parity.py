@@ -789,3 +789,76 @@ def test_bundled_list_evaluation_is_bit_identical_to_single_candidates(N, F, wl,
         assert np.array_equal(res["psnr_after"], ref)
         assert np.array_equal(res["action"], acts[:K])
     eng.close()
+
+
+# ---------------------------------------------------------------------------
+# round 2: batched observation path (bh_recon_batch), env.py:176-181
+# ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["eager", "device"])
+def test_observation_is_current_after_every_step(mode):
+    """obs["recon_image"] after EVERY step equals the oracle's reconstruction of the evaluated flip (kept or
+    rejected, appendix B-2), for every env, through the plane-wise double-buffered observation blocks; the
+    observation of step k is still intact after step k+1 (double buffering)."""
+    N, F, wl, E = 64, 6, O.WL_RGB, 3
+    loaders = [bh.SyntheticLoader(N, F, 3, seeds=(300 + i,)) for i in range(E)]
+    tf = lambda t: next(l for l in loaders if np.ascontiguousarray(t[0, 0, 0, :4]).tobytes() in l._pre).target_function(t)
+    vec = bh.HologramVecEnv(E, tf, loaders, max_steps=10 ** 6, T_PSNR_DIFF=1e9, IPS=N, CH=F, wl=wl, recon_obs=mode)
+    obs = vec.reset()
+    cfg = O.HoloConfig(N=N, F=F, wl=wl)
+    refs = []
+    for i in range(E):
+        pre, tgt = bh.synthetic_problem(N, F, 3, 300 + i)
+        e = O.OracleEnv(cfg, max_steps=10 ** 6, T_PSNR_DIFF=1e9)
+        e.reset(pre, tgt)
+        refs.append(e)
+
+    def host(x):
+        if isinstance(x, np.ndarray):
+            return x
+        import torch
+        return torch.as_tensor(x, device="cuda").cpu().numpy()
+
+    for i in range(E):
+        np.testing.assert_allclose(host(obs[i]["recon_image"])[0], refs[i].recon, atol=3e-5 * refs[i].recon.max())
+    rng = np.random.default_rng(8)
+    prev_obs, prev_copy, kept, rejected = None, None, 0, 0
+    for step in range(30):
+        acts = rng.integers(0, F * N * N, size=E)
+        obs, rewards, dones, infos = vec.step(acts)
+        if prev_obs is not None:              # step k's observation survives step k+1
+            for i in range(E):
+                assert np.array_equal(host(prev_obs[i]), prev_copy[i])
+        for i in range(E):
+            _, _, _, _, acc = refs[i].step(int(acts[i]))
+            kept += int(acc); rejected += int(not acc)
+            rec = host(obs[i]["recon_image"])
+            assert rec.shape == (1, 3, N, N)
+            np.testing.assert_allclose(rec[0], refs[i].recon, atol=3e-5 * refs[i].recon.max())
+        prev_obs = [o["recon_image"] for o in obs]
+        prev_copy = [host(p).copy() for p in prev_obs]
+    assert kept > 10 and rejected > 10
+    vec.close()
+
+
+@pytest.mark.gpu
+def test_single_env_eager_observation_and_reset():
+    """Single env (own engine), default recon_obs: the observation follows every step and a reset."""
+    N, F = 64, 8
+    ld = bh.SyntheticLoader(N, F, 1, seeds=(41, 42))
+    env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, verbose=False, max_steps=10 ** 6, T_PSNR_DIFF=1e9)
+    assert env.recon_obs == "eager"
+    cfg = O.HoloConfig(N=N, F=F)
+    rng = np.random.default_rng(3)
+    for ep, seed in enumerate((41, 42)):
+        obs, _ = env.reset()
+        pre, tgt = bh.synthetic_problem(N, F, 1, seed)
+        ref = O.OracleEnv(cfg, max_steps=10 ** 6, T_PSNR_DIFF=1e9)
+        ref.reset(pre, tgt)
+        np.testing.assert_allclose(obs["recon_image"][0], ref.recon, atol=3e-5 * ref.recon.max())
+        for _ in range(12):
+            a = int(rng.integers(0, F * N * N))
+            obs, *_ = env.step(a)
+            ref.step(a)
+            np.testing.assert_allclose(obs["recon_image"][0], ref.recon, atol=3e-5 * ref.recon.max())
+    env.close()
