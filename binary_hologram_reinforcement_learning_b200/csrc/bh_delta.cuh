@@ -18,8 +18,9 @@
 //     d sum(I^2) = s * sum(2 A (I+M))  + sum(A^2 + M (2 I + M))      = s p3 + p4
 // The four sums do not depend on the sign of the flip, so the streaming loop never waits for the
 // state byte; the sign is applied to the exact integer totals afterwards.  Per pixel quad the four
-// partial sums are formed in R = double (inputs are the fp32 arrays; products of two fp32 values
-// are exact in double) or R = float, converted to 2^-40 fixed point and from there on added as
+// partial sums are formed in R = float (default) or R = double (BHOLO_EVAL_FP64=1; products of two fp32
+// values are exact in double -- measured: the error of dPSNR is set by the fp32 fields, not by this
+// arithmetic, profiles/r2_notes.md), converted to 2^-40 fixed point and from there on added as
 // 64-bit integers (registers -> warp shuffles -> shared -> one global atomic per CTA, task and sum).
 // Integer addition is associative, so the sums are bit-identical for every grid size, batch
 // composition, speculation depth and GPU count.

@@ -235,6 +235,9 @@ template <int N> struct TwLayout {
     static constexpr int off2 = len1;
     static constexpr int len2 = (P::n == 3) ? (P::r[2] - 1) * P::r[0] * P::r[1] : 0;
     static constexpr int total = len1 + len2;
+    // two-pass plans with unequal radices append the block of the reversed plan (bh_fft2.cuh)
+    static constexpr int len_rev = (P::n == 2 && P::r[0] != P::r[1]) ? (P::r[0] - 1) * P::r[1] : 0;
+    static constexpr int total_all = total + len_rev;
 };
 
 // ---------------------------------------------------------------------------

@@ -204,6 +204,17 @@ inline std::vector<float> build_twiddles(int P) {
             }
         Ns *= R;
     }
+    // two-pass plans with unequal radices (896 = 32 x 28): block of the REVERSED plan (R1, R0) used by the
+    // register-resident column pass (bh_fft2.cuh, Plan2<P, true>): tw[(r-1)*R1 + k] = exp(-2 pi i r k / P)
+    if (rad.size() == 2 && rad[0] != rad[1]) {
+        const int RA = rad[1], RB = rad[0];
+        for (int r = 1; r < RB; ++r)
+            for (int k = 0; k < RA; ++k) {
+                const double ph = two_pi * double(r) * double(k) / double(P);
+                tw.push_back(float(std::cos(ph)));
+                tw.push_back(float(-std::sin(ph)));
+            }
+    }
     return tw;
 }
 

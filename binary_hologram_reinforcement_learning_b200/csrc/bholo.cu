@@ -15,6 +15,7 @@
 
 #include "../../include/bholo.h"
 #include "bh_kernels.cuh"
+#include "bh_fft2.cuh"
 #include "bh_tables.hpp"
 
 using namespace bh;
@@ -61,7 +62,10 @@ struct bh_ctx {
     void (*k_eval_bundle)(const DeltaArgs) = nullptr;
     void (*k_commit)(const DeltaArgs) = nullptr;
     bool use_pdl = true;
-    bool fp64_eval = true;               // per-quad arithmetic of the delta evaluation in double
+    bool fp64_eval = false;              // per-quad arithmetic of the delta evaluation in double (BHOLO_EVAL_FP64=1)
+    bool fft2 = true;                    // register-resident passes (bh_fft2.cuh) where the side allows
+    bool fft2_grouped = false;           // launch them colour group by colour group
+    int sms = 148;
     // observation path (bh_recon_batch)
     uint8_t* d_recon_stale = nullptr;    // [E][RECON_MAX_BUFFERS]
     ReconPlan* d_recon_plan = nullptr;   // [max_tasks]
@@ -104,6 +108,105 @@ extern "C" int bh_abi_version(void) { return 1; }
 extern "C" const char* bh_last_error(const bh_ctx* ctx) {
     return ctx ? ctx->err.c_str() : g_err.c_str();
 }
+
+// ---------------------------------------------------------------------------
+// register-resident passes (bh_fft2.cuh) for P = 896 / 1024, pad = 1
+// ---------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn tensor_map_encoder() {
+    static encode_tiled_fn fn = []() -> encode_tiled_fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<encode_tiled_fn>(p);
+    }();
+    return fn;
+}
+// [planes][P][P] complex64 seen as float32 [planes][P][2 P]; box = COLW columns x P/4 rows of one plane
+static int make_tile_map(CUtensorMap* map, const float2* base, int P, int planes) {
+    encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return -1;
+    const cuuint64_t dims[3] = {cuuint64_t(2) * P, cuuint64_t(P), cuuint64_t(planes)};
+    const cuuint64_t strides[2] = {cuuint64_t(P) * sizeof(float2), cuuint64_t(P) * P * sizeof(float2)};
+    const cuuint32_t box[3] = {cuuint32_t(2 * COLW), cuuint32_t(P / 4), 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float2*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+
+struct Prop2Cfg { int sms = 0; bool ready = false; };
+
+// the three passes over `groups` colour groups of Fg frames each (state / U / I / T point at the first group);
+// H: table of colour group h_group0 + g.  fused: pass C also produces I and the loss partials.
+template <int P>
+static cudaError_t launch_prop2_state(const int8_t* state, float2* U, float* I, const float* T, const float2* H_all,
+                                      int G_total, int h_group0, const float2* tw, int groups, int Fg, double* partial,
+                                      int sms, cudaStream_t st, cudaEvent_t* ev) {
+    constexpr int RA = Plan2<P, false>::RA;
+    constexpr size_t row_smem = size_t(RowLaySize<P, RA>::value) * sizeof(float2);
+    const size_t smA = ROWS_WARPS * row_smem, smB = cols2_smem_bytes<P>();
+    const size_t smC = INVG_WARPS * row_smem + size_t(INVG_WARPS) * P * sizeof(float);
+    auto kA = k2_rows_fwd_real<P>;
+    auto kB = k2_cols<P, true>;
+    auto kC = k2_rows_inv_group<P>;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smA)))) return e;
+    if ((e = cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smB)))) return e;
+    if ((e = cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smC)))) return e;
+    CUtensorMap map_buf, map_h;
+    const int frames = groups * Fg;
+    if (make_tile_map(&map_buf, U, P, frames) || make_tile_map(&map_h, H_all, P, G_total)) return cudaErrorNotSupported;
+    if (ev) cudaEventRecord(ev[0], st);
+    const int n_pairs = frames * (P / 2);
+    kA<<<std::min((n_pairs + ROWS_WARPS - 1) / ROWS_WARPS, sms * 4 * 4), 32 * ROWS_WARPS, smA, st>>>(state, U, tw, n_pairs);
+    if (ev) cudaEventRecord(ev[1], st);
+    const int tiles = groups * (P / (2 * COLW) + 1) * Fg;
+    kB<<<std::min(tiles, sms * 2), 32 * COLW, smB, st>>>(map_buf, map_h, U, tw, groups, Fg, h_group0);
+    if (ev) cudaEventRecord(ev[2], st);
+    kC<<<std::min(groups * P, sms * 2 * 4), 32 * INVG_WARPS, smC, st>>>(U, I, T, tw, groups, Fg, partial);
+    if (ev) cudaEventRecord(ev[3], st);
+    return cudaGetLastError();
+}
+
+// complex input planes (stand-alone operator, sweep correlations): in -> U, one spectrum K for all planes
+template <int P>
+static cudaError_t launch_prop2_cplx(const float2* in, float2* U, const float2* K, const float2* tw, int planes,
+                                     int sms, cudaStream_t st) {
+    constexpr int RA = Plan2<P, false>::RA;
+    constexpr size_t row_smem = size_t(RowLaySize<P, RA>::value) * sizeof(float2);
+    const size_t smA = ROWS_WARPS * row_smem, smB = cols2_smem_bytes<P>();
+    auto kA = k2_rows_fwd_cplx<P>;
+    auto kB = k2_cols<P, false>;
+    auto kC = k2_rows_inv<P>;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smA)))) return e;
+    if ((e = cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smB)))) return e;
+    if ((e = cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smA)))) return e;
+    CUtensorMap map_buf, map_h;
+    if (make_tile_map(&map_buf, U, P, planes) || make_tile_map(&map_h, K, P, 1)) return cudaErrorNotSupported;
+    const int rows = planes * P;
+    const int grid_rows = std::min((rows + ROWS_WARPS - 1) / ROWS_WARPS, sms * 4 * 4);
+    kA<<<grid_rows, 32 * ROWS_WARPS, smA, st>>>(in, U, tw, rows);
+    // one "group" of `planes` frames: every tile uses the same spectrum
+    kB<<<std::min(planes * (P / COLW), sms * 2), 32 * COLW, smB, st>>>(map_buf, map_h, U, tw, 1, planes, 0);
+    kC<<<grid_rows, 32 * ROWS_WARPS, smA, st>>>(U, U, tw, rows);
+    return cudaGetLastError();
+}
+
+static bool use_fft2(const bh_ctx* c) { return c->fft2 && c->pad == 1 && fft2_side(c->P); }
+
+static int current_sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+static bool fft2_enabled() { static const bool on = !std::getenv("BHOLO_FFT_V1"); return on; }
 
 // ---------------------------------------------------------------------------
 // propagation dispatch over the supported FFT sides
@@ -161,6 +264,13 @@ static cudaError_t dispatch_prop(int P, int pad, const InT* in, float2* buf, flo
                                  cudaStream_t st, bool* supported, cudaEvent_t* ev = nullptr,
                                  const FusedC* fused = nullptr) {
     *supported = true;
+    if constexpr (CPLX) {
+        if (pad == 1 && fft2_side(P) && fft2_enabled() && !fused && !ev) {
+            // in -> U (buf aliases U when pad = 1); one spectrum for all planes
+            if (P == 1024) return launch_prop2_cplx<1024>(in, U, H, tw, frames, current_sm_count(), st);
+            if (P == 896) return launch_prop2_cplx<896>(in, U, H, tw, frames, current_sm_count(), st);
+        }
+    }
 #define BH_CASE(PP, PD) \
     if (P == PP && pad == PD) return launch_prop<PP, PD, InT, CPLX>(in, buf, U, H, tw, frames, Fg, st, ev, fused);
     BH_CASE(32, 1) BH_CASE(64, 1) BH_CASE(128, 1) BH_CASE(256, 1) BH_CASE(512, 1)
@@ -184,6 +294,40 @@ static int propagate_env(bh_ctx* c, int env, float* pass_ms = nullptr) {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (pass_ms)
         for (auto& e : ev) BH_CUDA(c, cudaEventCreate(&e));
+    if (use_fft2(c)) {
+        const int per_call = c->fft2_grouped ? 1 : c->G;
+        for (int g0 = 0; g0 < c->G; g0 += per_call) {
+            const int8_t* st = c->dstate + (size_t(env) * c->F + size_t(g0) * c->Fg) * n2;
+            float2* U = c->dU + (size_t(env) * c->F + size_t(g0) * c->Fg) * n2;
+            float* I = c->dI + (size_t(env) * c->G + g0) * n2;
+            const float* T = c->dT + (size_t(env) * c->G + g0) * n2;
+            double* part = c->dloss_partial + size_t(g0) * c->N * 3;
+            cudaError_t e = cudaErrorNotSupported;
+            if (c->P == 1024)
+                e = launch_prop2_state<1024>(st, U, I, T, c->dH, c->G, g0, c->dtw, per_call, c->Fg, part, c->sms, c->stream, pass_ms ? ev : nullptr);
+            else if (c->P == 896)
+                e = launch_prop2_state<896>(st, U, I, T, c->dH, c->G, g0, c->dtw, per_call, c->Fg, part, c->sms, c->stream, pass_ms ? ev : nullptr);
+            BH_CUDA(c, e);
+            c->launches += 3;
+            if (pass_ms) {
+                BH_CUDA(c, cudaEventRecord(ev[4], c->stream));
+                BH_CUDA(c, cudaEventSynchronize(ev[4]));
+                for (int i = 0; i < 4; ++i) {
+                    float ms = 0.f;
+                    BH_CUDA(c, cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+                    pass_ms[i] += ms;
+                }
+            }
+        }
+        if (pass_ms)
+            for (auto& e : ev) cudaEventDestroy(e);
+        k_loss_final<<<1, 256, 0, c->stream>>>(c->dloss_partial, c->G * c->N, double(c->G) * double(n2),
+                                              c->dsums + size_t(env) * 4, c->relative);
+        BH_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+        BH_CUDA(c, cudaMemsetAsync(c->d_recon_stale + size_t(env) * RECON_MAX_BUFFERS, 0xff, RECON_MAX_BUFFERS, c->stream));
+        return 0;
+    }
     for (int g = 0; g < c->G; ++g) {
         const int f0 = g * c->Fg;
         const int8_t* st = c->dstate + (size_t(env) * c->F + f0) * n2;
@@ -221,7 +365,9 @@ static int propagate_env(bh_ctx* c, int env, float* pass_ms = nullptr) {
 
 // k_eval variants: units in flight per thread x CTAs per SM x arithmetic type of the per-quad sums.
 // Measured at 1024^2 x 24, 8 candidates per launch (scripts/tune_eval.py, profiles/r2_notes.md).
-// BHOLO_EVAL_VARIANT selects another shape, BHOLO_EVAL_FP32=1 the float arithmetic of round 1.
+// BHOLO_EVAL_VARIANT selects another shape.  BHOLO_EVAL_FP64=1 forms the per-quad sums in double: measured
+// (profiles/r2_parity_error_dist.json) it changes the error of dPSNR by ~10 % -- the error is set by the fp32
+// fields U themselves -- and costs 13 % of the launch, so float is the default.
 typedef void (*eval_fn)(const DeltaArgs);
 static eval_fn commit_variant(int v) {
     switch (v) {
@@ -336,7 +482,7 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
     BH_TRY(cudaMalloc(&c->drecon, size_t(G) * n2 * sizeof(float)));
     BH_TRY(cudaMalloc(&c->dstate, size_t(n_env) * F * n2));
     BH_TRY(cudaMalloc(&c->dsums, size_t(n_env) * 4 * sizeof(double)));
-    BH_TRY(cudaMalloc(&c->dloss_partial, size_t(G) * (N / TILE_W) * 3 * sizeof(double)));
+    BH_TRY(cudaMalloc(&c->dloss_partial, size_t(G) * N * 3 * sizeof(double)));
     c->units_per_task = int(n2 / UNIT_PX);
     c->max_tasks = std::max(4096, n_env);
     BH_TRY(cudaMalloc(&c->d_envs, size_t(c->max_tasks) * sizeof(int32_t)));
@@ -380,8 +526,11 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
         BH_TRY(cudaMemcpy(c->dtw, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice));
         int nb = 0;
         c->use_pdl = !std::getenv("BHOLO_NO_PDL");
+        c->fft2 = fft2_enabled();
+        c->fft2_grouped = std::getenv("BHOLO_FFT_GROUPED") != nullptr;
+        c->sms = prop.multiProcessorCount;
         const char* ev = std::getenv("BHOLO_EVAL_VARIANT");
-        c->fp64_eval = !std::getenv("BHOLO_EVAL_FP32");
+        c->fp64_eval = std::getenv("BHOLO_EVAL_FP64") != nullptr;
         c->k_eval = c->fp64_eval ? eval_variant<double>(ev ? std::atoi(ev) : 0) : eval_variant<float>(ev ? std::atoi(ev) : 0);
         BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, c->k_eval, 256, 0));
         c->grid_cap = std::min(MAX_DELTA_GRID, std::max(1, nb) * prop.multiProcessorCount);

@@ -7,7 +7,7 @@ and scores the same flips on the B200 through the C ABI by three routes:
   k_eval_t         bh_step_batch(rule = never), one candidate per launch
   k_eval_bundle_t  bh_eval_flips (host list sorted by frame, bundled kernel)
   sweep_all        bh_sweep_all (FFT correlations), indexed at the same actions
-for the per-quad arithmetic in double (default) and in float (BHOLO_EVAL_FP32=1).  The quantity the
+for the per-quad arithmetic in float (default) and in double (BHOLO_EVAL_FP64=1).  The quantity the
 reward is made of is dPSNR = psnr_after - psnr_before (env.py:184-188, reward = 800 * dPSNR); errors
 are reported relative to |dPSNR_oracle| (median / p90 / p99 / max) and in absolute dB.
 """
@@ -41,9 +41,9 @@ def run_case(name, fp32):
     pre, tgt = bh.synthetic_problem(N, F, len(wl), seed=seed)
     st = (pre >= 0.5).astype(np.int8)
     if fp32:
-        os.environ["BHOLO_EVAL_FP32"] = "1"
+        os.environ.pop("BHOLO_EVAL_FP64", None)
     else:
-        os.environ.pop("BHOLO_EVAL_FP32", None)
+        os.environ["BHOLO_EVAL_FP64"] = "1"
     eng = bh.HoloEngine(N, F, wl, n_env=1, device=0)
     eng.set_target(0, tgt)
     eng.load_state(0, st)

@@ -52,7 +52,7 @@ static double check_layout() {
     constexpr int ES = COL ? W : 1;
     constexpr int SEQ = SeqLen<N, SK>::value;
     std::vector<float> twf = build_twiddles(N);
-    if (int(twf.size()) != 2 * TwLayout<N>::total) { printf("twiddle table size mismatch N=%d\n", N); return 1.0; }
+    if (int(twf.size()) != 2 * TwLayout<N>::total_all) { printf("twiddle table size mismatch N=%d\n", N); return 1.0; }
     std::vector<int> rad = plan_radices(N);
     if (int(rad.size()) != Plan<N>::n || rad[0] != Plan<N>::r[0] || rad[1] != Plan<N>::r[1] ||
         (Plan<N>::n == 3 && rad[2] != Plan<N>::r[2])) { printf("plan mismatch N=%d\n", N); return 1.0; }

@@ -1,8 +1,17 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
 
 Tolerances (BASELINE.json north_star): PSNR within 1e-3 dB, per-step reward within
-1e-5 relative (of the reward scale of the step, with an absolute floor for the
-fp32 fields), accept/reject sequences identical except documented near-ties.
+1e-5 relative, accept/reject sequences identical except documented near-ties.
+
+The reward is 800 * dPSNR (env.py:184-188).  Measured against the float64 oracle over 2048 random flips per
+BASELINE shape (profiles/r2_parity_error_dist.json, scripts/parity_error_dist.py): the relative error of dPSNR has
+median 4e-7, p90 2.5e-6, p99 2e-5; what is left above 1e-5 relative are flips whose dPSNR is itself tiny, with an
+ABSOLUTE error of at most 4e-12 dB at 1024^2 x 24 (1.1e-10 dB at 256^2 x 8).  That error is set by the fp32
+storage of the fields U (6e-8 relative per element, summed in quadrature over the support of the impulse
+response and divided by n * mse with n = G N^2), not by the kernel arithmetic -- forming the per-quad sums in
+double changes it by 10 %.  The asserted bound is therefore
+    |dPSNR_gpu - dPSNR_oracle| <= 1e-5 |dPSNR_oracle| + DPSNR_C / (G N^2)   dB,   DPSNR_C = 3e-5
+(9.5e-12 dB at 1024^2 x 3, i.e. 7.6e-9 reward units; 20 000 x below the floor round 1 used).
 """
 import os
 
@@ -17,7 +26,21 @@ from oracle import hologram_oracle as O
 from tests.golden import make_golden as MG
 
 PSNR_TOL = 1e-3          # dB, north_star
-NEAR_TIE = 2e-6          # |dPSNR| (dB) below which fp32 fields may flip a decision
+DPSNR_C = 3e-5           # see the module docstring
+
+
+def dpsnr_floor(N, G):
+    """Absolute error bound (dB) of one flip's dPSNR from the fp32 fields."""
+    return DPSNR_C / (G * N * N)
+
+
+def reward_tol(r_ref, N, G):
+    return 1e-5 * abs(r_ref) + 800.0 * dpsnr_floor(N, G)
+
+
+def near_tie(N, G):
+    """|dPSNR| (dB) below which the fp32 fields may flip an accept decision."""
+    return 4.0 * dpsnr_floor(N, G)
 
 
 def _problem(N, F, wl, seed):
@@ -148,9 +171,11 @@ def test_sweep_all_correlation_matches_oracle_and_delta_kernel(N, F, wl, relativ
 # ---------------------------------------------------------------------------
 # golden fixtures (tests/golden/*.npz, made by the float64 oracle)
 # ---------------------------------------------------------------------------
-def _decisions_equal_up_to_near_ties(acc, acc_ref, delta_ref):
+def _decisions_equal_up_to_near_ties(acc, acc_ref, delta_ref, N, G):
+    """Greedy runs keep thousands of flips without re-propagating; the incrementally updated fields collect
+    one fp32 rounding per kept flip and frame, so the near-tie band of a long run is wider than one flip's."""
     bad = np.flatnonzero(np.asarray(acc, bool) != np.asarray(acc_ref, bool))
-    return all(abs(delta_ref[i]) < NEAR_TIE for i in bad), bad
+    return all(abs(delta_ref[i]) < 25.0 * dpsnr_floor(N, G) for i in bad), bad
 
 
 @pytest.mark.parametrize("name", list(MG.CASES))
@@ -173,10 +198,10 @@ def test_golden_env_trajectory(name, golden_dir):
         assert isinstance(r, float) and isinstance(term, bool) and isinstance(trunc, bool)
         got_acc = env.flip_count == flips_before + 1      # kept flips count (env.py:167,194)
         if got_acc != acc_ref:
-            assert abs(d_ref) < NEAR_TIE, (i, d_ref)
+            assert abs(d_ref) < near_tie(N, len(wl)), (i, d_ref)
             pytest.skip("near-tie divergence: trajectories legitimately differ from here")
         r_ref = float(g["env_rewards"][i])
-        assert abs(r - r_ref) <= 1e-5 * abs(r_ref) + 800 * 2e-7, (i, r, r_ref)
+        assert abs(r - r_ref) <= reward_tol(r_ref, N, len(wl)), (i, r, r_ref)
         assert term == bool(g["env_terminated"][i])
         if acc_ref:
             prev = float(g["env_psnr"][i])
@@ -199,7 +224,7 @@ def test_golden_dbs_greedy(name, k_spec, golden_dir):
     ref_acc, ref_trace = g["dbs_accepted"], g["dbs_trace"]
     prev = np.concatenate([[float(g["initial_psnr"])], ref_trace[:-1]])
     running = np.maximum.accumulate(np.concatenate([[float(g["initial_psnr"])], np.where(ref_acc, ref_trace, -np.inf)]))[:-1]
-    ok, bad = _decisions_equal_up_to_near_ties(acc, ref_acc, ref_trace - running)
+    ok, bad = _decisions_equal_up_to_near_ties(acc, ref_acc, ref_trace - running, N, len(wl))
     assert ok, bad
     if bad.size == 0:
         np.testing.assert_allclose(trace, ref_trace, rtol=0, atol=1e-4)
@@ -221,7 +246,7 @@ def test_golden_sweep(name, golden_dir):
     np.testing.assert_allclose(r["psnr_after"], g["sweep_psnr"], rtol=0, atol=1e-4)
     assert np.array_equal(r["attempted"], g["sweep_attempted"])
     d_ref = g["sweep_psnr"] - float(g["initial_psnr"])
-    if np.all(np.abs(d_ref) > NEAR_TIE):
+    if np.all(np.abs(d_ref) > near_tie(N, len(wl))):
         assert np.array_equal(r["improved"], g["sweep_improved"])
         np.testing.assert_allclose(r["gains"], g["sweep_gain"], rtol=1e-4, atol=1e-7)
     eng.close()
@@ -251,7 +276,7 @@ def test_vec_env_matches_independent_oracle_envs():
         obs, rewards, dones, infos = vec.step(acts)
         for i in range(E):
             r, term, trunc, p, acc = refs[i].step(int(acts[i]))
-            assert abs(rewards[i] - r) <= 1e-5 * abs(r) + 800 * 2e-7
+            assert abs(rewards[i] - r) <= reward_tol(r, N, len(wl))
             assert not dones[i]
     vec.sync_envs()
     for i in range(E):
@@ -288,7 +313,7 @@ def test_vec_env_episode_end_bonus_and_autoreset(verbose, capsys):
         obs, rewards, dones, infos = vec.step(acts)
         for i in range(E):
             r, term, trunc, p, acc = refs[i].step(int(acts[i]))
-            assert abs(rewards[i] - r) <= 1e-5 * abs(r) + 800 * 2e-7, (step, i, rewards[i], r)
+            assert abs(rewards[i] - r) <= reward_tol(r, N, len(wl)), (step, i, rewards[i], r)
             assert bool(dones[i]) == bool(term or trunc)
             if dones[i]:
                 n_done += 1
@@ -538,9 +563,9 @@ def test_large_golden(name, golden_dir):
     # sweep: delta kernel and correlation map against the oracle
     d_ref = g["sweep_psnr"] - float(g["initial_psnr"])
     d_eval = eng.eval_flips(g["sweep_order"]) - psnr0
-    np.testing.assert_allclose(d_eval, d_ref, rtol=2e-4, atol=2e-9)
+    assert np.all(np.abs(d_eval - d_ref) <= 1e-5 * np.abs(d_ref) + dpsnr_floor(N, G))
     d_map = eng.sweep_all(0).reshape(-1)[g["sweep_order"]] - psnr0
-    np.testing.assert_allclose(d_map, d_ref, rtol=5e-4, atol=5e-9)
+    assert np.all(np.abs(d_map - d_ref) <= 3e-5 * np.abs(d_ref) + 3.5 * dpsnr_floor(N, G))
     # greedy DBS prefix on a second context (the env keeps its own state for the trajectory)
     eng2 = bh.HoloEngine(N, F, wl)
     pre, tgt = bh.synthetic_problem(N, F, G, seed)
@@ -549,7 +574,7 @@ def test_large_golden(name, golden_dir):
     acc, tr, nacc, fin = eng2.dbs_run(g["dbs_order"], trace=True)
     prev = np.maximum.accumulate(np.concatenate([[float(g["initial_psnr"])],
                                                  np.where(g["dbs_accepted"], g["dbs_trace"], -np.inf)]))[:-1]
-    ok, bad = _decisions_equal_up_to_near_ties(acc, g["dbs_accepted"], g["dbs_trace"] - prev)
+    ok, bad = _decisions_equal_up_to_near_ties(acc, g["dbs_accepted"], g["dbs_trace"] - prev, N, G)
     assert ok, bad
     if bad.size == 0:
         np.testing.assert_allclose(tr, g["dbs_trace"], rtol=0, atol=1e-4)
@@ -562,10 +587,10 @@ def test_large_golden(name, golden_dir):
         obs, r, term, trunc, _ = env.step(int(a))
         acc_ref = bool(g["env_accepted"][i])
         if (env.flip_count == flips_before + 1) != acc_ref:
-            assert abs(float(g["env_psnr"][i]) - prev) < NEAR_TIE, i
+            assert abs(float(g["env_psnr"][i]) - prev) < near_tie(N, G), i
             break                                            # legitimately diverged on a near-tie
         r_ref = float(g["env_rewards"][i])
-        assert abs(r - r_ref) <= 1e-5 * abs(r_ref) + 800 * 2e-7, (i, r, r_ref)
+        assert abs(r - r_ref) <= reward_tol(r_ref, N, G), (i, r, r_ref)
         assert term == bool(g["env_terminated"][i])
         if acc_ref:
             prev = float(g["env_psnr"][i])
@@ -593,10 +618,8 @@ def test_large_golden_dbs64_exhaustive(golden_dir):
     eng.close()
 
 
-@pytest.mark.skipif(not os.environ.get("BHOLO_LONG_TESTS"), reason="long run: set BHOLO_LONG_TESTS=1")
 def test_large_golden_dbs256_first_50k(golden_dir):
-    """first 50 000 candidates of the greedy DBS of a 256^2 x 8 stack (DBS.py:243-294).
-    Opt-in (BHOLO_LONG_TESTS=1): generated after the last GPU session of round 1, not yet run on a B200."""
+    """first 50 000 candidates of the greedy DBS of a 256^2 x 8 stack (DBS.py:243-294)."""
     g = _need(golden_dir, "large_dbs256_50k")
     N, F, seed = 256, 8, 61
     pre, tgt, st = _problem(N, F, O.WL_MONO, seed)
@@ -713,7 +736,7 @@ def test_group_rollouts_from_cloned_reset_state():
     N, F, E, M = 64, 8, 6, 3
     loaders = [bh.SyntheticLoader(N, F, 1, seeds=(500 + i // M,)) for i in range(E)]
     tf = lambda t: next(l for l in loaders if np.ascontiguousarray(t[0, 0, 0, :4]).tobytes() in l._pre).target_function(t)
-    kw = dict(max_steps=10 ** 6, T_PSNR_DIFF=1e9, IPS=N, CH=F)
+    kw = dict(max_steps=10 ** 6, T_PSNR_DIFF=1e9, IPS=N, CH=F, recon_obs="lazy")   # count propagation launches only
     grp = bh.HologramVecEnv(E, tf, loaders, **kw)
     ind = bh.HologramVecEnv(E, tf, [bh.SyntheticLoader(N, F, 1, seeds=(500 + i // M,)) for i in range(E)], **kw)
     launches0 = grp.engine.launch_count
@@ -862,3 +885,82 @@ def test_single_env_eager_observation_and_reset():
             ref.step(a)
             np.testing.assert_allclose(obs["recon_image"][0], ref.recon, atol=3e-5 * ref.recon.max())
     env.close()
+
+
+# ---------------------------------------------------------------------------
+# round 2: reward parity at the documented bound, fixed-point range
+# ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mono256", "rgb896", "rgb1024"])
+def test_reward_parity_bound(name, golden_dir):
+    """dPSNR (reward / 800, env.py:184-188) of 2048 random flips per BASELINE shape against the float64 oracle
+    (tests/golden/make_flip_oracle.py), through k_eval_t, k_eval_bundle_t and bh_sweep_all: every flip inside
+    1e-5 |dPSNR| + DPSNR_C / (G N^2) dB, and the distribution of the relative error as measured
+    (profiles/r2_parity_error_dist.json): median < 1.5e-6, p90 < 8e-6, p99 < 8e-5."""
+    path = os.path.join(golden_dir, f"flips_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture missing: python tests/golden/make_flip_oracle.py")
+    d = np.load(path)
+    N, F, wl, seed = int(d["N"]), int(d["F"]), tuple(float(w) for w in d["wl"]), int(d["seed"])
+    G = len(wl)
+    pre, tgt, st = _problem(N, F, wl, seed)
+    eng = _engine(N, F, wl)
+    eng.set_target(0, tgt)
+    eng.load_state(0, st)
+    psnr0 = eng.metrics(0)[0]
+    assert abs(psnr0 - float(d["psnr0"])) < 1e-5
+    acts, ref = d["actions"], d["psnr_after"] - float(d["psnr0"])
+    floor = dpsnr_floor(N, G)
+    zero = np.zeros(1, np.int32)
+    single = np.array([eng.step_batch(acts[i:i + 1], zero, RULE_NEVER)["psnr_after"][0] for i in range(512)])
+    listed = eng.eval_flips(acts)
+    assert np.array_equal(listed[:512], single)                      # k_eval_t == k_eval_bundle_t, bit for bit
+    err = np.abs((listed - psnr0) - ref)
+    assert np.all(err <= 1e-5 * np.abs(ref) + floor), float((err - 1e-5 * np.abs(ref)).max() / floor)
+    rel = err / np.abs(ref)
+    assert np.median(rel) < 1.5e-6 and np.quantile(rel, 0.9) < 8e-6 and np.quantile(rel, 0.99) < 8e-5
+    # decisions of the env rule (keep iff dPSNR >= 0) agree wherever the oracle is outside the near-tie band
+    clear = np.abs(ref) > near_tie(N, G)
+    assert np.array_equal(((listed - psnr0) >= 0)[clear], (ref >= 0)[clear])
+    sw = eng.sweep_all(0).reshape(-1)[acts] - psnr0
+    assert np.all(np.abs(sw - ref) <= 3e-5 * np.abs(ref) + 3.5 * floor)
+    # the change of the loss sums themselves (relative to the largest change seen)
+    res = np.concatenate([eng.step_batch(acts[i:i + 1], zero, RULE_NEVER) for i in range(256)])
+    for key in ("d_sii", "d_sit"):
+        scale = np.abs(d[key][:256]).max()
+        assert np.abs(res[key] - d[key][:256]).max() < 2e-6 * scale
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_fixed_point_range_dark_target_and_tiny_fields():
+    """The 2^-40 fixed-point sums of the delta kernels (bh_delta.cuh): per-quad terms far below 2^-41 round
+    to zero, so a pathological case -- an almost black target (1e-4) and a state with a single lit pixel per
+    frame (|U| ~ |h| ~ 1e-2, |dI| ~ 1e-5) -- must stay inside the documented absolute bound N^2 * 2^-43 on
+    both sums, and the PSNR change inside the usual band."""
+    N, F = 256, 8
+    cfg = O.HoloConfig(N=N, F=F)
+    rng = np.random.default_rng(17)
+    tgt = (1e-4 * rng.random((1, N, N))).astype(np.float32)
+    st = np.zeros((F, N, N), np.int8)
+    for f in range(F):
+        st[f, rng.integers(0, N), rng.integers(0, N)] = 1
+    eng = _engine(N, F, O.WL_MONO)
+    eng.set_target(0, tgt)
+    eng.load_state(0, st)
+    U = O.propagate_group(cfg, st, 0)
+    I = O.group_mean_intensity(U)
+    t64 = tgt.astype(np.float64)
+    sii, sit, stt = O.loss_sums(I[None], t64)
+    acts = rng.integers(0, F * N * N, size=64)
+    zero = np.zeros(1, np.int32)
+    bound = N * N * 2.0 ** -43
+    for a in acts:
+        f, r, c = cfg.decode(int(a))
+        s = 1 - 2 * int(st[f, r, c])
+        d_sii, d_sit, _ = O.delta_terms(cfg, U[f], I, t64[0], 0, r, c, s)
+        res = eng.step_batch(np.array([a]), zero, RULE_NEVER)[0]
+        # fp32 fields contribute a relative error; the fixed-point rounding the absolute one
+        assert abs(res["d_sii"] - d_sii) <= 2e-6 * abs(d_sii) + bound, (res["d_sii"], d_sii)
+        assert abs(res["d_sit"] - d_sit) <= 2e-6 * abs(d_sit) + bound, (res["d_sit"], d_sit)
+    eng.close()
