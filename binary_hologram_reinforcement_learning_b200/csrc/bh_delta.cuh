@@ -871,6 +871,7 @@ struct ReconArgs {
     const int32_t* envs;          // device env ids or nullptr (identity / inline)
     int n_inline; int inl_envs[32];
     uint8_t* stale;               // [E][RECON_MAX_BUFFERS]
+    unsigned long long* planes_written;   // running count of planes written (bytes accounting of the bench)
     ReconPlan* plan;              // [n_tasks]
     float* out;                   // [E][G][N][N]
     int n_tasks, E, N, P, HP, F, G, Fg, buffer, full;
@@ -899,6 +900,7 @@ k_recon_plan(const ReconArgs a) {
         }
         pl.mask = mask;
         *sm = uint8_t(after);
+        if (a.planes_written) atomicAdd(a.planes_written, (unsigned long long)__popc(mask));
         a.plan[k] = pl;
     }
 }

@@ -504,6 +504,7 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
     BH_TRY(cudaEventCreate(&c->ev1));
     BH_TRY(cudaEventCreateWithFlags(&c->ev_eval, cudaEventDisableTiming));
     if (rc == 0) {
+        BH_TRY(cudaMemset(c->d_scalars, 0, 4 * sizeof(long long)));
         BH_TRY(cudaMemset(c->d_tickets, 0, size_t(c->max_tasks) * sizeof(unsigned)));
         BH_TRY(cudaMemset(c->d_acc, 0, size_t(c->max_tasks) * 2 * sizeof(unsigned long long)));
         BH_TRY(cudaMemset(c->dsums, 0, size_t(n_env) * 4 * sizeof(double)));
@@ -912,7 +913,7 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
         if (psnr_trace) BH_DBS(cudaMalloc(&d_trace, size_t(n) * sizeof(double)));
         BH_DBS(cudaMemcpyAsync(d_order, order, size_t(n) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
         BH_DBS(cudaMemsetAsync(d_acc, 0, size_t(n), c->stream));
-        BH_DBS(cudaMemsetAsync(c->d_scalars, 0, 4 * sizeof(long long), c->stream));
+        BH_DBS(cudaMemsetAsync(c->d_scalars, 0, 2 * sizeof(long long), c->stream));
         const int kmax = std::min(SORT_WINDOW_MAX, c->max_tasks);
         int K = k_spec > 0 ? std::min(k_spec, c->max_tasks) : 2;
         const int iters_per_sync = 32;
@@ -1225,6 +1226,7 @@ extern "C" int bh_recon_batch(bh_ctx* c, int n, const int32_t* env_ids, const bh
         BH_FAIL(c, -3, "n=%d tasks but only %d environments", n, c->E);
     }
     a.stale = c->d_recon_stale; a.plan = c->d_recon_plan; a.out = dst;
+    a.planes_written = reinterpret_cast<unsigned long long*>(c->d_scalars + 2);
     a.n_tasks = n; a.E = c->E; a.N = c->N; a.P = c->P; a.HP = h_stride(c->P); a.F = c->F; a.G = c->G; a.Fg = c->Fg;
     a.buffer = buffer; a.full = (flags & BH_OBS_FULL) ? 1 : 0;
     k_recon_plan<<<1, 256, 0, c->stream>>>(a);
@@ -1237,6 +1239,14 @@ extern "C" int bh_recon_batch(bh_ctx* c, int n, const int32_t* env_ids, const bh
         BH_CUDA(c, cudaEventSynchronize(c->ev_recon));
     }
     return 0;
+}
+
+extern "C" int64_t bh_recon_planes_written(bh_ctx* c) {
+    if (!c || cudaSetDevice(c->device) != cudaSuccess) return -1;
+    long long v = 0;
+    if (cudaMemcpyAsync(&v, c->d_scalars + 2, sizeof v, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    return v;
 }
 
 extern "C" int bh_stream_sync(bh_ctx* c) {

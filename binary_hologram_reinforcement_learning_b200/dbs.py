@@ -156,10 +156,12 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, crop_mar
                    checkpoint: Optional[str] = None, max_segments: Optional[int] = None) -> List[dict]:
     """DBS.py:202-307 / DBS_1024_24.py:206-469 on the device-resident engine.
 
-    ``checkpoint``: path of an .npz written after every segment (binary state, candidate
-    order, cursor, decisions so far).  If it exists when an image starts and holds the same
-    order, the run resumes from its cursor instead of starting over -- the reference keeps
-    nothing but the before/after reconstructions (DBS_1024_24.py:282-287,446-451).
+    ``checkpoint``: path of an .npz written after every segment (image number, binary state,
+    candidate order, cursor, decisions so far).  A later call with the same path skips the
+    images that were already finished, and continues the image in progress from its cursor
+    WITH THE STORED ORDER (a freshly drawn permutation would never match it) -- the reference keeps
+    nothing but the before/after reconstructions (DBS_1024_24.py:282-287,446-451).  An explicit
+    ``order`` must equal the stored one, otherwise the image starts over.
     ``max_segments`` bounds the work of one call (the result then has ``complete = False``
     and a later call with the same checkpoint continues).
     ``crop_margin`` (DBS_1024_24-128.py:187): optimise the centre window only; passed to
@@ -170,9 +172,18 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, crop_mar
     """
     results = []
     db_num = 0
+    segments_run, out_of_budget = 0, False               # max_segments bounds the whole call
     stats = (env.G > 1) if range_stats is None else bool(range_stats)
     if max_datasets is None:
         max_datasets = 800 if env.G == 1 else 10          # DBS.py:205, DBS_1024_24.py:208
+    if checkpoint and os.path.exists(checkpoint):
+        # a restarted process begins at the loader's first image again: skip what the checkpoint has finished
+        with np.load(checkpoint) as ck0:
+            done_images = (int(ck0["db_num"]) - (0 if int(ck0["image_done"]) else 1)) if "db_num" in ck0.files else 0
+        for _ in range(max(0, done_images)):
+            env._next_target()
+            env.episode_num_count += 1
+            db_num += 1
     while db_num <= max_datasets:                         # DBS.py:208 (runs max+1 images)
         try:
             obs, info = env.reset(z=z, pixel_pitch=pixel_pitch, crop_margin=crop_margin)
@@ -208,8 +219,12 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, crop_mar
         start = 0
         if checkpoint and os.path.exists(checkpoint):
             ck = np.load(checkpoint)
-            if (ck["fname"].item() == file_name and ck["order"].shape == perm.shape
-                    and np.array_equal(ck["order"], perm)):
+            same_image = ck["fname"].item() == file_name and not ("image_done" in ck.files and int(ck["image_done"]))
+            if same_image and order is None and (max_candidates is None or ck["order"].shape[0] == max_candidates):
+                perm = ck["order"]                         # adopt the stored order of the image in progress
+                accepted = np.zeros(perm.shape[0], dtype=np.uint8)
+                trace = np.zeros(perm.shape[0], dtype=np.float64)
+            if same_image and ck["order"].shape == perm.shape and np.array_equal(ck["order"], perm):
                 start = int(ck["cursor"])
                 accepted[:start], trace[:start] = ck["accepted"][:start], ck["trace"][:start]
                 eng.load_state(e, ck["state"])             # re-propagates from the saved hologram
@@ -221,9 +236,11 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, crop_mar
         done_upto = start
         stopped = False
         seg_len = segment if psnr_diff_threshold is None else min(segment, 4096)
-        for seg_i, lo in enumerate(range(start, perm.shape[0], seg_len)):
-            if max_segments is not None and seg_i >= max_segments:
+        for lo in range(start, perm.shape[0], seg_len):
+            if max_segments is not None and segments_run >= max_segments:
+                out_of_budget = True
                 break
+            segments_run += 1
             hi = min(perm.shape[0], lo + seg_len)
             state_before = eng.state(e) if psnr_diff_threshold is not None else None
             acc, tr, nacc, psnr_now = eng.dbs_run(perm[lo:hi], env=e, k_spec=k_spec,
@@ -268,7 +285,8 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, crop_mar
             if checkpoint:
                 tmp = checkpoint + ".tmp.npz"
                 np.savez_compressed(tmp, fname=np.array(file_name), order=perm, cursor=np.array(hi),
-                                    accepted=accepted, trace=trace, state=eng.state(e))
+                                    accepted=accepted, trace=trace, state=eng.state(e), db_num=np.array(db_num),
+                                    image_done=np.array(int(hi == perm.shape[0])))
                 os.replace(tmp, checkpoint)
         # host mirrors follow the device state
         new_state = eng.state(e)
@@ -312,6 +330,8 @@ def dbs_greedy_env(env: BinaryHologramEnv, z=2e-3, pixel_pitch=7.56e-6, crop_mar
         if verbose and stats:                             # DBS_1024_24.py:453-469
             _print_bins(out["bin_counts"], improved, gains)
             print("\n")
+        if out_of_budget:
+            break
     return results
 
 

@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "bh_set_target", "bh_load_state", "bh_clone_env", "bh_resync", "bh_get_metrics", "bh_eval_flips",
     "bh_step_batch", "bh_vec_step", "bh_vec_book_update", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
     "bh_commit_flip", "bh_dbs_run", "bh_sweep_all", "bh_sweep_stats", "bh_get_recon", "bh_get_state", "bh_get_field",
-    "bh_recon_batch", "bh_recon_device_block", "bh_stream_sync",
+    "bh_recon_batch", "bh_recon_device_block", "bh_recon_planes_written", "bh_stream_sync",
     "bh_device_ptr", "bh_host_alloc", "bh_host_free", "bh_simulate", "bh_time_eval", "bh_time_step", "bh_time_commit",
     "bh_time_propagate", "bh_time_propagate_passes", "bh_launch_count",
 )
@@ -102,6 +102,7 @@ def load_library(build_if_missing: bool = True):
         "bh_recon_batch": (i32, [vp, i32, vp, vp, vp, i32, i32, i32]),
         "bh_recon_device_block": (vp, [vp, i32]),
         "bh_stream_sync": (i32, [vp]),
+        "bh_recon_planes_written": (i64, [vp]),
         "bh_time_step": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, P(C.c_float)]),
         "bh_time_commit": (i32, [vp, i32, vp, vp, i32, i32, P(C.c_float)]),
         "bh_get_field": (i32, [vp, i32, i32, vp, i32]),
@@ -391,6 +392,10 @@ class HoloEngine:
         if not ptr:
             raise HoloError("bh_recon_device_block failed: " + self.lib.bh_last_error(self._h).decode())
         return DeviceArray(int(ptr), (self.n_env, 1, self.G, self.N, self.N), "<f4", owner=self)
+
+    @property
+    def recon_planes_written(self) -> int:
+        return int(self.lib.bh_recon_planes_written(self._h))
 
     def stream_sync(self):
         self._check(self.lib.bh_stream_sync(self._h), "bh_stream_sync")

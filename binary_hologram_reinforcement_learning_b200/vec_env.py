@@ -89,25 +89,12 @@ class HologramVecEnv:
         # vectorised bookkeeping (env.py:154-260 evaluated for all envs at once); used when no
         # per-step printing, cropping or rank-table reward is involved
         self._fast = (crop_margin == 0 and reward_mode in ("psnr", "group") and not verbose)
-        # observation blocks of obs["recon_image"]: [E][1][G][nsim][nsim], written by bh_recon_batch
-        self.recon_obs = recon_obs
-        self._obs_live = recon_obs in ("eager", "device")
-        self._cur = 0
-        if self._obs_live:
-            self._n_obs = max(1, min(int(obs_buffers), 4))
-            shape = (self.num_envs, 1, len(wl), nsim, nsim)
-            if recon_obs == "device":
-                self._obs_kind = OBS_CONTEXT
-                self._blocks = [self.engine.recon_device_block(b) for b in range(self._n_obs)]
-                self._block_ptrs = [0] * self._n_obs
-            else:
-                self._obs_kind = OBS_PINNED_HOST
-                self._blocks = [pinned_empty(shape, np.float32) for _ in range(self._n_obs)]
-                self._block_ptrs = [b.ctypes.data for b in self._blocks]
-            self._views = [[blk[i] for i in range(self.num_envs)] for blk in self._blocks]
-            for env in self.envs:
-                env._vec = self
+        self._obs_shape = (self.num_envs, 1, len(wl), nsim, nsim)
+        self._n_obs = max(1, min(int(obs_buffers), 4))
         self._sub_eids = np.zeros(self.num_envs, dtype=np.int32)
+        self._blocks_by_mode = {}
+        self._cur = 0
+        self.set_recon_obs(recon_obs)
         self._group = reward_mode == "group"
         self._changes = self._ranks = None      # (E, num_samples) tables of env_group.py:90-143
         self._sorted = [None] * self.num_envs
@@ -182,6 +169,50 @@ class HologramVecEnv:
             self._sorted[i] = (sv, order, np.searchsorted(sv, sv, side="left"))
 
     # -- observation blocks ------------------------------------------------
+    def set_recon_obs(self, mode: str):
+        """Select how obs["recon_image"] is kept ("eager" / "device" / "lazy"); may be switched between steps.
+        Blocks: [E][1][G][nsim][nsim], written plane by plane by bh_recon_batch."""
+        if mode not in ("eager", "device", "lazy"):
+            raise ValueError(f"recon_obs must be 'eager', 'device' or 'lazy', not {mode!r}")
+        self.recon_obs = mode
+        self._obs_live = mode in ("eager", "device")
+        for env in self.envs:
+            env.recon_obs = mode
+            env._vec = self if self._obs_live else None
+        if not self._obs_live:
+            for env in self.envs:
+                if env._engine is not None and env.steps is not None:
+                    env._recon_buf = None
+                    env._attach_obs()
+                    env.refresh_recon()
+            self._refresh_obs_cache()
+            return
+        if mode not in self._blocks_by_mode:
+            if mode == "device":
+                blocks = [self.engine.recon_device_block(b) for b in range(self._n_obs)]
+                ptrs = [0] * self._n_obs
+            else:
+                blocks = [pinned_empty(self._obs_shape, np.float32) for _ in range(self._n_obs)]
+                ptrs = [b.ctypes.data for b in blocks]
+            self._blocks_by_mode[mode] = (blocks, ptrs)
+        self._blocks, self._block_ptrs = self._blocks_by_mode[mode]
+        self._obs_kind = OBS_CONTEXT if mode == "device" else OBS_PINNED_HOST
+        self._views = [[blk[i] for i in range(self.num_envs)] for blk in self._blocks]
+        self._stale_all = [True] * self._n_obs          # a (re)selected block holds nothing current
+        if self.envs[0].steps is not None:               # already reset: fill the current block now
+            from .engine import OBS_FULL
+            self.engine.recon_batch(self.num_envs, self._block_ptrs[self._cur], self._obs_kind, self._cur,
+                                    OBS_SYNC | OBS_COMMITTED_ONLY | OBS_FULL, env_ids_ptr=self._eids.ctypes.data)
+            self._stale_all[self._cur] = False
+            for env in self.envs:
+                self._attach_env_obs(env)
+            self._refresh_obs_cache()
+
+    def _refresh_obs_cache(self):
+        for i, env in enumerate(self.envs):
+            if self._obs_cache[i] is not None:
+                self._obs_cache[i] = env._obs()
+
     def _attach_env_obs(self, env: BinaryHologramEnv):
         env._recon_buf = self._views[self._cur][env._e]
 
@@ -195,14 +226,18 @@ class HologramVecEnv:
         """After a step of n envs: advance to the next block and bring it up to date for every env."""
         b = self._cur = (self._cur + 1) % self._n_obs
         eng, ptr, kind = self.engine, self._block_ptrs[b], self._obs_kind
+        full = 0
+        if self._stale_all[b]:                        # first use of this block since it was (re)selected
+            from .engine import OBS_FULL
+            full, self._stale_all[b] = OBS_FULL, False
         if rest is not None and rest.size:            # envs without an engine step this time (cropped-out pixels)
             self._rest_eids = np.ascontiguousarray(rest, dtype=np.int32)
             if n:
-                eng.recon_batch(n, ptr, kind, b, 0, env_ids_ptr=eids_ptr)
-            eng.recon_batch(int(rest.size), ptr, kind, b, OBS_SYNC | OBS_COMMITTED_ONLY,
+                eng.recon_batch(n, ptr, kind, b, full, env_ids_ptr=eids_ptr)
+            eng.recon_batch(int(rest.size), ptr, kind, b, OBS_SYNC | OBS_COMMITTED_ONLY | full,
                             env_ids_ptr=self._rest_eids.ctypes.data)
         else:
-            eng.recon_batch(n, ptr, kind, b, OBS_SYNC, env_ids_ptr=eids_ptr)
+            eng.recon_batch(n, ptr, kind, b, OBS_SYNC | full, env_ids_ptr=eids_ptr)
         views = self._views[b]
         for i, env in enumerate(self.envs):
             env._recon_buf = views[i]

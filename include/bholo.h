@@ -202,6 +202,9 @@ int bh_recon_batch(bh_ctx* ctx, int n, const int32_t* env_ids, const bh_result* 
                    float* out, int out_kind, int buffer, int flags);
 /* Device observation block `buffer` of the context, float [E][G][N][N] (allocated on first use). */
 void* bh_recon_device_block(bh_ctx* ctx, int buffer);
+/* Colour planes (N*N floats each) written by bh_recon_batch since the context was created:
+ * the bytes of the observation path, for accounting.  Synchronises the stream. */
+int64_t bh_recon_planes_written(bh_ctx* ctx);
 /* Wait for everything enqueued on the context's stream. */
 int bh_stream_sync(bh_ctx* ctx);
 /* Field of one frame, complex64 [N][N] as interleaved floats (test hook). */

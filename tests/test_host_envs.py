@@ -242,6 +242,34 @@ def test_dbs_greedy_driver_checkpoint_and_resume(tmp_path):
     assert rest["final_psnr"] == full["final_psnr"]
 
 
+def test_dbs_resume_adopts_stored_order_and_skips_finished_images(tmp_path):
+    """A restarted process draws a NEW permutation and starts at the loader's first image again: the checkpoint
+    carries the image number and the order of the image in progress, so the run continues where it stopped."""
+    N, F = 16, 4
+
+    def run(rng, **kw):
+        ld = bh.SyntheticLoader(N, F, 1, seeds=(21, 22))
+        env = bh.BinaryHologramEnv(ld.target_function, ld, IPS=N, CH=F, verbose=False)
+        out = bh.optimize_with_random_pixel_flips(env, 2e-3, 7.56e-6, max_datasets=1, rng=rng, verbose=False, **kw)
+        env.close()
+        return out
+
+    ref = run(np.random.default_rng(6))
+    assert len(ref) == 2 and all(r["complete"] for r in ref)
+    ck = str(tmp_path / "dbs2.npz")
+    # 1024 candidates per image, 300 per segment: image 1 takes 4 segments, the call stops inside image 2
+    part = run(np.random.default_rng(6), checkpoint=ck, segment=300, max_segments=6)
+    assert len(part) == 2 and part[0]["complete"] and not part[1]["complete"] and part[1]["steps"] == 600
+    # the "restarted process": an unrelated rng stream, a fresh loader and env
+    rest = run(np.random.default_rng(12345), checkpoint=ck, segment=300)
+    assert len(rest) == 1 and rest[0]["complete"] and rest[0]["file"] == ref[1]["file"]
+    assert np.array_equal(rest[0]["order"], ref[1]["order"])
+    assert np.array_equal(rest[0]["accepted"], ref[1]["accepted"]) and np.array_equal(rest[0]["state"], ref[1]["state"])
+    assert rest[0]["final_psnr"] == ref[1]["final_psnr"]
+    # everything is finished now: another restart has nothing left to do
+    assert run(np.random.default_rng(1), checkpoint=ck, segment=300) == []
+
+
 def test_dbs_sweep_driver_full_sharded_and_partial():
     """dbs-1024-1024-24-6464.py:194-478: crop, score every flip against the fixed state, decile statistics;
     the whole-image path, the rank-sharded path and a candidate subset agree with the oracle."""
