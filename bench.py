@@ -9,17 +9,21 @@ uniformly random single-pixel flips, keep iff dPSNR >= 0 (env.py:184-196).
 One bench "step" = one rollout of ROLLOUT = 512 vectorised env steps
 (train-PPO.py:300 n_steps=512), i.e. 4096 env steps per GPU.
 
-  value   env steps/s, device-resident inputs (actions pre-uploaded), CUDA events
-  e2e     same metric through HologramVecEnv.step(): host numpy actions copied
-          from pinned memory every step, results (PSNR, accept) read back every
-          step, Python reward logic included
+  value     env steps/s, device-resident inputs (actions pre-uploaded), CUDA events
+  e2e       same metric through HologramVecEnv.step() as the reference returns it (env.py:176-181):
+            host numpy actions in, results (PSNR, accept) AND obs["recon_image"] of every env current on
+            the host after every step (recon_obs="eager", the default); e2e.lazy_obs / e2e.device_obs are
+            the same loop without the observation copy / with a device-resident observation
   roofline  delta-eval kernel k_eval: 16*N^2 algorithmic HBM bytes per candidate
-          (U 8 B/px + I 4 + T 4; the shifted impulse response is L2 resident)
-  cpu_baseline  the reference-shaped torch CPU path (oracle/torch_path.py)
+            (U 8 B/px + I 4 + T 4; the shifted impulse response is L2 resident); roofline_commit
+            (24*N^2 per kept flip) and roofline_propagate (N^2 + 32 P^2 per frame) beside it
+  dbs       greedy DBS candidates/s at three accept-rate regimes (metric's second half)
+  cpu_baseline  the reference-shaped torch CPU path (oracle/torch_path.py) + comparators
+  parity_check  the first vectorised steps of two envs replayed on the float64 oracle
 
 Under torchrun (N > 1) every rank owns one GPU and its own 8 envs (weak
-scaling, no data-path collective); NCCL is used for the max-over-ranks timing
-and one all-gather of episode statistics after the timed region.
+scaling, no data-path collective); NCCL is used for the max-over-ranks timing,
+one all-gather of episode statistics and one all-reduce of sweep histograms after the timed region.
 """
 from __future__ import annotations
 
@@ -45,6 +49,15 @@ WORKLOAD = ("env_1024_24 x 8 vectorised envs per GPU: 1024x1024, 24 binary frame
             "1 step = rollout of 512 vectorised env steps (4096 env steps per GPU)")
 
 
+def bench_config(envs: int, rollout: int) -> dict:
+    """The workload description: identical for the repo arm and the reference arm."""
+    return {"workload": WORKLOAD, "envs_per_gpu": envs, "rollout": rollout, "N": N_SIDE, "frames": FRAMES,
+            "groups": GROUPS, "pad": 1, "relative": True, "recon_obs": "eager (env.py:176-181)",
+            "l2": ("inputs larger than L2: 8 envs x 226 MB resident per GPU, every step streams a random "
+                   "frame (16.8 MB) of each env"),
+            "episodes": "max_steps raised so no episode ends inside the timed region"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -55,6 +68,8 @@ def parse():
     ap.add_argument("--rollout", type=int, default=ROLLOUT)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the dbs / group / sweep blocks")
+    ap.add_argument("--dbs-full", action="store_true", help="also time one full greedy pass (25.2 M candidates)")
     return ap.parse_args()
 
 
@@ -164,8 +179,10 @@ def cpu_reference_rate(seconds_budget=None, samples=None, sample_steps=8, warm=1
 
 def comparator_rates(seconds=4.0):
     """Other shapes of the same reference-shaped torch path, part of the cpu_baseline leg:
-    the 256^2 x 8 full step on the host cores, and the call sequence "simply run on the B200"
-    (torch.fft = cuFFT, the colour group re-uploaded every step as env.py:170 does, blocking .item())."""
+    the 256^2 x 8 full step on the host cores, the call sequence "simply run on the B200"
+    (torch.fft = cuFFT, the colour group re-uploaded every step as env.py:170 does, blocking .item()),
+    and the DEVICE-RESIDENT torch.fft propagation of the 24 x 1024^2 stack (+ abs^2 + mean + relative loss) --
+    the on-GPU bar SURVEY 2.1 sets for the hand-written FFT passes."""
     import torch
     from oracle.torch_path import TorchRefEnv
     from oracle import hologram_oracle as O
@@ -189,7 +206,69 @@ def comparator_rates(seconds=4.0):
     if torch.cuda.is_available():
         out["torch_on_b200_1024x24_single_group_env_steps_per_s"] = rate(N_SIDE, FRAMES, O.WL_RGB, "cuda")
         out["torch_on_b200_256x8_full_step_env_steps_per_s"] = rate(256, 8, O.WL_MONO, "cuda")
+        # device-resident propagation with cuFFT: nothing crosses PCIe inside the timed region
+        pre, tgt = O.synthetic_problem(N_SIDE, FRAMES, GROUPS, 0)
+        x = torch.from_numpy((pre >= 0.5).astype(np.float32)).cuda()
+        T = torch.from_numpy(tgt).cuda()
+        H = torch.stack([torch.from_numpy(O.transfer_function(N_SIDE, O.PIXEL_PITCH, w, O.Z_DEFAULT)
+                                          .astype(np.complex64)) for w in O.WL_RGB]).cuda()
+        Fg = FRAMES // GROUPS
+
+        def propagate():
+            means = []
+            for g in range(GROUPS):
+                U = torch.fft.ifft2(torch.fft.fft2(x[g * Fg:(g + 1) * Fg]) * H[g])
+                means.append((U.abs() ** 2).mean(dim=0))
+            I = torch.stack(means)
+            s = (I * T).sum() / (I * I).sum()
+            return 10.0 * torch.log10(1.0 / ((s * I - T) ** 2).mean())
+
+        for _ in range(3):
+            propagate()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            p = propagate()
+        e1.record()
+        torch.cuda.synchronize()
+        out["torch_fft_device_resident_propagate_ms_24_frames"] = e0.elapsed_time(e1) / 10.0
+        out["torch_fft_device_resident_psnr"] = float(p.item())
     return out
+
+
+def oracle_replay(seed: int, actions: np.ndarray):
+    """float64 replay of one env's first steps (oracle/hologram_oracle.py: propagate_group + delta_terms +
+    closed-form loss; env.py:154-196 decision rule).  Returns (rewards, accepted)."""
+    from oracle import hologram_oracle as O
+    cfg = O.HoloConfig(N=N_SIDE, F=FRAMES, wl=O.WL_RGB)
+    pre, tgt = O.synthetic_problem(N_SIDE, FRAMES, GROUPS, seed=seed)
+    st = (pre >= 0.5).astype(np.int8)
+    t64 = tgt.astype(np.float64)
+    U = [O.propagate_group(cfg, st[g * cfg.Fg:(g + 1) * cfg.Fg], g) for g in range(cfg.G)]
+    I = [O.group_mean_intensity(u) for u in U]
+    sii, sit, stt = O.loss_sums(np.stack(I), t64)
+    n = cfg.G * N_SIDE * N_SIDE
+    prev = O.psnr_from_mse(O.mse_from_sums(sii, sit, stt, n, True))
+    rewards, accepted = [], []
+    for a in actions:
+        f, r, c = cfg.decode(int(a))
+        g = cfg.group_of(f)
+        s = 1 - 2 * int(st[f, r, c])
+        d_sii, d_sit, dI = O.delta_terms(cfg, U[g][f - g * cfg.Fg], I[g], t64[g], g, r, c, s)
+        after = O.psnr_from_mse(O.mse_from_sums(sii + d_sii, sit + d_sit, stt, n, True))
+        change = after - prev
+        rewards.append(change * 800.0)
+        acc = not (change < 0)                                  # env.py:191
+        accepted.append(acc)
+        if acc:
+            h = cfg.h(g)
+            yy = (np.arange(N_SIDE) - r) % cfg.P
+            xx = (np.arange(N_SIDE) - c) % cfg.P
+            U[g][f - g * cfg.Fg] += s * h[np.ix_(yy, xx)]
+            I[g] = I[g] + dI
+            sii, sit, prev = sii + d_sii, sit + d_sit, after
+            st[f, r, c] = 1 - st[f, r, c]
+    return np.array(rewards), np.array(accepted)
 
 
 def run_reference(args):
@@ -210,8 +289,7 @@ def run_reference(args):
         "impl": "reference", "metric": "env_steps_per_s", "value": rate, "unit": "env steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "N": N_SIDE, "frames": FRAMES,
-                                        "groups": GROUPS, "pad": 1, "relative": True},
+        "data": "synthetic", "config": bench_config(args.envs, args.rollout),
         "cpu_baseline": {"value": rate, "unit": "env steps/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": rate, "unit": "env steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -224,6 +302,136 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
+def make_vec(bh, E, rank, local, recon_obs, N=N_SIDE, F=FRAMES, wl=None, seed0=0, **kw):
+    wl = bh.WL_RGB if wl is None else wl
+    loaders = [bh.SyntheticLoader(N, F, len(wl), seeds=(seed0 + rank * E + i,)) for i in range(E)]
+
+    def target_function(t):
+        key = np.ascontiguousarray(t[0, 0, 0, :4], dtype=np.float32).tobytes()
+        for ld in loaders:
+            if key in ld._pre:
+                return ld._pre[key][None]
+        raise KeyError("unknown synthetic target")
+
+    return bh.HologramVecEnv(E, target_function, loaders, max_steps=10 ** 9, T_PSNR_DIFF=1e9, IPS=N, CH=F,
+                             wl=wl, device=local, recon_obs=recon_obs, obs_mode="views", verbose=False,
+                             seed=rank, **kw)
+
+
+def dbs_block(eng, env, rng, peak, torch):
+    """Greedy DBS (DBS_1024_24.py:313-422) candidates/s at three accept-rate regimes of ONE 1024^2 x 24 target.
+
+    fresh: the random initial hologram.  mid / late: after 12 / 60 rounds of a parallel pre-pass that is NOT the
+    reference's algorithm, only a quick way to a well-optimised state for the measurement: score every pixel
+    (bh_sweep_all), take the best improving candidate of every 64 x 64 tile and frame, run them through the
+    greedy loop.  Roofline per regime: (16 N^2 per scored candidate + 24 N^2 per kept flip) / time -- discarded
+    speculation is not credited."""
+    n2 = N_SIDE * N_SIDE
+    n_pix = FRAMES * n2
+    d_map = torch.empty(n_pix, dtype=torch.float64, device="cuda")
+    out = {}
+
+    def measure(label, n_cand):
+        order = np.unique(rng.integers(0, n_pix, size=n_cand))
+        rng.shuffle(order)
+        eng.stream_sync()
+        t0 = time.perf_counter()
+        acc, _, nacc, psnr = eng.dbs_run(order, env=env, k_spec=0, resync_every=1024)
+        dt = time.perf_counter() - t0
+        useful = (order.size * 16.0 + nacc * 24.0) * n2
+        out[label] = {"candidates": int(order.size), "candidates_per_s": order.size / dt,
+                      "accept_rate": nacc / order.size, "psnr": psnr,
+                      "hbm_frac_useful_bytes": useful / dt / 1e9 / peak}
+
+    def prepass(rounds, tile=64):
+        for _ in range(rounds):
+            eng.sweep_all_device(env, d_map.data_ptr())
+            eng.stream_sync()
+            p0 = eng.metrics(env)[0]
+            oy, ox = (int(v) for v in rng.integers(0, tile, size=2))
+            gain = torch.roll(d_map.view(FRAMES, N_SIDE, N_SIDE) - p0, shifts=(oy, ox), dims=(1, 2))
+            t = gain.view(FRAMES, N_SIDE // tile, tile, N_SIDE // tile, tile).permute(0, 1, 3, 2, 4)
+            t = t.reshape(FRAMES, N_SIDE // tile, N_SIDE // tile, tile * tile)
+            best, arg = t.max(dim=-1)
+            f, ty, tx = torch.nonzero(best > 0, as_tuple=True)
+            a = arg[f, ty, tx]
+            y = (ty * tile + a // tile - oy) % N_SIDE
+            x = (tx * tile + a % tile - ox) % N_SIDE
+            acts = (f * n2 + y * N_SIDE + x)[torch.argsort(best[f, ty, tx], descending=True)]
+            if acts.numel() == 0:
+                break
+            eng.dbs_run(acts.cpu().numpy(), env=env, k_spec=0, resync_every=4096)
+
+    measure("fresh", 40000)
+    t0 = time.perf_counter()
+    prepass(12)
+    measure("mid", 40000)
+    prepass(48)
+    out["prepass_seconds"] = time.perf_counter() - t0 - 0.0
+    measure("late", 40000)
+    return out
+
+
+def group_block(bh, bdist, rank, local):
+    """BASELINE configs[4]: env_group reward (10 000 scored candidates per reset, env_group.py:90-143) with
+    GRPO-style groups of M = 8 members cloned from one reset state, 512-step rollouts (lazy observation)."""
+    out = {}
+    for name, N, F, wl, E in (("256x8_64envs", 256, 8, bh.WL_MONO, 64), ("1024x24_8envs", 1024, 24, bh.WL_RGB, 8)):
+        M = 8
+        loaders = [bh.SyntheticLoader(N, F, len(wl), seeds=(9000 + rank * E + i // M,)) for i in range(E)]
+
+        def tf(t, loaders=loaders):
+            key = np.ascontiguousarray(t[0, 0, 0, :4], dtype=np.float32).tobytes()
+            for ld in loaders:
+                if key in ld._pre:
+                    return ld._pre[key][None]
+            raise KeyError
+
+        vec = bh.HologramVecEnv(E, tf, loaders, max_steps=10 ** 9, T_PSNR_DIFF=1e9, IPS=N, CH=F, wl=wl,
+                                device=local, reward_mode="group", recon_obs="lazy", verbose=False, seed=rank)
+        vec.reset_groups(M)                              # warm (tables, allocations)
+        vec.engine.stream_sync()
+        bdist.barrier()
+        t0 = time.perf_counter()
+        vec.reset_groups(M)
+        vec.engine.stream_sync()
+        t_reset = bdist.max_over_ranks(time.perf_counter() - t0)
+        rng = np.random.default_rng(77 + rank)
+        acts = rng.integers(0, F * N * N, size=(512 + 32, E), dtype=np.int64)
+        for i in range(32):
+            vec.step(acts[i])
+        vec.engine.stream_sync()
+        bdist.barrier()
+        t0 = time.perf_counter()
+        for i in range(32, 32 + 512):
+            vec.step(acts[i])
+        vec.engine.stream_sync()
+        t_roll = bdist.max_over_ranks(time.perf_counter() - t0)
+        world = bdist.env_info()[1]
+        out[name] = {"envs_per_gpu": E, "group_size": M, "reset_groups_s": t_reset,
+                     "candidates_scored_per_s_at_reset": world * (E // M) * 10000 / t_reset,
+                     "rollout_env_steps_per_s": world * E * 512 / t_roll}
+        vec.close()
+    return out
+
+
+def sharded_sweep_block(bh, bdist, rank, world, local):
+    """BASELINE configs[3]: the 64-pixel-crop sweep of one 1024^2 x 24 target (dbs-1024-1024-24-6464.py:330-395),
+    its 19.3 M candidates sharded over the ranks as contiguous slices of one global order; the decile
+    histograms meet in one NCCL all-reduce."""
+    ld = bh.SyntheticLoader(N_SIDE, FRAMES, GROUPS, seeds=(4242,))
+    bdist.barrier()
+    t0 = time.perf_counter()
+    r = bh.dbs_sweep(ld.target_function, ld, 2e-3, 7.56e-6, 64, CH=FRAMES, wl=bh.WL_RGB, max_datasets=0,
+                     rng=np.random.default_rng(9), verbose=False, device=local,
+                     shard=(rank, world) if world > 1 else None)[0]
+    att, imp, gains = bdist.reduce_histograms(r["attempted"], r["improved"], r["gains"])
+    dt = bdist.max_over_ranks(time.perf_counter() - t0)
+    n_all = FRAMES * 896 * 896
+    return {"candidates": n_all, "seconds_incl_setup": dt, "flip_evals_per_s": n_all / dt,
+            "attempted_total": int(np.sum(att)), "improved_total": int(np.sum(imp))}
+
+
 def run_b200(args):
     import torch
     import binary_hologram_reinforcement_learning_b200 as bh
@@ -238,20 +446,11 @@ def run_b200(args):
         bdist.init_process_group("nccl")
     E, R, K, W = args.envs, args.rollout, args.steps, max(args.warmup, 0)
     n_pix = FRAMES * N_SIDE * N_SIDE
+    plane_bytes = 4 * N_SIDE * N_SIDE
+    peak, peak_src = measured_peak_gbs()
 
-    # ---- environments (public API) --------------------------------------
-    loaders = [bh.SyntheticLoader(N_SIDE, FRAMES, GROUPS, seeds=(rank * E + i,)) for i in range(E)]
-
-    def target_function(t):
-        key = np.ascontiguousarray(t[0, 0, 0, :4], dtype=np.float32).tobytes()
-        for ld in loaders:
-            if key in ld._pre:
-                return ld._pre[key][None]
-        raise KeyError("unknown synthetic target")
-
-    vec = bh.HologramVecEnv(E, target_function, loaders, max_steps=10 ** 9, T_PSNR_DIFF=1e9,
-                            IPS=N_SIDE, CH=FRAMES, wl=bh.WL_RGB, device=local, recon_obs="lazy",
-                            obs_mode="views", verbose=False, seed=rank)
+    # ---- environments (public API), reference-faithful observation ---------
+    vec = make_vec(bh, E, rank, local, "eager")
     eng = vec.engine
     stream = torch.cuda.Stream(device=local)
     eng.set_stream(stream.cuda_stream)
@@ -263,37 +462,51 @@ def run_b200(args):
     sampler.start()
     windows = []
 
-    # ---- e2e: HologramVecEnv.step with host actions ----------------------
-    e2e_steps = R * K
+    # ---- e2e: HologramVecEnv.step, host actions in, results + recon_image on the host every step ----
     acts_host = rng.integers(0, n_pix, size=(R * (K + W), E), dtype=np.int64)
+    n_chk = min(32, R * W) if W > 0 else 0               # steps recorded for the oracle replay
+    chk_rewards, chk_accept = np.zeros((n_chk, E)), np.zeros((n_chk, E), dtype=bool)
     for i in range(R * W):
-        vec.step(acts_host[i])
-    torch.cuda.synchronize()
+        obs, rewards, _, _ = vec.step(acts_host[i])
+        if i < n_chk:
+            chk_rewards[i], chk_accept[i] = rewards, vec._res["accept"] != 0
+    eng.stream_sync()
     bdist.barrier()
+    planes0 = eng.recon_planes_written
     t0w = time.time()
     t0 = time.perf_counter()
-    reward_sum = 0.0
+    reward_sum, obs_sum = 0.0, 0.0
     for i in range(R * W, R * (W + K)):
-        _, rewards, _, _ = vec.step(acts_host[i])
+        obs, rewards, _, _ = vec.step(acts_host[i])
         reward_sum += float(rewards[0])
-    torch.cuda.synchronize()
+        obs_sum += float(obs[0]["recon_image"][0, 0, 0, 0])          # the observation is host memory
+    eng.stream_sync()
     e2e_s = time.perf_counter() - t0
     windows.append((t0w, time.time()))
+    planes = eng.recon_planes_written - planes0
     bdist.barrier()
     e2e_s = bdist.max_over_ranks(e2e_s)
-    e2e_value = world * E * e2e_steps / e2e_s
+    e2e_value = world * E * R * K / e2e_s
     h2d = R * E * (8 + 4)                       # actions int64 + env ids int32 per vec step
-    d2h = R * E * RESULT_DTYPE.itemsize         # bh_result records per vec step
+    d2h = R * E * RESULT_DTYPE.itemsize + planes * plane_bytes / max(K, 1)     # records + recon planes per bench step
 
-    # ---- e2e with the reference's eager observation: recon_image copied to the host every step
-    n_eager = 64
-    t0 = time.perf_counter()
-    for i in range(n_eager):
-        vec.step(acts_host[i % len(acts_host)])
-        for j in range(E):
-            vec.refresh_recon(j)                  # 12.6 MB D2H per env into pinned memory
-    torch.cuda.synchronize()
-    eager_s = bdist.max_over_ranks(time.perf_counter() - t0)
+    # ---- the same loop without the observation copy, and with a device-resident observation ----
+    def short_loop(mode, n_roll):
+        vec.set_recon_obs(mode)
+        a = rng.integers(0, n_pix, size=(R * (n_roll + 1), E), dtype=np.int64)
+        for i in range(R):
+            vec.step(a[i])
+        eng.stream_sync()
+        bdist.barrier()
+        t0 = time.perf_counter()
+        for i in range(R, R * (n_roll + 1)):
+            vec.step(a[i])
+        eng.stream_sync()
+        return world * E * R * n_roll / bdist.max_over_ranks(time.perf_counter() - t0)
+
+    lazy_value = short_loop("lazy", max(2, min(K, 5)))
+    device_value = short_loop("device", max(2, min(K, 5)))
+    vec.set_recon_obs("lazy")
 
     # ---- value: device-resident actions, CUDA events ---------------------
     d_acts = torch.from_numpy(rng.integers(0, n_pix, size=(R * (K + W), E), dtype=np.int64)).cuda(local)
@@ -327,41 +540,66 @@ def run_b200(args):
     res_host = d_res.cpu().numpy().view(RESULT_DTYPE).reshape(R, E)
     accept_rate = float(res_host["accept"].mean())
 
-    # ---- roofline of the dominant kernel (k_eval), measured live ---------
+    # ---- rooflines of the delta kernels, measured live ---------------------
     n_sets = 64
     d_sets = torch.from_numpy(rng.integers(0, n_pix, size=(n_sets, E), dtype=np.int64)).cuda(local)
+    d_fresh = torch.from_numpy(rng.integers(0, n_pix, size=(600, E), dtype=np.int64)).cuda(local)
     with torch.cuda.stream(stream):
         t0w = time.time()
         eval_ms = eng.time_eval(E, e_ptr, d_sets.data_ptr(), n_sets, 512)
+        chain_ms = eng.time_step(E, e_ptr, d_fresh.data_ptr(), 600, 512, RULE_ENV, True)
+        commit_ms = eng.time_commit(E, e_ptr, d_sets.data_ptr(), n_sets, 512)
         windows.append((t0w, time.time()))
     alg_bytes = 16.0 * N_SIDE * N_SIDE * E
     achieved = alg_bytes / (eval_ms / 1000.0) / 1e9
-    peak, peak_src = measured_peak_gbs()
+    commit_bytes = 24.0 * N_SIDE * N_SIDE * E
+    commit_gbs = commit_bytes / (commit_ms / 1000.0) / 1e9
+    # whole step: one evaluation + accept_rate kept flips per env
+    step_bytes = (16.0 + 24.0 * accept_rate) * N_SIDE * N_SIDE * E
+    step_gbs = step_bytes / (dev_ms / (K * R) / 1000.0) / 1e9
 
-    # ---- secondary figures: sweep flip-evals/s, propagation ---------------
-    n_cand = 8192
-    cand = rng.integers(0, n_pix, size=n_cand, dtype=np.int64)
-    eng.eval_flips(cand[:1024], env=0)
-    t0 = time.perf_counter()
-    eng.eval_flips(cand, env=0)
-    sweep_s = time.perf_counter() - t0
+    # ---- propagation (reset / re-sync) ------------------------------------
     with torch.cuda.stream(stream):
-        prop_ms = eng.time_propagate(0, 5)
+        prop_ms = min(eng.time_propagate(0, 10) for _ in range(3))
         prop_pass_ms = eng.time_propagate_passes(0, 3)
-    # exhaustive sweep of all 24*1024^2 candidates of env 0 by FFT correlation (device output)
-    d_map = torch.empty(n_pix, dtype=torch.float64, device=f"cuda:{local}")
-    eng.sweep_all_device(0, d_map.data_ptr())
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    eng.sweep_all_device(0, d_map.data_ptr())
-    torch.cuda.synchronize()
-    sweep_all_s = time.perf_counter() - t0
-    # greedy DBS (device loop, speculative batches) on env 1
-    order = rng.permutation(n_pix)[:20000]
-    t0 = time.perf_counter()
-    _, _, dbs_nacc, _ = eng.dbs_run(order, env=min(1, E - 1), k_spec=0, resync_every=0)
-    dbs_s = time.perf_counter() - t0
-    prop_bytes = FRAMES * (N_SIDE ** 2 + 40.0 * N_SIDE ** 2) + 8.0 * GROUPS * N_SIDE ** 2
+    prop_bytes_survey = FRAMES * (N_SIDE ** 2 + 32.0 * N_SIDE ** 2) + 8.0 * GROUPS * N_SIDE ** 2
+    prop_bytes_design = FRAMES * (N_SIDE ** 2 + 40.0 * N_SIDE ** 2) + 8.0 * GROUPS * N_SIDE ** 2     # + U written
+
+    extra = {"accept_rate": accept_rate, "psnr_env0_initial": psnr0[0]}
+    dbs = group = sharded = None
+    if not args.no_extras:
+        # ---- secondary figures: candidate lists, exhaustive sweep -------------
+        n_cand = 8192
+        cand = rng.integers(0, n_pix, size=n_cand, dtype=np.int64)
+        eng.eval_flips(cand[:1024], env=0)
+        t0 = time.perf_counter()
+        eng.eval_flips(cand, env=0)
+        sweep_s = time.perf_counter() - t0
+        d_map = torch.empty(n_pix, dtype=torch.float64, device=f"cuda:{local}")
+        eng.sweep_all_device(0, d_map.data_ptr())
+        eng.stream_sync()
+        t0 = time.perf_counter()
+        eng.sweep_all_device(0, d_map.data_ptr())
+        eng.stream_sync()
+        sweep_all_s = time.perf_counter() - t0
+        del d_map
+        extra.update({"flip_evals_per_s_kernel": E / (eval_ms / 1000.0) * world,
+                      "flip_evals_per_s_sweep_api": n_cand / sweep_s * world,
+                      "flip_evals_per_s_exhaustive_sweep_all": n_pix / sweep_all_s * world,
+                      "sweep_all_ms_25M_candidates": sweep_all_s * 1e3})
+        # ---- greedy DBS at three regimes (env 1), the metric's second half ----
+        with torch.cuda.stream(stream):
+            dbs = dbs_block(eng, min(1, E - 1), rng, peak, torch)
+        if args.dbs_full:
+            order = np.random.default_rng(31).permutation(n_pix)
+            eng.load_state(E - 1, vec.envs[E - 1].state[0] * 0 + (vec.envs[E - 1].observation[0] >= 0.5))
+            t0 = time.perf_counter()
+            acc, _, nacc, psnr = eng.dbs_run(order, env=E - 1, k_spec=0, resync_every=1024)
+            dt = time.perf_counter() - t0
+            dbs["full_pass"] = {"candidates": int(n_pix), "seconds": dt, "candidates_per_s": n_pix / dt,
+                                "accept_rate": nacc / n_pix, "final_psnr": psnr,
+                                "accept_rate_by_tenth": [float(acc[i * n_pix // 10:(i + 1) * n_pix // 10].mean())
+                                                         for i in range(10)]}
     clocks = sampler.stop(windows)
 
     # ---- the one collective: all-gather of per-env episode statistics ----
@@ -369,8 +607,16 @@ def run_b200(args):
     stats = np.array([[vec._ep_reward[i], vec.envs[i].steps, vec.envs[i].flip_count, psnr0[i],
                        vec.envs[i].previous_psnr] for i in range(E)])
     all_stats = bdist.gather_episode_stats(stats)
+    extra["episode_stats_rows_gathered"] = int(all_stats.shape[0])
+    vec.close()
+    del vec, eng, d_acts, d_res
+    torch.cuda.empty_cache()
 
-    cpu = None
+    if not args.no_extras:
+        group = group_block(bh, bdist, rank, local)
+        sharded = sharded_sweep_block(bh, bdist, rank, world, local)
+
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, times, cores = cpu_reference_rate(seconds_budget=args.cpu_seconds)
         cpu = {"value": rate, "unit": "env steps/s", "cores": cores, "kind": "port",
@@ -378,47 +624,64 @@ def run_b200(args):
                           f"re-simulation, float32 torch CPU ({cores} threads), "
                           f"{sum(times):.1f} s (oracle/torch_path.py)"),
                "comparators": comparator_rates()}
+    if rank == 0 and n_chk > 0 and not args.no_cpu_baseline:
+        # ---- self-check: the first vectorised steps of envs 0 and 1 on the float64 oracle ----
+        worst, equal, n_cmp = 0.0, True, 0
+        for e in (0, min(1, E - 1)):
+            r_ref, a_ref = oracle_replay(rank * E + e, acts_host[:n_chk, e])
+            for i in range(n_chk):
+                if bool(chk_accept[i, e]) != bool(a_ref[i]):
+                    equal = False                        # trajectories differ from here on
+                    break
+                worst = max(worst, abs(chk_rewards[i, e] - r_ref[i]) / max(abs(r_ref[i]), 1e-300))
+                n_cmp += 1
+        parity = {"envs": [0, min(1, E - 1)], "steps_each": n_chk, "steps_compared": n_cmp,
+                  "decisions_equal": equal, "max_rel_reward_err": worst,
+                  "oracle": "float64 delta replay (oracle/hologram_oracle.py)"}
 
     if rank == 0:
         line = {
             "metric": "env_steps_per_s", "value": value, "unit": "env steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / max(K, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "rollout": R, "N": N_SIDE,
-                       "frames": FRAMES, "groups": GROUPS, "pad": 1, "relative": True,
-                       "l2": ("inputs larger than L2: 8 envs x 226 MB resident per GPU, every step "
-                              "streams a random frame (16.8 MB) of each env"),
-                       "episodes": "max_steps raised so no episode ends inside the timed region",
-                       "accept_rate": accept_rate},
+            "config": bench_config(E, R),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                          "kernel": "k_eval (delta evaluation of 8 candidates, one per env)",
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": eval_ms,
                          "peak_source": peak_src},
+            "roofline_commit": {"bound": "hbm", "achieved": commit_gbs, "peak": peak, "unit": "GB/s",
+                                "frac": commit_gbs / peak, "kernel": "k_commit (8 kept flips per launch)",
+                                "algorithmic_bytes_per_launch": commit_bytes, "ms_per_launch": commit_ms},
+            "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                              "frac": step_gbs / peak,
+                              "what": "k_eval + k_commit of the timed region: (16 + 24 * accept_rate) N^2 B per env step",
+                              "us_per_vec_step": 1e3 * dev_ms / (K * R),
+                              "us_per_vec_step_fresh_chain_hook": 1e3 * chain_ms},
+            "roofline_propagate": {"bound": "hbm", "ms_24_frames": prop_ms, "pass_ms": prop_pass_ms,
+                                   "achieved": prop_bytes_survey / (prop_ms / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": prop_bytes_survey / (prop_ms / 1000.0) / 1e9 / peak,
+                                   "model": "SURVEY 8d: N^2 + 32 P^2 B per frame + 8 G N^2 = 0.856 GB per 24 frames",
+                                   "frac_design_model_40P2": prop_bytes_design / (prop_ms / 1000.0) / 1e9 / peak},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "env steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "api": "HologramVecEnv.step (bh_vec_step)",
-                    "checksum_reward_env0": reward_sum,
-                    "with_eager_recon_obs": {"value": world * E * n_eager / eager_s, "unit": "env steps/s",
-                                             "d2h_bytes_per_env_step": 4 * GROUPS * N_SIDE * N_SIDE}},
+                    "d2h_bytes_per_step": d2h, "api": "HologramVecEnv.step (bh_vec_step + bh_recon_batch), recon_obs=eager",
+                    "recon_planes_per_env_step": planes / max(1, K * R * E),
+                    "pcie_d2h_gb_per_s": d2h * K / e2e_s / 1e9,
+                    "checksum_reward_env0": reward_sum, "checksum_obs": obs_sum,
+                    "lazy_obs": {"value": lazy_value, "unit": "env steps/s",
+                                 "what": "same loop, recon_image only on refresh_recon() (round-1 headline)"},
+                    "device_obs": {"value": device_value, "unit": "env steps/s",
+                                   "what": "same loop, recon_image current in device memory (zero-copy view)"}},
+            "parity_check": parity,
+            "dbs": dbs,
+            "group": group,
+            "sharded_sweep": sharded,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "extra": {
-                "flip_evals_per_s_kernel": E / (eval_ms / 1000.0) * world,
-                "flip_evals_per_s_sweep_api": n_cand / sweep_s * world,
-                "flip_evals_per_s_exhaustive_sweep_all": n_pix / sweep_all_s * world,
-                "sweep_all_ms_25M_candidates": sweep_all_s * 1e3,
-                "dbs_greedy_candidates_per_s": len(order) / dbs_s * world,
-                "dbs_greedy_accept_rate": dbs_nacc / len(order),
-                "propagate_ms_24_frames": prop_ms,
-                "propagate_pass_ms": prop_pass_ms,
-                "propagate_gbs_algorithmic": prop_bytes / (prop_ms / 1000.0) / 1e9,
-                "episode_stats_rows_gathered": int(all_stats.shape[0]),
-                "psnr_env0_initial": psnr0[0],
-            },
+            "extra": extra,
         }
         emit(line)
-    vec.close()
     if world > 1:
         import torch.distributed as tdist
         tdist.destroy_process_group()

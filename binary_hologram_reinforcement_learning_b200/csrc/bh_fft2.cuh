@@ -317,7 +317,10 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 // ---------------------------------------------------------------------------
 template <int P> constexpr size_t cols2_smem_bytes() { return size_t(3) * P * COLW * sizeof(float2) + 128 + 16; }
 
-template <int P, bool HERM>
+// IN_TMA = false: the input tile is gathered straight into the butterfly registers (32-byte row segments,
+// 8 rows per warp instruction) instead of through s_in; only the H tile (shared by the Fg frames of a column
+// tile) arrives by TMA.
+template <int P, bool HERM, bool IN_TMA>
 __global__ void __launch_bounds__(32 * COLW, 2)
 k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUtensorMap map_h,
         float2* buf, const float2* __restrict__ tw, int n_groups, int Fg, int h_group0) {
@@ -356,7 +359,7 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
         for (int b = 0; b < 4; ++b)
             tma_load_3d(s_h + b * (P / 4) * W, &map_h, &bar_h, 2 * W * t, b * (P / 4), h_group0 + g);
     };
-    if (tid == 0) { issue_in(beg); issue_h(beg); }
+    if (tid == 0) { if (IN_TMA) issue_in(beg); issue_h(beg); }
     unsigned ph_in = 0, ph_h = 0;
     bool h_pending = true;
     for (int idx = beg; idx < end; ++idx) {
@@ -365,12 +368,21 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
         const bool col_ok = HERM ? (kx <= P / 2) : true;
         const bool mirror_ok = HERM && col_ok && kx != 0 && kx != P / 2;
         float2* frame = buf + size_t(g * Fg + fi) * P * P;
-        __syncthreads();                               // B0: the previous tile's reads of s_wk are done
-        mbar_wait(&bar_in, ph_in); ph_in ^= 1u;
         float2 v[32];
-        if (RB == 32 || j < RB) {
+        if (IN_TMA) {
+            __syncthreads();                           // B0: the previous tile's reads of s_wk are done
+            mbar_wait(&bar_in, ph_in); ph_in ^= 1u;
+            if (RB == 32 || j < RB) {
 #pragma unroll
-            for (int r = 0; r < RA; ++r) v[r] = s_in[(j + r * RB) * W + w];
+                for (int r = 0; r < RA; ++r) v[r] = s_in[(j + r * RB) * W + w];
+            }
+        } else {
+            if (RB == 32 || j < RB) {
+                const float2* src = frame + size_t(j) * P + kx;
+#pragma unroll
+                for (int r = 0; r < RA; ++r) v[r] = __ldcg(src + size_t(r) * RB * P);
+            }
+            __syncthreads();                           // B0 (the loads are in flight across it)
         }
         fft2_pass1<P, false, false, ColLay>(v, s_wk + w, j);
         __syncthreads();                               // B1
@@ -403,7 +415,7 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
         __syncthreads();                               // B3: all reads of s_in and s_h are done
         if (idx + 1 < end) {
             const bool new_h = (idx + 1) / Fg != gt;
-            if (tid == 0) { issue_in(idx + 1); if (new_h) issue_h(idx + 1); }
+            if (tid == 0) { if (IN_TMA) issue_in(idx + 1); if (new_h) issue_h(idx + 1); }
             h_pending = new_h;
         }
         if (HERM) {

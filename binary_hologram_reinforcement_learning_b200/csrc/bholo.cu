@@ -152,24 +152,54 @@ static cudaError_t launch_prop2_state(const int8_t* state, float2* U, float* I, 
     constexpr size_t row_smem = size_t(RowLaySize<P, RA>::value) * sizeof(float2);
     const size_t smA = ROWS_WARPS * row_smem, smB = cols2_smem_bytes<P>();
     const size_t smC = INVG_WARPS * row_smem + size_t(INVG_WARPS) * P * sizeof(float);
+    // experiment switches (profiles/r2_notes.md): BHOLO_FFT_A / _B / _C = 1 selects the shared-memory kernel of
+    // round 1 for that pass (launched per colour group), BHOLO_FFT_B = 3 the TMA-staged input tile
+    static const int selA = std::getenv("BHOLO_FFT_A") ? std::atoi(std::getenv("BHOLO_FFT_A")) : 2;
+    static const int selB = std::getenv("BHOLO_FFT_B") ? std::atoi(std::getenv("BHOLO_FFT_B")) : 2;
+    static const int selC = std::getenv("BHOLO_FFT_C") ? std::atoi(std::getenv("BHOLO_FFT_C")) : 2;
     auto kA = k2_rows_fwd_real<P>;
-    auto kB = k2_cols<P, true>;
+    auto kB = selB == 3 ? k2_cols<P, true, true> : k2_cols<P, true, false>;
     auto kC = k2_rows_inv_group<P>;
+    auto kA1 = k_rows_fwd<P, 1, int8_t, false>;
+    auto kB1 = k_cols_herm<P, 1>;
+    auto kC1 = k_rows_inv_group<P, 1>;
+    const size_t smr1 = FftCfg<P>::smem_row, smc1 = FftCfg<P>::smem_col;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smA)))) return e;
     if ((e = cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smB)))) return e;
     if ((e = cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smC)))) return e;
+    if ((e = cudaFuncSetAttribute(kA1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smr1)))) return e;
+    if ((e = cudaFuncSetAttribute(kB1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * smc1)))) return e;
+    if ((e = cudaFuncSetAttribute(kC1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * smr1)))) return e;
     CUtensorMap map_buf, map_h;
     const int frames = groups * Fg;
     if (make_tile_map(&map_buf, U, P, frames) || make_tile_map(&map_h, H_all, P, G_total)) return cudaErrorNotSupported;
+    const size_t n2 = size_t(P) * P;
     if (ev) cudaEventRecord(ev[0], st);
     const int n_pairs = frames * (P / 2);
-    kA<<<std::min((n_pairs + ROWS_WARPS - 1) / ROWS_WARPS, sms * 4 * 4), 32 * ROWS_WARPS, smA, st>>>(state, U, tw, n_pairs);
+    if (selA == 1) {
+        kA1<<<dim3(P / (2 * TILE_W), frames), FftCfg<P>::T, smr1, st>>>(state, U, tw);
+    } else {
+        kA<<<std::min((n_pairs + ROWS_WARPS - 1) / ROWS_WARPS, sms * 4 * 4), 32 * ROWS_WARPS, smA, st>>>(state, U, tw, n_pairs);
+    }
     if (ev) cudaEventRecord(ev[1], st);
-    const int tiles = groups * (P / (2 * COLW) + 1) * Fg;
-    kB<<<std::min(tiles, sms * 2), 32 * COLW, smB, st>>>(map_buf, map_h, U, tw, groups, Fg, h_group0);
+    if (selB == 1) {
+        for (int g = 0; g < groups; ++g)
+            kB1<<<dim3(P / (2 * FftCfg<P>::WC) + 1, Fg), FftCfg<P>::TC, 2 * smc1, st>>>(
+                U + size_t(g) * Fg * n2, H_all + size_t(h_group0 + g) * n2, tw);
+    } else {
+        const int tiles = groups * (P / (2 * COLW) + 1) * Fg;
+        kB<<<std::min(tiles, sms * 2), 32 * COLW, smB, st>>>(map_buf, map_h, U, tw, groups, Fg, h_group0);
+    }
     if (ev) cudaEventRecord(ev[2], st);
-    kC<<<std::min(groups * P, sms * 2 * 4), 32 * INVG_WARPS, smC, st>>>(U, I, T, tw, groups, Fg, partial);
+    if (selC == 1) {
+        for (int g = 0; g < groups; ++g)
+            kC1<<<dim3(P / TILE_W, 1), FftCfg<P>::T, 2 * smr1, st>>>(
+                U + size_t(g) * Fg * n2, U + size_t(g) * Fg * n2, I + size_t(g) * n2, T + size_t(g) * n2, tw, Fg,
+                partial + size_t(g) * (P / TILE_W) * 3);
+    } else {
+        kC<<<std::min(groups * P, sms * 2 * 4), 32 * INVG_WARPS, smC, st>>>(U, I, T, tw, groups, Fg, partial);
+    }
     if (ev) cudaEventRecord(ev[3], st);
     return cudaGetLastError();
 }
@@ -182,7 +212,7 @@ static cudaError_t launch_prop2_cplx(const float2* in, float2* U, const float2* 
     constexpr size_t row_smem = size_t(RowLaySize<P, RA>::value) * sizeof(float2);
     const size_t smA = ROWS_WARPS * row_smem, smB = cols2_smem_bytes<P>();
     auto kA = k2_rows_fwd_cplx<P>;
-    auto kB = k2_cols<P, false>;
+    auto kB = k2_cols<P, false, false>;
     auto kC = k2_rows_inv<P>;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smA)))) return e;
@@ -296,6 +326,8 @@ static int propagate_env(bh_ctx* c, int env, float* pass_ms = nullptr) {
         for (auto& e : ev) BH_CUDA(c, cudaEventCreate(&e));
     if (use_fft2(c)) {
         const int per_call = c->fft2_grouped ? 1 : c->G;
+        if (std::getenv("BHOLO_FFT_C"))     // experiment: the round-1 pass C fills only half of the partial slots
+            BH_CUDA(c, cudaMemsetAsync(c->dloss_partial, 0, size_t(c->G) * c->N * 3 * sizeof(double), c->stream));
         for (int g0 = 0; g0 < c->G; g0 += per_call) {
             const int8_t* st = c->dstate + (size_t(env) * c->F + size_t(g0) * c->Fg) * n2;
             float2* U = c->dU + (size_t(env) * c->F + size_t(g0) * c->Fg) * n2;

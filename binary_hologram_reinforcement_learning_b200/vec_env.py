@@ -94,6 +94,7 @@ class HologramVecEnv:
         self._sub_eids = np.zeros(self.num_envs, dtype=np.int32)
         self._blocks_by_mode = {}
         self._cur = 0
+        self._obs_cache = [None] * self.num_envs
         self.set_recon_obs(recon_obs)
         self._group = reward_mode == "group"
         self._changes = self._ranks = None      # (E, num_samples) tables of env_group.py:90-143
@@ -110,7 +111,6 @@ class HologramVecEnv:
         self._tdiff = np.full(E, float(T_PSNR_DIFF))
         self._tpsnr = np.full(E, float(T_PSNR))
         self._maxsteps = np.full(E, int(max_steps), dtype=np.int64)
-        self._obs_cache = [None] * E
         self._rewards = np.zeros(E)
         self._change = np.zeros(E)
         self._diff = np.zeros(E)
