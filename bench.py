@@ -318,17 +318,22 @@ def make_vec(bh, E, rank, local, recon_obs, N=N_SIDE, F=FRAMES, wl=None, seed0=0
                              seed=rank, **kw)
 
 
-def dbs_block(eng, env, rng, peak, torch):
-    """Greedy DBS (DBS_1024_24.py:313-422) candidates/s at three accept-rate regimes of ONE 1024^2 x 24 target.
+def dbs_block(eng, env, rng, peak, torch, n_env):
+    """Greedy DBS (DBS_1024_24.py:313-422) candidates/s at three accept-rate regimes of ONE 1024^2 x 24 target,
+    plus the dataset form (bh_dbs_run_batch: one candidate per image and launch, n_env images in flight).
 
-    fresh: the random initial hologram.  mid / late: after 12 / 60 rounds of a parallel pre-pass that is NOT the
+    fresh: the random initial hologram.  mid / late: after rounds of a parallel pre-pass that is NOT the
     reference's algorithm, only a quick way to a well-optimised state for the measurement: score every pixel
-    (bh_sweep_all), take the best improving candidate of every 64 x 64 tile and frame, run them through the
-    greedy loop.  Roofline per regime: (16 N^2 per scored candidate + 24 N^2 per kept flip) / time -- discarded
-    speculation is not credited."""
+    (bh_sweep_all), flip the best improving pixel of every 32 x 32 tile of every frame directly in the
+    device-resident state, re-propagate (a round is undone if it lowered the PSNR).  Roofline per regime:
+    (16 N^2 per scored candidate + 24 N^2 per kept flip) / time -- discarded speculation is not credited."""
+    from binary_hologram_reinforcement_learning_b200.engine import DeviceArray
     n2 = N_SIDE * N_SIDE
     n_pix = FRAMES * n2
     d_map = torch.empty(n_pix, dtype=torch.float64, device="cuda")
+    state_all = torch.as_tensor(DeviceArray(eng.device_ptr("state"), (eng.n_env, FRAMES, N_SIDE, N_SIDE), "|i1", owner=eng),
+                                device="cuda")
+    state = state_all[env]
     out = {}
 
     def measure(label, n_cand):
@@ -343,7 +348,7 @@ def dbs_block(eng, env, rng, peak, torch):
                       "accept_rate": nacc / order.size, "psnr": psnr,
                       "hbm_frac_useful_bytes": useful / dt / 1e9 / peak}
 
-    def prepass(rounds, tile=64):
+    def prepass(rounds, tile=32):
         for _ in range(rounds):
             eng.sweep_all_device(env, d_map.data_ptr())
             eng.stream_sync()
@@ -354,21 +359,37 @@ def dbs_block(eng, env, rng, peak, torch):
             t = t.reshape(FRAMES, N_SIDE // tile, N_SIDE // tile, tile * tile)
             best, arg = t.max(dim=-1)
             f, ty, tx = torch.nonzero(best > 0, as_tuple=True)
+            if f.numel() == 0:
+                break
             a = arg[f, ty, tx]
             y = (ty * tile + a // tile - oy) % N_SIDE
             x = (tx * tile + a % tile - ox) % N_SIDE
-            acts = (f * n2 + y * N_SIDE + x)[torch.argsort(best[f, ty, tx], descending=True)]
-            if acts.numel() == 0:
-                break
-            eng.dbs_run(acts.cpu().numpy(), env=env, k_spec=0, resync_every=4096)
+            state[f, y, x] = 1 - state[f, y, x]
+            torch.cuda.synchronize()
+            eng.resync(env)
+            if eng.metrics(env)[0] < p0:                 # interacting flips: undo the round
+                state[f, y, x] = 1 - state[f, y, x]
+                torch.cuda.synchronize()
+                eng.resync(env)
+                tile = min(128, tile * 2)
 
     measure("fresh", 40000)
     t0 = time.perf_counter()
-    prepass(12)
+    prepass(40)
     measure("mid", 40000)
-    prepass(48)
-    out["prepass_seconds"] = time.perf_counter() - t0 - 0.0
+    prepass(160)
+    out["prepass_seconds"] = time.perf_counter() - t0
     measure("late", 40000)
+    # dataset form: n_env images in flight, no speculation (state of the envs as the rollouts left it)
+    n_it = 6000
+    orders = np.stack([rng.permutation(n_pix)[:n_it] for _ in range(n_env)])
+    eng.stream_sync()
+    t0 = time.perf_counter()
+    acc, _, nacc, _ = eng.dbs_run_batch(orders, resync_every=0)
+    dt = time.perf_counter() - t0
+    out["batch_images_in_flight"] = {"images": n_env, "candidates": int(orders.size), "candidates_per_s": orders.size / dt,
+                                     "accept_rate": float(nacc.sum()) / orders.size,
+                                     "hbm_frac_useful_bytes": (orders.size * 16.0 + float(nacc.sum()) * 24.0) * n2 / dt / 1e9 / peak}
     return out
 
 
@@ -391,6 +412,11 @@ def group_block(bh, bdist, rank, local):
                                 device=local, reward_mode="group", recon_obs="lazy", verbose=False, seed=rank)
         vec.reset_groups(M)                              # warm (tables, allocations)
         vec.engine.stream_sync()
+        cand = np.random.default_rng(5 + rank).integers(0, F * N * N, size=10000)
+        vec.engine.eval_flips(cand, env=0)
+        t0 = time.perf_counter()
+        vec.engine.eval_flips(cand, env=0)               # the scoring itself (env_group.py:96-119)
+        t_score = time.perf_counter() - t0
         bdist.barrier()
         t0 = time.perf_counter()
         vec.reset_groups(M)
@@ -408,8 +434,10 @@ def group_block(bh, bdist, rank, local):
         vec.engine.stream_sync()
         t_roll = bdist.max_over_ranks(time.perf_counter() - t0)
         world = bdist.env_info()[1]
-        out[name] = {"envs_per_gpu": E, "group_size": M, "reset_groups_s": t_reset,
-                     "candidates_scored_per_s_at_reset": world * (E // M) * 10000 / t_reset,
+        out[name] = {"envs_per_gpu": E, "group_size": M,
+                     "reset_groups_s_incl_host_mirrors_and_synthetic_targets": t_reset,
+                     "importance_scoring_ms_10000_candidates": 1e3 * t_score,
+                     "candidates_scored_per_s": world * 10000 / t_score,
                      "rollout_env_steps_per_s": world * E * 512 / t_roll}
         vec.close()
     return out
@@ -428,7 +456,8 @@ def sharded_sweep_block(bh, bdist, rank, world, local):
     att, imp, gains = bdist.reduce_histograms(r["attempted"], r["improved"], r["gains"])
     dt = bdist.max_over_ranks(time.perf_counter() - t0)
     n_all = FRAMES * 896 * 896
-    return {"candidates": n_all, "seconds_incl_setup": dt, "flip_evals_per_s": n_all / dt,
+    return {"candidates": n_all, "seconds_incl_setup": dt, "sweep_seconds": bdist.max_over_ranks(r["seconds"]),
+            "flip_evals_per_s": n_all / bdist.max_over_ranks(r["seconds"]),
             "attempted_total": int(np.sum(att)), "improved_total": int(np.sum(imp))}
 
 
@@ -589,7 +618,7 @@ def run_b200(args):
                       "sweep_all_ms_25M_candidates": sweep_all_s * 1e3})
         # ---- greedy DBS at three regimes (env 1), the metric's second half ----
         with torch.cuda.stream(stream):
-            dbs = dbs_block(eng, min(1, E - 1), rng, peak, torch)
+            dbs = dbs_block(eng, min(1, E - 1), rng, peak, torch, E)
         if args.dbs_full:
             order = np.random.default_rng(31).permutation(n_pix)
             eng.load_state(E - 1, vec.envs[E - 1].state[0] * 0 + (vec.envs[E - 1].observation[0] >= 0.5))

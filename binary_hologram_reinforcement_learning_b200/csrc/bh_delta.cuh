@@ -88,6 +88,8 @@ struct DeltaArgs {
     int inl_envs[32];
     // bundled evaluation (k_eval_bundle_t): order a speculation window by frame inside the CTA
     int sort_window;
+    // batched greedy DBS (bh_dbs_run_batch): decision / PSNR log of this iteration, [n_tasks]
+    uint8_t* log_accept; double* log_psnr;
     // observation bookkeeping: k_commit marks the plane of a kept flip stale in every
     // observation buffer (see k_recon_plan); [E][RECON_MAX_BUFFERS] or nullptr
     uint8_t* recon_stale;
@@ -283,6 +285,8 @@ __device__ __forceinline__ void write_result(const DeltaArgs& a, int k, const De
     r.action = act; r.accept = acc; r.sgn = sg;
     a.results[k] = r;
     if (a.results_host) a.results_host[k] = r;
+    if (a.log_accept) a.log_accept[k] = uint8_t(acc);
+    if (a.log_psnr) a.log_psnr[k] = psnr;
     a.acc[2 * k] = 0ull; a.acc[2 * k + 1] = 0ull;
     (void)d;
 }

@@ -44,17 +44,19 @@ template <int P, bool REV> struct Plan2 {
 //   wr(j, r): position p = j RA + r   (pass 1, thread j, output r)
 //   rd(j, r): position p = j + r RA   (pass 2, thread j, input r)
 // Row layout: one padding slot after every RA elements (lanes j -> stride RA + 1: 2-way = ideal for 8-byte
-// words).  Column layout: W = 4 sequences interleaved, dense (TMA tiles alias these buffers), the two low
-// position bits XORed with the block index p / RA -- a bijection inside each block since 4 | RA.
+// words).  Column layout: W sequences interleaved, dense (TMA tiles alias these buffers), the two low
+// position bits XORed with the block index p / RA -- a bijection inside each block since 4 | RA (W = 4 or 8
+// sequences interleaved: the 16 threads of a half-warp are 4 or 2 consecutive j, which land in distinct bank groups).
 template <int RA> struct RowLay {
     static __device__ __forceinline__ int wr(int j, int r) { return j * (RA + 1) + r; }
     static __device__ __forceinline__ int rd(int j, int r) { return j + r * (RA + 1); }
 };
 template <int P, int RA> struct RowLaySize { static constexpr int value = P + P / RA; };
-constexpr int COLW = 4;
-template <int RA> struct ColLay {
-    static __device__ __forceinline__ int wr(int j, int r) { return ((j * RA + r) ^ (j & 3)) * COLW; }
-    static __device__ __forceinline__ int rd(int j, int r) { return ((j + r * RA) ^ (r & 3)) * COLW; }
+template <int W> struct ColLayW {
+    template <int RA> struct L {
+        static __device__ __forceinline__ int wr(int j, int r) { return ((j * RA + r) ^ (j & 3)) * W; }
+        static __device__ __forceinline__ int rd(int j, int r) { return ((j + r * RA) ^ (r & 3)) * W; }
+    };
 };
 
 template <int P, bool INV, bool REV, template <int> class Lay>
@@ -302,6 +304,138 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// 1-D bulk copy global -> shared (TMA without a tensor map; SASS: UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// dense row buffer used in place for the exchange: the low 4 position bits XORed with the block index
+// (p / RA) -- conflict-free for the 16 lanes of a half-warp in both directions, a bijection inside each
+// block since 16 | RA
+template <int RA> struct RowSwz {
+    static __device__ __forceinline__ int wr(int j, int r) { return (j * RA + r) ^ (j & 15); }
+    static __device__ __forceinline__ int rd(int j, int r) { return (j + r * RA) ^ (r & 15); }
+};
+
+// ---------------------------------------------------------------------------
+// pass C (fused), TMA-fed: one persistent CTA per SM, 8 warps = 8 frames of one (colour group, window row)
+// task.  Every warp owns two 8 KB row buffers and two mbarriers: while it transforms its row of task i out of
+// one buffer (pass 1 reads the row as the bulk copy left it, the exchange happens in place, XOR-swizzled), the
+// bulk copy of its row of task i + 1 lands in the other -- the rows are contiguous 8 KB runs, the shape a bulk
+// copy is made for.  U is stored from registers, |U|^2 goes to a per-warp slice of shared memory, the CTA adds
+// the slices in frame order -> I row + float64 loss partials (same arithmetic as k2_rows_inv_group).
+// ---------------------------------------------------------------------------
+template <int P> constexpr size_t invg3_smem_bytes() {
+    return size_t(INVG_WARPS) * 2 * P * sizeof(float2) + size_t(INVG_WARPS) * P * sizeof(float) + 128 + INVG_WARPS * 2 * 8;
+}
+
+template <int P>
+__global__ void __launch_bounds__(32 * INVG_WARPS, 1)
+k3_rows_inv_group(float2* U, float* __restrict__ I, const float* __restrict__ T, const float2* __restrict__ tw,
+                  int G, int Fg, double* __restrict__ partial) {
+    constexpr int RA = Plan2<P, false>::RA, RB = Plan2<P, false>::RB;
+    constexpr unsigned ROW_BYTES = unsigned(P) * sizeof(float2);
+    extern __shared__ __align__(128) float2 s2a[];
+    float2* rows = s2a;
+    float* sq_all = reinterpret_cast<float*>(rows + size_t(INVG_WARPS) * 2 * P);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sq_all + size_t(INVG_WARPS) * P);
+    __shared__ double shd[3][INVG_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float2* my_rows = rows + size_t(warp) * 2 * P;
+    uint64_t* my_bar = bars + warp * 2;
+    float* sq = sq_all + warp * P;
+    const size_t n2 = size_t(P) * P;
+    const float inv = 1.f / float(Fg);
+    const int n_tasks = G * P;
+    const int rounds = (Fg + INVG_WARPS - 1) / INVG_WARPS;
+    // the sequence of (task, round) items of this CTA; item k uses buffer k & 1
+    const int my_tasks = (n_tasks - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+    const int n_items = my_tasks * rounds;
+    if (lane == 0) { mbar_init(&my_bar[0], 1); mbar_init(&my_bar[1], 1); fence_barrier_init(); }
+    __syncwarp();
+    auto row_of = [&](int item) -> float2* {
+        const int task = int(blockIdx.x) + (item / rounds) * int(gridDim.x);
+        const int fi = (item % rounds) * INVG_WARPS + warp;
+        const int g = task / P, y = task - g * P;
+        return fi < Fg ? U + (size_t(g) * Fg + fi) * n2 + size_t(y) * P : nullptr;
+    };
+    auto prefetch = [&](int item) {                    // lane 0
+        const float2* src = row_of(item);
+        if (src) {
+            mbar_expect_tx(&my_bar[item & 1], ROW_BYTES);
+            bulk_load(my_rows + size_t(item & 1) * P, src, ROW_BYTES, &my_bar[item & 1]);
+        }
+    };
+    if (lane == 0 && n_items > 0) prefetch(0);
+    unsigned phase[2] = {0u, 0u};
+    for (int item = 0; item < n_items; ++item) {
+        const int task = int(blockIdx.x) + (item / rounds) * int(gridDim.x);
+        const int round = item % rounds;
+        const int g = task / P, y = task - g * P;
+        float2* row = row_of(item);
+        float2* sb = my_rows + size_t(item & 1) * P;
+        if (item + 1 < n_items) {
+            // the other buffer was last written by this warp's exchange of item - 1: order those
+            // generic-proxy accesses before the bulk copy that overwrites it
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) prefetch(item + 1);
+        }
+        if (row) {
+            mbar_wait(&my_bar[item & 1], phase[item & 1]); phase[item & 1] ^= 1u;
+            float2 v[32];
+            if (RB == 32 || lane < RB) {
+#pragma unroll
+                for (int r = 0; r < RA; ++r) v[r] = sb[lane + r * RB];
+            }
+            __syncwarp();                              // every lane has its inputs before the in-place exchange
+            fft2_pass1<P, true, false, RowSwz>(v, sb, lane);
+            __syncwarp();
+            fft2_pass2<P, true, false, RowSwz>(v, sb, lane, tw);
+            float2* dst = row + lane;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                dst[r * RA] = v[r];
+                const float a = fmaf(v[r].x, v[r].x, v[r].y * v[r].y);
+                if (round == 0) sq[lane + r * RA] = a; else sq[lane + r * RA] += a;
+            }
+        }
+        if (round != rounds - 1) continue;
+        __syncthreads();
+        double a = 0, b = 0, c = 0;
+        if (tid < P / 4) {
+            const int nw = Fg < INVG_WARPS ? Fg : INVG_WARPS;
+            float4 acc = *reinterpret_cast<const float4*>(sq_all + 4 * tid);
+            for (int w = 1; w < nw; ++w) {
+                const float4 q = *reinterpret_cast<const float4*>(sq_all + w * P + 4 * tid);
+                acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+            }
+            const size_t p = size_t(g) * n2 + size_t(y) * P + 4 * tid;
+            const float4 tv = __ldg(reinterpret_cast<const float4*>(T + p));
+            const float4 iv = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+            *reinterpret_cast<float4*>(I + p) = iv;
+            a = double(iv.x) * iv.x + double(iv.y) * iv.y + double(iv.z) * iv.z + double(iv.w) * iv.w;
+            b = double(iv.x) * tv.x + double(iv.y) * tv.y + double(iv.z) * tv.z + double(iv.w) * tv.w;
+            c = double(tv.x) * tv.x + double(tv.y) * tv.y + double(tv.z) * tv.z + double(tv.w) * tv.w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        if (lane == 0) { shd[0][warp] = a; shd[1][warp] = b; shd[2][warp] = c; }
+        __syncthreads();
+        if (tid == 0) {
+            double x = 0, yv = 0, z = 0;
+            for (int i = 0; i < INVG_WARPS; ++i) { x += shd[0][i]; yv += shd[1][i]; z += shd[2][i]; }
+            double* out = partial + size_t(task) * 3;
+            out[0] = x; out[1] = yv; out[2] = z;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // pass B: for tiles of COLW = 4 canvas columns: FFT along y, multiply by H, inverse FFT along y, in place on
 // buf (H carries 1/P^2).  Persistent CTAs of 128 threads (thread = column w x butterfly slot j), 2 per SM,
@@ -315,27 +449,28 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 // HERM = false (complex input): every column is transformed, no mirror column.
 // Four CTA barriers per tile; shared memory 3 x 8 P W bytes = 96 KB at P = 1024 (cols2_smem_bytes).
 // ---------------------------------------------------------------------------
-template <int P> constexpr size_t cols2_smem_bytes() { return size_t(3) * P * COLW * sizeof(float2) + 128 + 16; }
+template <int P, int W> constexpr size_t cols2_smem_bytes() { return size_t(3) * P * W * sizeof(float2) + 128 + 16; }
 
 // IN_TMA = false: the input tile is gathered straight into the butterfly registers (32-byte row segments,
 // 8 rows per warp instruction) instead of through s_in; only the H tile (shared by the Fg frames of a column
 // tile) arrives by TMA.
-template <int P, bool HERM, bool IN_TMA>
-__global__ void __launch_bounds__(32 * COLW, 2)
+template <int P, bool HERM, bool IN_TMA, int W>
+__global__ void __launch_bounds__(32 * W, W == 4 ? 2 : 1)
 k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUtensorMap map_h,
         float2* buf, const float2* __restrict__ tw, int n_groups, int Fg, int h_group0) {
-    constexpr int W = COLW;
     constexpr int RA = Plan2<P, false>::RA, RB = Plan2<P, false>::RB;     // forward (RA, RB), inverse (RB, RA)
     constexpr int NT = HERM ? P / (2 * W) + 1 : P / W;                    // column tiles per frame
     constexpr unsigned TILE_BYTES = unsigned(P) * W * sizeof(float2);
-    extern __shared__ unsigned char smem_raw[];        // 3 tiles + 128 B alignment slack + 2 mbarriers
-    float2* s_in = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    // 3 tiles + 2 mbarriers.  The array is declared 128-byte aligned (TMA destination) and indexed directly: an
+    // address laundered through an integer makes the compiler emit generic LD / ST instead of LDS / STS.
+    extern __shared__ __align__(128) float2 s2a[];
+    float2* s_in = s2a;
     float2* s_h = s_in + P * W;
     float2* s_wk = s_h + P * W;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_wk + P * W);
     uint64_t& bar_in = bars[0];
     uint64_t& bar_h = bars[1];
-    const int tid = threadIdx.x, w = tid & (W - 1), j = tid >> 2;
+    const int tid = threadIdx.x, w = tid & (W - 1), j = tid / W;
     const long long total = (long long)n_groups * NT * Fg;
     const int beg = int((long long)blockIdx.x * total / gridDim.x);
     const int end = int((long long)(blockIdx.x + 1) * total / gridDim.x);
@@ -380,13 +515,13 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
             if (RB == 32 || j < RB) {
                 const float2* src = frame + size_t(j) * P + kx;
 #pragma unroll
-                for (int r = 0; r < RA; ++r) v[r] = __ldcg(src + size_t(r) * RB * P);
+                for (int r = 0; r < RA; ++r) v[r] = src[size_t(r) * RB * P];
             }
             __syncthreads();                           // B0 (the loads are in flight across it)
         }
-        fft2_pass1<P, false, false, ColLay>(v, s_wk + w, j);
+        fft2_pass1<P, false, false, ColLayW<W>::template L>(v, s_wk + w, j);
         __syncthreads();                               // B1
-        fft2_pass2<P, false, false, ColLay>(v, s_wk + w, j, tw);
+        fft2_pass2<P, false, false, ColLayW<W>::template L>(v, s_wk + w, j, tw);
         if (h_pending) { mbar_wait(&bar_h, ph_h); ph_h ^= 1u; h_pending = false; }
         // thread j < RA holds F[j + r RA], r < RB: the entry pattern of the reversed plan
         float2 a[32];
@@ -394,9 +529,9 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
 #pragma unroll
             for (int r = 0; r < RB; ++r) a[r] = cmul(v[r], s_h[(j + r * RA) * W + w]);
         }
-        fft2_pass1<P, true, true, ColLay>(a, s_in + w, j);
+        fft2_pass1<P, true, true, ColLayW<W>::template L>(a, s_in + w, j);
         __syncthreads();                               // B2
-        fft2_pass2<P, true, true, ColLay>(a, s_in + w, j, tw);
+        fft2_pass2<P, true, true, ColLayW<W>::template L>(a, s_in + w, j, tw);
         if (col_ok && (RB == 32 || j < RB)) {          // thread j < RB holds out[j + r RB], r < RA
 #pragma unroll
             for (int r = 0; r < RA; ++r) frame[size_t(j + r * RB) * P + kx] = a[r];
@@ -409,7 +544,7 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
                     a[r] = cmul(v[r], make_float2(hv.x, -hv.y));
                 }
             }
-            fft2_pass1<P, true, true, ColLay>(a, s_wk + w, j);
+            fft2_pass1<P, true, true, ColLayW<W>::template L>(a, s_wk + w, j);
         }
         fence_proxy_async();                           // s_in was written by threads; the next TMA overwrites it
         __syncthreads();                               // B3: all reads of s_in and s_h are done
@@ -419,7 +554,7 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
             h_pending = new_h;
         }
         if (HERM) {
-            fft2_pass2<P, true, true, ColLay>(a, s_wk + w, j, tw);
+            fft2_pass2<P, true, true, ColLayW<W>::template L>(a, s_wk + w, j, tw);
             if (mirror_ok && (RB == 32 || j < RB)) {
 #pragma unroll
                 for (int r = 0; r < RA; ++r) frame[size_t(j + r * RB) * P + (P - kx)] = make_float2(a[r].x, -a[r].y);

@@ -64,7 +64,7 @@ struct bh_ctx {
     bool use_pdl = true;
     bool fp64_eval = false;              // per-quad arithmetic of the delta evaluation in double (BHOLO_EVAL_FP64=1)
     bool fft2 = true;                    // register-resident passes (bh_fft2.cuh) where the side allows
-    bool fft2_grouped = false;           // launch them colour group by colour group
+    int fft2_mode = 1;                   // launch shape of those passes, see propagate_env
     int sms = 148;
     // observation path (bh_recon_batch)
     uint8_t* d_recon_stale = nullptr;    // [E][RECON_MAX_BUFFERS]
@@ -126,13 +126,13 @@ static encode_tiled_fn tensor_map_encoder() {
     }();
     return fn;
 }
-// [planes][P][P] complex64 seen as float32 [planes][P][2 P]; box = COLW columns x P/4 rows of one plane
-static int make_tile_map(CUtensorMap* map, const float2* base, int P, int planes) {
+// [planes][P][P] complex64 seen as float32 [planes][P][2 P]; box = colw columns x P/4 rows of one plane
+static int make_tile_map(CUtensorMap* map, const float2* base, int P, int planes, int colw) {
     encode_tiled_fn enc = tensor_map_encoder();
     if (!enc) return -1;
     const cuuint64_t dims[3] = {cuuint64_t(2) * P, cuuint64_t(P), cuuint64_t(planes)};
     const cuuint64_t strides[2] = {cuuint64_t(P) * sizeof(float2), cuuint64_t(P) * P * sizeof(float2)};
-    const cuuint32_t box[3] = {cuuint32_t(2 * COLW), cuuint32_t(P / 4), 1u};
+    const cuuint32_t box[3] = {cuuint32_t(2 * colw), cuuint32_t(P / 4), 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float2*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -147,19 +147,22 @@ struct Prop2Cfg { int sms = 0; bool ready = false; };
 template <int P>
 static cudaError_t launch_prop2_state(const int8_t* state, float2* U, float* I, const float* T, const float2* H_all,
                                       int G_total, int h_group0, const float2* tw, int groups, int Fg, double* partial,
-                                      int sms, cudaStream_t st, cudaEvent_t* ev) {
+                                      int sms, cudaStream_t st, cudaEvent_t* ev, int phases = 3) {
     constexpr int RA = Plan2<P, false>::RA;
     constexpr size_t row_smem = size_t(RowLaySize<P, RA>::value) * sizeof(float2);
-    const size_t smA = ROWS_WARPS * row_smem, smB = cols2_smem_bytes<P>();
+    static const int colw = std::getenv("BHOLO_FFT_W") ? std::atoi(std::getenv("BHOLO_FFT_W")) : 8;
+    const size_t smA = ROWS_WARPS * row_smem, smB = colw == 8 ? cols2_smem_bytes<P, 8>() : cols2_smem_bytes<P, 4>();
     const size_t smC = INVG_WARPS * row_smem + size_t(INVG_WARPS) * P * sizeof(float);
     // experiment switches (profiles/r2_notes.md): BHOLO_FFT_A / _B / _C = 1 selects the shared-memory kernel of
     // round 1 for that pass (launched per colour group), BHOLO_FFT_B = 3 the TMA-staged input tile
     static const int selA = std::getenv("BHOLO_FFT_A") ? std::atoi(std::getenv("BHOLO_FFT_A")) : 2;
-    static const int selB = std::getenv("BHOLO_FFT_B") ? std::atoi(std::getenv("BHOLO_FFT_B")) : 2;
+    static const int selB = std::getenv("BHOLO_FFT_B") ? std::atoi(std::getenv("BHOLO_FFT_B")) : 3;
     static const int selC = std::getenv("BHOLO_FFT_C") ? std::atoi(std::getenv("BHOLO_FFT_C")) : 2;
     auto kA = k2_rows_fwd_real<P>;
-    auto kB = selB == 3 ? k2_cols<P, true, true> : k2_cols<P, true, false>;
+    auto kB = colw == 8 ? (selB == 3 ? k2_cols<P, true, true, 8> : k2_cols<P, true, false, 8>)
+                        : (selB == 3 ? k2_cols<P, true, true, 4> : k2_cols<P, true, false, 4>);
     auto kC = k2_rows_inv_group<P>;
+    auto kC3 = k3_rows_inv_group<P>;
     auto kA1 = k_rows_fwd<P, 1, int8_t, false>;
     auto kB1 = k_cols_herm<P, 1>;
     auto kC1 = k_rows_inv_group<P, 1>;
@@ -168,28 +171,47 @@ static cudaError_t launch_prop2_state(const int8_t* state, float2* U, float* I, 
     if ((e = cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smA)))) return e;
     if ((e = cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smB)))) return e;
     if ((e = cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smC)))) return e;
+    if ((e = cudaFuncSetAttribute(kC3, cudaFuncAttributeMaxDynamicSharedMemorySize, int(invg3_smem_bytes<P>())))) return e;
     if ((e = cudaFuncSetAttribute(kA1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smr1)))) return e;
     if ((e = cudaFuncSetAttribute(kB1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * smc1)))) return e;
     if ((e = cudaFuncSetAttribute(kC1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * smr1)))) return e;
     CUtensorMap map_buf, map_h;
     const int frames = groups * Fg;
-    if (make_tile_map(&map_buf, U, P, frames) || make_tile_map(&map_h, H_all, P, G_total)) return cudaErrorNotSupported;
+    if (make_tile_map(&map_buf, U, P, frames, colw) || make_tile_map(&map_h, H_all, P, G_total, colw)) return cudaErrorNotSupported;
     const size_t n2 = size_t(P) * P;
-    if (ev) cudaEventRecord(ev[0], st);
+    if (ev && (phases & 1)) cudaEventRecord(ev[0], st);
     const int n_pairs = frames * (P / 2);
-    if (selA == 1) {
+    if (!(phases & 1)) {
+    } else if (selA == 1) {
         kA1<<<dim3(P / (2 * TILE_W), frames), FftCfg<P>::T, smr1, st>>>(state, U, tw);
     } else {
         kA<<<std::min((n_pairs + ROWS_WARPS - 1) / ROWS_WARPS, sms * 4 * 4), 32 * ROWS_WARPS, smA, st>>>(state, U, tw, n_pairs);
     }
+    if (!(phases & 2)) {
+        if (ev) cudaEventRecord(ev[1], st);
+        return cudaGetLastError();
+    }
     if (ev) cudaEventRecord(ev[1], st);
+    static const bool rev = std::getenv("BHOLO_FFT_REV") != nullptr;     // most recently written group first (L2)
+    if (selB == 1 && selC == 1 && rev) {
+        // pass B and pass C of a group back to back, groups in reverse order of pass A's writes
+        for (int g = groups - 1; g >= 0; --g) {
+            kB1<<<dim3(P / (2 * FftCfg<P>::WC) + 1, Fg), FftCfg<P>::TC, 2 * smc1, st>>>(
+                U + size_t(g) * Fg * n2, H_all + size_t(h_group0 + g) * n2, tw);
+            kC1<<<dim3(P / TILE_W, 1), FftCfg<P>::T, 2 * smr1, st>>>(
+                U + size_t(g) * Fg * n2, U + size_t(g) * Fg * n2, I + size_t(g) * n2, T + size_t(g) * n2, tw, Fg,
+                partial + size_t(g) * (P / TILE_W) * 3);
+        }
+        if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); }
+        return cudaGetLastError();
+    }
     if (selB == 1) {
         for (int g = 0; g < groups; ++g)
             kB1<<<dim3(P / (2 * FftCfg<P>::WC) + 1, Fg), FftCfg<P>::TC, 2 * smc1, st>>>(
                 U + size_t(g) * Fg * n2, H_all + size_t(h_group0 + g) * n2, tw);
     } else {
-        const int tiles = groups * (P / (2 * COLW) + 1) * Fg;
-        kB<<<std::min(tiles, sms * 2), 32 * COLW, smB, st>>>(map_buf, map_h, U, tw, groups, Fg, h_group0);
+        const int tiles = groups * (P / (2 * colw) + 1) * Fg;
+        kB<<<std::min(tiles, sms * (colw == 8 ? 1 : 2)), 32 * colw, smB, st>>>(map_buf, map_h, U, tw, groups, Fg, h_group0);
     }
     if (ev) cudaEventRecord(ev[2], st);
     if (selC == 1) {
@@ -197,6 +219,8 @@ static cudaError_t launch_prop2_state(const int8_t* state, float2* U, float* I, 
             kC1<<<dim3(P / TILE_W, 1), FftCfg<P>::T, 2 * smr1, st>>>(
                 U + size_t(g) * Fg * n2, U + size_t(g) * Fg * n2, I + size_t(g) * n2, T + size_t(g) * n2, tw, Fg,
                 partial + size_t(g) * (P / TILE_W) * 3);
+    } else if (selC == 3) {
+        kC3<<<std::min(groups * P, sms), 32 * INVG_WARPS, invg3_smem_bytes<P>(), st>>>(U, I, T, tw, groups, Fg, partial);
     } else {
         kC<<<std::min(groups * P, sms * 2 * 4), 32 * INVG_WARPS, smC, st>>>(U, I, T, tw, groups, Fg, partial);
     }
@@ -210,21 +234,22 @@ static cudaError_t launch_prop2_cplx(const float2* in, float2* U, const float2* 
                                      int sms, cudaStream_t st) {
     constexpr int RA = Plan2<P, false>::RA;
     constexpr size_t row_smem = size_t(RowLaySize<P, RA>::value) * sizeof(float2);
-    const size_t smA = ROWS_WARPS * row_smem, smB = cols2_smem_bytes<P>();
+    constexpr int COLW = 8;
+    const size_t smA = ROWS_WARPS * row_smem, smB = cols2_smem_bytes<P, COLW>();
     auto kA = k2_rows_fwd_cplx<P>;
-    auto kB = k2_cols<P, false, false>;
+    auto kB = k2_cols<P, false, true, COLW>;
     auto kC = k2_rows_inv<P>;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smA)))) return e;
     if ((e = cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smB)))) return e;
     if ((e = cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smA)))) return e;
     CUtensorMap map_buf, map_h;
-    if (make_tile_map(&map_buf, U, P, planes) || make_tile_map(&map_h, K, P, 1)) return cudaErrorNotSupported;
+    if (make_tile_map(&map_buf, U, P, planes, COLW) || make_tile_map(&map_h, K, P, 1, COLW)) return cudaErrorNotSupported;
     const int rows = planes * P;
     const int grid_rows = std::min((rows + ROWS_WARPS - 1) / ROWS_WARPS, sms * 4 * 4);
     kA<<<grid_rows, 32 * ROWS_WARPS, smA, st>>>(in, U, tw, rows);
     // one "group" of `planes` frames: every tile uses the same spectrum
-    kB<<<std::min(planes * (P / COLW), sms * 2), 32 * COLW, smB, st>>>(map_buf, map_h, U, tw, 1, planes, 0);
+    kB<<<std::min(planes * (P / COLW), sms), 32 * COLW, smB, st>>>(map_buf, map_h, U, tw, 1, planes, 0);
     kC<<<grid_rows, 32 * ROWS_WARPS, smA, st>>>(U, U, tw, rows);
     return cudaGetLastError();
 }
@@ -325,9 +350,31 @@ static int propagate_env(bh_ctx* c, int env, float* pass_ms = nullptr) {
     if (pass_ms)
         for (auto& e : ev) BH_CUDA(c, cudaEventCreate(&e));
     if (use_fft2(c)) {
-        const int per_call = c->fft2_grouped ? 1 : c->G;
+        // launch shapes (measured, profiles/r2_notes.md): mode 0 all groups per pass; 1 (default) colour group by
+        // colour group, so a group's 100 MB of intermediates stay in the 126 MB L2 between its passes;
+        // 2: pass A for all groups in one launch, passes B and C group by group
+        const int mode = c->fft2_mode;
+        const int per_call = mode == 0 ? c->G : 1;
         if (std::getenv("BHOLO_FFT_C"))     // experiment: the round-1 pass C fills only half of the partial slots
             BH_CUDA(c, cudaMemsetAsync(c->dloss_partial, 0, size_t(c->G) * c->N * 3 * sizeof(double), c->stream));
+        if (mode == 2) {
+            cudaError_t e = cudaErrorNotSupported;
+            if (c->P == 1024)
+                e = launch_prop2_state<1024>(c->dstate + size_t(env) * c->F * n2, c->dU + size_t(env) * c->F * n2, nullptr, nullptr,
+                                             c->dH, c->G, 0, c->dtw, c->G, c->Fg, nullptr, c->sms, c->stream, pass_ms ? ev : nullptr, 1);
+            else if (c->P == 896)
+                e = launch_prop2_state<896>(c->dstate + size_t(env) * c->F * n2, c->dU + size_t(env) * c->F * n2, nullptr, nullptr,
+                                            c->dH, c->G, 0, c->dtw, c->G, c->Fg, nullptr, c->sms, c->stream, pass_ms ? ev : nullptr, 1);
+            BH_CUDA(c, e);
+            c->launches += 1;
+            if (pass_ms) {
+                float ms = 0.f;
+                BH_CUDA(c, cudaEventSynchronize(ev[1]));
+                BH_CUDA(c, cudaEventElapsedTime(&ms, ev[0], ev[1]));
+                pass_ms[0] += ms;
+            }
+        }
+        const int phases = mode == 2 ? 2 : 3;
         for (int g0 = 0; g0 < c->G; g0 += per_call) {
             const int8_t* st = c->dstate + (size_t(env) * c->F + size_t(g0) * c->Fg) * n2;
             float2* U = c->dU + (size_t(env) * c->F + size_t(g0) * c->Fg) * n2;
@@ -336,15 +383,15 @@ static int propagate_env(bh_ctx* c, int env, float* pass_ms = nullptr) {
             double* part = c->dloss_partial + size_t(g0) * c->N * 3;
             cudaError_t e = cudaErrorNotSupported;
             if (c->P == 1024)
-                e = launch_prop2_state<1024>(st, U, I, T, c->dH, c->G, g0, c->dtw, per_call, c->Fg, part, c->sms, c->stream, pass_ms ? ev : nullptr);
+                e = launch_prop2_state<1024>(st, U, I, T, c->dH, c->G, g0, c->dtw, per_call, c->Fg, part, c->sms, c->stream, pass_ms ? ev : nullptr, phases);
             else if (c->P == 896)
-                e = launch_prop2_state<896>(st, U, I, T, c->dH, c->G, g0, c->dtw, per_call, c->Fg, part, c->sms, c->stream, pass_ms ? ev : nullptr);
+                e = launch_prop2_state<896>(st, U, I, T, c->dH, c->G, g0, c->dtw, per_call, c->Fg, part, c->sms, c->stream, pass_ms ? ev : nullptr, phases);
             BH_CUDA(c, e);
-            c->launches += 3;
+            c->launches += (phases == 3 ? 3 : 2);
             if (pass_ms) {
                 BH_CUDA(c, cudaEventRecord(ev[4], c->stream));
                 BH_CUDA(c, cudaEventSynchronize(ev[4]));
-                for (int i = 0; i < 4; ++i) {
+                for (int i = (phases == 2 ? 1 : 0); i < 4; ++i) {
                     float ms = 0.f;
                     BH_CUDA(c, cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
                     pass_ms[i] += ms;
@@ -560,7 +607,7 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
         int nb = 0;
         c->use_pdl = !std::getenv("BHOLO_NO_PDL");
         c->fft2 = fft2_enabled();
-        c->fft2_grouped = std::getenv("BHOLO_FFT_GROUPED") != nullptr;
+        c->fft2_mode = std::getenv("BHOLO_FFT_MODE") ? std::atoi(std::getenv("BHOLO_FFT_MODE")) : 1;
         c->sms = prop.multiProcessorCount;
         const char* ev = std::getenv("BHOLO_EVAL_VARIANT");
         c->fp64_eval = std::getenv("BHOLO_EVAL_FP64") != nullptr;
@@ -673,6 +720,7 @@ static DeltaArgs make_args(bh_ctx* c, int n, int env_fixed, const int32_t* d_env
     a.acc = c->d_acc; a.tickets = c->d_tickets; a.results = d_results;
     a.results_host = nullptr; a.n_inline = 0; a.sort_window = 0;
     a.recon_stale = c->d_recon_stale;
+    a.log_accept = nullptr; a.log_psnr = nullptr;
     a.dbs_accepted = nullptr; a.dbs_trace = nullptr; a.dbs_count = nullptr; a.dbs_cursor = nullptr;
     return a;
 }
@@ -1008,6 +1056,94 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
 #undef BH_DBS
     cleanup();
     if (final_psnr) return bh_get_metrics(c, env, final_psnr, nullptr, nullptr);
+    return 0;
+}
+
+// Greedy DBS of several images at once (the dataset loop of DBS.py:208 / DBS_1024_24.py:211 is independent
+// per image): iteration i scores candidate orders[e][i] of every environment e in ONE k_eval launch and keeps
+// the improving ones in ONE k_commit launch.  No speculation: every evaluation is used, the decisions of each
+// image are exactly those of its sequential loop, and the launch overhead is shared by n_env candidates.
+extern "C" int bh_dbs_run_batch(bh_ctx* c, int n_env, const int32_t* env_ids, const int64_t* orders, int64_t n,
+                                int64_t resync_every, uint8_t* accepted, double* psnr_trace,
+                                int64_t* n_accepted, double* final_psnr) {
+    BH_CHECK_CTX(c);
+    if (n_env < 1 || n_env > c->E || n_env > COMMIT_MAX_TASKS || n < 0 || (n > 0 && (!orders || !accepted)))
+        BH_FAIL(c, -1, "bad arguments");
+    std::vector<int32_t> ids(n_env);
+    std::vector<char> seen(c->E, 0);
+    for (int e = 0; e < n_env; ++e) {
+        ids[e] = env_ids ? env_ids[e] : e;
+        BH_CHECK_ENV(c, ids[e]);
+        if (seen[ids[e]]) BH_FAIL(c, -3, "environment %d appears twice", ids[e]);
+        seen[ids[e]] = 1;
+    }
+    for (int e = 0; e < n_env; ++e)
+        if (int rc = check_actions(c, orders + size_t(e) * n, n)) return rc;
+    const int64_t chunk = std::min<int64_t>(n, 1 << 18);
+    long long* d_ord = nullptr; uint8_t* d_acc = nullptr; double* d_tr = nullptr; int32_t* d_ids = nullptr;
+    long long* h_ord = nullptr; uint8_t* h_acc = nullptr; double* h_tr = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_ord); cudaFree(d_acc); cudaFree(d_tr); cudaFree(d_ids);
+        cudaFreeHost(h_ord); cudaFreeHost(h_acc); cudaFreeHost(h_tr);
+    };
+#define BH_DB(expr)                                                                        \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            cleanup();                                                                     \
+            BH_FAIL(c, -2, "%s failed: %s", #expr, cudaGetErrorString(_e));                \
+        }                                                                                  \
+    } while (0)
+    if (n > 0) {
+        const size_t cells = size_t(chunk) * n_env;
+        BH_DB(cudaMalloc(&d_ord, cells * sizeof(long long)));
+        BH_DB(cudaMalloc(&d_acc, cells));
+        if (psnr_trace) BH_DB(cudaMalloc(&d_tr, cells * sizeof(double)));
+        BH_DB(cudaMalloc(&d_ids, size_t(n_env) * sizeof(int32_t)));
+        BH_DB(cudaMallocHost(&h_ord, cells * sizeof(long long)));
+        BH_DB(cudaMallocHost(&h_acc, cells));
+        if (psnr_trace) BH_DB(cudaMallocHost(&h_tr, cells * sizeof(double)));
+        BH_DB(cudaMemcpyAsync(d_ids, ids.data(), size_t(n_env) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        int64_t since_resync = 0;
+        for (int64_t base = 0; base < n; base += chunk) {
+            const int64_t m = std::min<int64_t>(chunk, n - base);
+            for (int64_t i = 0; i < m; ++i)                     // [iteration][env]
+                for (int e = 0; e < n_env; ++e) h_ord[size_t(i) * n_env + e] = orders[size_t(e) * n + base + i];
+            BH_DB(cudaMemcpyAsync(d_ord, h_ord, size_t(m) * n_env * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+            for (int64_t i = 0; i < m; ++i) {
+                DeltaArgs a = make_args(c, n_env, 0, d_ids, d_ord + size_t(i) * n_env, RULE_DBS, c->d_results);
+                a.log_accept = d_acc + size_t(i) * n_env;
+                a.log_psnr = d_tr ? d_tr + size_t(i) * n_env : nullptr;
+                launch_eval(c, a);
+                launch_commit(c, a);
+                if (resync_every > 0 && ++since_resync >= resync_every && base + i + 1 < n) {
+                    for (int e = 0; e < n_env; ++e)
+                        if (int rc = propagate_env(c, ids[e])) { cleanup(); return rc; }
+                    since_resync = 0;
+                }
+            }
+            BH_DB(cudaGetLastError());
+            BH_DB(cudaMemcpyAsync(h_acc, d_acc, size_t(m) * n_env, cudaMemcpyDeviceToHost, c->stream));
+            if (d_tr) BH_DB(cudaMemcpyAsync(h_tr, d_tr, size_t(m) * n_env * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            BH_DB(cudaStreamSynchronize(c->stream));
+            for (int64_t i = 0; i < m; ++i)
+                for (int e = 0; e < n_env; ++e) {
+                    accepted[size_t(e) * n + base + i] = h_acc[size_t(i) * n_env + e];
+                    if (psnr_trace) psnr_trace[size_t(e) * n + base + i] = h_tr[size_t(i) * n_env + e];
+                }
+        }
+    }
+#undef BH_DB
+    cleanup();
+    for (int e = 0; e < n_env; ++e) {
+        if (n_accepted) {
+            int64_t k = 0;
+            for (int64_t i = 0; i < n; ++i) k += accepted[size_t(e) * n + i];
+            n_accepted[e] = k;
+        }
+        if (final_psnr)
+            if (int rc = bh_get_metrics(c, ids[e], final_psnr + e, nullptr, nullptr)) return rc;
+    }
     return 0;
 }
 

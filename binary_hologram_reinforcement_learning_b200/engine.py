@@ -23,7 +23,7 @@ ABI_SYMBOLS = (
     "bh_abi_version", "bh_last_error", "bh_create", "bh_destroy", "bh_set_stream",
     "bh_set_target", "bh_load_state", "bh_clone_env", "bh_resync", "bh_get_metrics", "bh_eval_flips",
     "bh_step_batch", "bh_vec_step", "bh_vec_book_update", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
-    "bh_commit_flip", "bh_dbs_run", "bh_sweep_all", "bh_sweep_stats", "bh_get_recon", "bh_get_state", "bh_get_field",
+    "bh_commit_flip", "bh_dbs_run", "bh_dbs_run_batch", "bh_sweep_all", "bh_sweep_stats", "bh_get_recon", "bh_get_state", "bh_get_field",
     "bh_recon_batch", "bh_recon_device_block", "bh_recon_planes_written", "bh_stream_sync",
     "bh_device_ptr", "bh_host_alloc", "bh_host_free", "bh_simulate", "bh_time_eval", "bh_time_step", "bh_time_commit",
     "bh_time_propagate", "bh_time_propagate_passes", "bh_launch_count",
@@ -95,6 +95,7 @@ def load_library(build_if_missing: bool = True):
         "bh_max_tasks": (i32, [vp]),
         "bh_commit_flip": (i32, [vp, i32, i64]),
         "bh_dbs_run": (i32, [vp, i32, vp, i64, i32, i64, vp, vp, P(i64), P(dbl)]),
+        "bh_dbs_run_batch": (i32, [vp, i32, vp, vp, i64, i64, vp, vp, vp, vp]),
         "bh_sweep_all": (i32, [vp, i32, vp, i32]),
         "bh_sweep_stats": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
         "bh_get_recon": (i32, [vp, i32, vp, i32, i64]),
@@ -342,6 +343,20 @@ class HoloEngine:
         self._check(self.lib.bh_dbs_run(self._h, env, _ptr(o), n, k_spec, resync_every, _ptr(acc),
                                         _ptr(tr), C.byref(nacc), C.byref(fin)), "bh_dbs_run")
         return acc, tr, int(nacc.value), fin.value
+
+    def dbs_run_batch(self, orders: np.ndarray, env_ids: Optional[np.ndarray] = None, resync_every: int = 0,
+                      trace: bool = False):
+        """Greedy DBS of several images at once: ``orders`` (E, n), one candidate order per environment.
+        Returns (accepted uint8 (E, n), psnr_trace (E, n) | None, n_accepted int64 (E,), final psnr (E,))."""
+        o = np.ascontiguousarray(orders, dtype=np.int64)
+        E, n = o.shape
+        ids = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
+        acc = np.zeros((E, n), dtype=np.uint8)
+        tr = np.zeros((E, n), dtype=np.float64) if trace else None
+        nacc, fin = np.zeros(E, dtype=np.int64), np.zeros(E, dtype=np.float64)
+        self._check(self.lib.bh_dbs_run_batch(self._h, E, _ptr(ids), _ptr(o), n, resync_every, _ptr(acc), _ptr(tr),
+                                              _ptr(nacc), _ptr(fin)), "bh_dbs_run_batch")
+        return acc, tr, nacc, fin
 
     def sweep_all(self, env: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
         """PSNR after flipping each pixel of each frame (fixed state): float64 (F, N, N)."""

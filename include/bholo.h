@@ -170,6 +170,16 @@ int bh_dbs_run(bh_ctx* ctx, int env, const int64_t* order, int64_t n, int k_spec
                int64_t resync_every, uint8_t* accepted, double* psnr_trace,
                int64_t* n_accepted, double* final_psnr);
 
+/* Greedy DBS of n_env images at once: the dataset loop of DBS.py:208 / DBS_1024_24.py:211 is independent per
+ * image, so iteration i scores candidate orders[e][i] of every environment in one launch and keeps the
+ * improving flips in one launch -- no speculation, every evaluation counts, and each image's decisions are
+ * those of its own sequential loop.  orders / accepted / psnr_trace: [n_env][n] (psnr_trace nullable);
+ * env_ids NULL = 0..n_env-1; resync_every (<= 0: never): re-propagate all listed environments every that
+ * many CANDIDATES; n_accepted / final_psnr: [n_env] (nullable). */
+int bh_dbs_run_batch(bh_ctx* ctx, int n_env, const int32_t* env_ids, const int64_t* orders, int64_t n,
+                     int64_t resync_every, uint8_t* accepted, double* psnr_trace,
+                     int64_t* n_accepted, double* final_psnr);
+
 /* Reconstruction float [G][N][N].  candidate_action >= 0 adds the intensity
  * change of that (uncommitted) flip -- obs["recon_image"] of a rejected step
  * (env.py:176-181). */

@@ -964,3 +964,28 @@ def test_fixed_point_range_dark_target_and_tiny_fields():
         assert abs(res["d_sii"] - d_sii) <= 2e-6 * abs(d_sii) + bound, (res["d_sii"], d_sii)
         assert abs(res["d_sit"] - d_sit) <= 2e-6 * abs(d_sit) + bound, (res["d_sit"], d_sit)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_batched_dbs_equals_the_sequential_loop_of_every_image():
+    """bh_dbs_run_batch: several images in flight, one candidate per image and launch; each image's decisions,
+    PSNR trace and final hologram are those of its own sequential greedy loop (bh_dbs_run, no speculation)."""
+    N, F, wl, E, n = 64, 6, O.WL_RGB, 3, 1500
+    eng = _engine(N, F, wl, n_env=E)
+    one = _engine(N, F, wl)
+    rng = np.random.default_rng(4)
+    orders = np.stack([rng.permutation(F * N * N)[:n] for _ in range(E)])
+    probs = [_problem(N, F, wl, 800 + e) for e in range(E)]
+    for e, (pre, tgt, st) in enumerate(probs):
+        eng.set_target(e, tgt)
+        eng.load_state(e, st)
+    acc, tr, nacc, fin = eng.dbs_run_batch(orders, trace=True)
+    for e, (pre, tgt, st) in enumerate(probs):
+        one.set_target(0, tgt)
+        one.load_state(0, st)
+        a1, t1, n1, f1 = one.dbs_run(orders[e], k_spec=1, trace=True)
+        assert np.array_equal(acc[e], a1) and n1 == nacc[e]
+        np.testing.assert_array_equal(tr[e], t1)
+        assert fin[e] == f1
+        assert np.array_equal(eng.state(e), one.state(0))
+    eng.close(); one.close()
