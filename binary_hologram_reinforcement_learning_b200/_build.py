@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libbholo_b200.so")
 SOURCES = ["bholo.cu"]
-HEADERS = ["bh_fft.cuh", "bh_fft2.cuh", "bh_kernels.cuh", "bh_delta.cuh", "bh_tables.hpp",
+HEADERS = ["bh_fft.cuh", "bh_fft2.cuh", "bh_kernels.cuh", "bh_delta.cuh", "bh_async.cuh", "bh_tables.hpp",
            os.path.join("..", "..", "include", "bholo.h")]
 
 NVCC_FLAGS = [

@@ -27,10 +27,17 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "bh_fft.cuh"
+#include "bh_async.cuh"
 
 namespace bh {
 
 constexpr bool fft2_side(int P) { return P == 896 || P == 1024; }
+
+// Programmatic dependent launch between the passes (each pass needs ALL of its predecessor's output, so only the
+// launch latency and the CTA ramp-up overlap): a kernel lets its successor be scheduled at once and waits for
+// its predecessor's memory before its first global access.
+__device__ __forceinline__ void fft_pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void fft_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // radices of the (optionally reversed) two-pass plan and the offset of its twiddle block
 template <int P, bool REV> struct Plan2 {
@@ -106,6 +113,8 @@ k2_rows_fwd_real(const int8_t* __restrict__ state, float2* __restrict__ buf, con
     extern __shared__ float2 s2[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* sw = s2 + warp * SZ;
+    fft_pdl_release();
+    fft_pdl_wait();
     for (int task = blockIdx.x * ROWS_WARPS + warp; task < n_pairs; task += gridDim.x * ROWS_WARPS) {
         const int f = task / (P / 2), yp = task - f * (P / 2);
         const int8_t* pa = state + (size_t(f) * P + 2 * yp) * P + lane;
@@ -218,6 +227,8 @@ k2_rows_inv_group(float2* U, float* __restrict__ I, const float* __restrict__ T,
     float* sq = sq_all + warp * P;
     const size_t n2 = size_t(P) * P;
     const float inv = 1.f / float(Fg);
+    fft_pdl_release();
+    fft_pdl_wait();
     for (int task = blockIdx.x; task < G * P; task += gridDim.x) {
         const int g = task / P, y = task - g * P;
         for (int f0 = 0; f0 < Fg; f0 += INVG_WARPS) {
@@ -273,41 +284,6 @@ k2_rows_inv_group(float2* U, float* __restrict__ I, const float* __restrict__ T,
             out[0] = x; out[1] = yv; out[2] = z;
         }
     }
-}
-
-// ---------------------------------------------------------------------------
-// TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS)
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return unsigned(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-// 1-D bulk copy global -> shared (TMA without a tensor map; SASS: UBLKCP), completion on an mbarrier
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // dense row buffer used in place for the exchange: the low 4 position bits XORed with the block index
@@ -474,12 +450,14 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
     const long long total = (long long)n_groups * NT * Fg;
     const int beg = int((long long)blockIdx.x * total / gridDim.x);
     const int end = int((long long)(blockIdx.x + 1) * total / gridDim.x);
+    fft_pdl_release();
     if (beg >= end) return;
     if (tid == 0) {
         mbar_init(&bar_in, 1); mbar_init(&bar_h, 1);
         fence_barrier_init();
     }
     __syncthreads();
+    fft_pdl_wait();
     auto issue_in = [&](int idx) {                     // one thread
         const int gt = idx / Fg, fi = idx - gt * Fg, g = gt / NT, t = gt - g * NT;
         mbar_expect_tx(&bar_in, TILE_BYTES);

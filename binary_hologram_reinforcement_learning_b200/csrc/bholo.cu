@@ -140,7 +140,19 @@ static int make_tile_map(CUtensorMap* map, const float2* base, int P, int planes
     return r == CUDA_SUCCESS ? 0 : -1;
 }
 
-struct Prop2Cfg { int sms = 0; bool ready = false; };
+// launch with programmatic stream serialization (the kernels call griddepcontrol.wait before their first
+// global access); BHOLO_NO_PDL / BHOLO_FFT_NO_PDL fall back to plain stream order
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    static const bool pdl = !std::getenv("BHOLO_NO_PDL") && !std::getenv("BHOLO_FFT_NO_PDL");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // the three passes over `groups` colour groups of Fg frames each (state / U / I / T point at the first group);
 // H: table of colour group h_group0 + g.  fused: pass C also produces I and the loss partials.
@@ -185,7 +197,7 @@ static cudaError_t launch_prop2_state(const int8_t* state, float2* U, float* I, 
     } else if (selA == 1) {
         kA1<<<dim3(P / (2 * TILE_W), frames), FftCfg<P>::T, smr1, st>>>(state, U, tw);
     } else {
-        kA<<<std::min((n_pairs + ROWS_WARPS - 1) / ROWS_WARPS, sms * 4 * 4), 32 * ROWS_WARPS, smA, st>>>(state, U, tw, n_pairs);
+        launch_pdl(kA, std::min((n_pairs + ROWS_WARPS - 1) / ROWS_WARPS, sms * 4 * 4), 32 * ROWS_WARPS, smA, st, state, U, tw, n_pairs);
     }
     if (!(phases & 2)) {
         if (ev) cudaEventRecord(ev[1], st);
@@ -211,7 +223,7 @@ static cudaError_t launch_prop2_state(const int8_t* state, float2* U, float* I, 
                 U + size_t(g) * Fg * n2, H_all + size_t(h_group0 + g) * n2, tw);
     } else {
         const int tiles = groups * (P / (2 * colw) + 1) * Fg;
-        kB<<<std::min(tiles, sms * (colw == 8 ? 1 : 2)), 32 * colw, smB, st>>>(map_buf, map_h, U, tw, groups, Fg, h_group0);
+        launch_pdl(kB, std::min(tiles, sms * (colw == 8 ? 1 : 2)), 32 * colw, smB, st, map_buf, map_h, U, tw, groups, Fg, h_group0);
     }
     if (ev) cudaEventRecord(ev[2], st);
     if (selC == 1) {
@@ -222,7 +234,7 @@ static cudaError_t launch_prop2_state(const int8_t* state, float2* U, float* I, 
     } else if (selC == 3) {
         kC3<<<std::min(groups * P, sms), 32 * INVG_WARPS, invg3_smem_bytes<P>(), st>>>(U, I, T, tw, groups, Fg, partial);
     } else {
-        kC<<<std::min(groups * P, sms * 2 * 4), 32 * INVG_WARPS, smC, st>>>(U, I, T, tw, groups, Fg, partial);
+        launch_pdl(kC, std::min(groups * P, sms * 2 * 4), 32 * INVG_WARPS, smC, st, U, I, T, tw, groups, Fg, partial);
     }
     if (ev) cudaEventRecord(ev[3], st);
     return cudaGetLastError();

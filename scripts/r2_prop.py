@@ -33,15 +33,18 @@ if len(sys.argv) > 1 and sys.argv[1] == "run":
     bytes_survey = F * (N * N + 32.0 * N * N) + 8.0 * 3 * N * N
     print(json.dumps({"N": N, "v1": bool(os.environ.get("BHOLO_FFT_V1")), "mode": os.environ.get("BHOLO_FFT_MODE", "1"),
                       "ABC": os.environ.get("BHOLO_FFT_A", "2") + os.environ.get("BHOLO_FFT_B", "3") + os.environ.get("BHOLO_FFT_C", "2"), "W": os.environ.get("BHOLO_FFT_W", "8"),
-                      "rev": bool(os.environ.get("BHOLO_FFT_REV")),
+                      "rev": bool(os.environ.get("BHOLO_FFT_REV")), "lib": os.path.basename(os.environ.get("BHOLO_LIB", "default")),
                       "psnr": psnr, "propagate_ms": round(ms, 4), "passes_ms": [round(x, 4) for x in passes],
                       "gbs_survey_model": round(bytes_survey / ms / 1e6), "sweep_all_ms": round(sweep_ms, 3),
                       "sweep_checksum": float(d_map[::4097].sum().item())}))
 else:
     M0, M2 = {"BHOLO_FFT_MODE": "0"}, {"BHOLO_FFT_MODE": "2"}
-    variants = [{}, M2, M0, {"BHOLO_FFT_B": "2"}, {"BHOLO_FFT_C": "3"}, {"BHOLO_FFT_C": "1"}, {"BHOLO_FFT_V1": "1"}]
+    SC = {"BHOLO_LIB": os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "exp", "lib_scalar.so")}
+    if not os.path.exists(SC["BHOLO_LIB"]):
+        SC = None
+    variants = [{}, M2, M0, {"BHOLO_FFT_B": "2"}, {"BHOLO_FFT_C": "3"}] + ([SC, dict(SC, **M0)] if SC else [])
     for N in (1024, 896):
-        for extra in (variants if N == 1024 else [{}, M2, {"BHOLO_FFT_V1": "1"}]):
+        for extra in (variants if N == 1024 else [{}, M2] + ([SC] if SC else [])):
             env = dict(os.environ, **extra)
             r = subprocess.run([sys.executable, __file__, "run", str(N)], env=env, capture_output=True, text=True)
             print(r.stdout.strip() or r.stderr[-1500:], flush=True)
