@@ -81,6 +81,7 @@ struct DeltaArgs {
     Result* results_host;          // optional mapped pinned mirror written by the finaliser
     // speculative greedy DBS (k_commit does the selection): decision log, PSNR trace, counter
     uint8_t* dbs_accepted; double* dbs_trace; long long* dbs_count; long long* dbs_cursor;
+    double* dbs_s0;                // [4] running sums + PSNR the window was scored against (written by the finalisers)
     // small batches (one env step of <= INLINE_MAX envs) carry their tasks in the
     // kernel parameters: no host-to-device copy on the step path
     int n_inline;
@@ -267,26 +268,32 @@ __device__ __forceinline__ int cta_of_unit(long long u, long long total, int gri
     return int(((u + 1) * grid - 1) / total);
 }
 
+// PSNR of the running sums (tt.relativeLoss + tm.get_PSNR in closed form, float64) and the accept rules
+__device__ __forceinline__ double psnr_from_sums(const DeltaArgs& a, double sii, double sit, double stt, size_t n2) {
+    const double n = double(a.G) * double(n2);
+    const double mse = a.relative ? (stt - sit * sit / sii) / n
+                                  : (sii - 2.0 * sit + stt) / n;
+    return -10.0 * log10(mse);
+}
+__device__ __forceinline__ int apply_rule(int rule, double psnr, double prev) {
+    if (rule == RULE_ENV) return !(psnr - prev < 0.0);      // env.py:191
+    if (rule == RULE_DBS) return psnr > prev;               // DBS.py:273
+    return rule == RULE_ALWAYS;
+}
+
 __device__ __forceinline__ void write_result(const DeltaArgs& a, int k, const Decoded& d, long long act,
                                              int sg, long long sII, long long sIT, const double (&S)[4],
                                              size_t n2) {
     const double dII = double(sII) * FIX_INV, dIT = double(sIT) * FIX_INV;
-    const double sii = S[0] + dII, sit = S[1] + dIT, stt = S[2];
-    const double n = double(a.G) * double(n2);
-    const double mse = a.relative ? (stt - sit * sit / sii) / n
-                                  : (sii - 2.0 * sit + stt) / n;
-    const double psnr = -10.0 * log10(mse);
-    const double prev = S[3];
-    int acc = 0;
-    if (a.rule == RULE_ENV) acc = !(psnr - prev < 0.0);     // env.py:191
-    else if (a.rule == RULE_DBS) acc = (psnr > prev);       // DBS.py:273
-    else if (a.rule == RULE_ALWAYS) acc = 1;
+    const double psnr = psnr_from_sums(a, S[0] + dII, S[1] + dIT, S[2], n2);
+    const int acc = apply_rule(a.rule, psnr, S[3]);
     Result r; r.psnr_after = psnr; r.d_sii = dII; r.d_sit = dIT;
     r.action = act; r.accept = acc; r.sgn = sg;
     a.results[k] = r;
     if (a.results_host) a.results_host[k] = r;
     if (a.log_accept) a.log_accept[k] = uint8_t(acc);
     if (a.log_psnr) a.log_psnr[k] = psnr;
+    if (a.dbs_s0) { a.dbs_s0[0] = S[0]; a.dbs_s0[1] = S[1]; a.dbs_s0[2] = S[2]; a.dbs_s0[3] = S[3]; }
     a.acc[2 * k] = 0ull; a.acc[2 * k + 1] = 0ull;
     (void)d;
 }
@@ -712,30 +719,67 @@ k_commit_t(const DeltaArgs a) {
     __syncthreads();
     int n_acc;
     if (a.dbs_cursor) {
-        // speculative greedy DBS (DBS.py:247-294 order): all K candidates were scored against
-        // the same state; keep the first accepted one, the candidates after it are scored
-        // again by the next batch.  Block 0 logs the decisions and advances the cursor
-        // (idle slots carry accept = 0, so no other block needs the cursor).
+        // speculative greedy DBS (DBS.py:247-294 order): all K candidates were scored against the same state S0.
+        // Candidates before the first kept one were rejected against the right state.  After it, a candidate
+        // of ANOTHER colour group still has exact delta sums (its frame's field and its group's I and T are
+        // untouched; DBS_1024_24.py:324-352 re-simulates only the flipped group), only the running sums
+        // moved: thread 0 walks on, re-decides such candidates in order with the updated sums (same float64
+        // closed form, same order of additions as the sequential loop) and stops at the first candidate whose
+        // group has been touched -- that one is scored again by the next batch.  Every CTA does the same walk
+        // from the same inputs (results + S0 as published by the finalisers); block 0 logs and advances.
         if (bal && lane == 0) atomicMin(&s_first, warp * 32 + (__ffs(bal) - 1));
         __syncthreads();
         const int first = (s_first == 0x7fffffff) ? -1 : s_first;
-        if (tid == 0 && first >= 0) s_list[0] = first;
-        n_acc = first >= 0 ? 1 : 0;
-        if (blockIdx.x == 0) {
-            const long long off = *a.dbs_cursor;
-            long long cnt = a.n_total - off;
+        const bool log = (blockIdx.x == 0);
+        long long off = 0, cnt = 0;
+        if (log) {
+            off = *a.dbs_cursor;
+            cnt = a.n_total - off;
             if (cnt > a.n_tasks) cnt = a.n_tasks;
-            if (cnt > 0) {
-                const int used = first >= 0 ? first + 1 : int(cnt);
-                if (tid < used) {
-                    a.dbs_accepted[off + tid] = (tid == first) ? 1 : 0;
-                    if (a.dbs_trace) a.dbs_trace[off + tid] = a.results[tid].psnr_after;
+        }
+        if (tid == 0) {
+            int kept = 0, used = -1;
+            if (first >= 0) {
+                const size_t n2w = size_t(a.N) * a.N;
+                const Result r0 = a.results[first];
+                double sii = a.dbs_s0[0] + r0.d_sii, sit = a.dbs_s0[1] + r0.d_sit, prev = r0.psnr_after;
+                const double stt = a.dbs_s0[2];
+                const unsigned all = (1u << a.G) - 1u;
+                unsigned dirty = 1u << (int(r0.action / (long long)n2w) / a.Fg);
+                s_list[0] = first; kept = 1;
+                int k = first + 1;
+                for (; k < a.n_tasks && dirty != all; ++k) {
+                    const Result rk = a.results[k];
+                    if (rk.action < 0) break;                        // idle slot: end of the list
+                    const int g = int(rk.action / (long long)n2w) / a.Fg;
+                    if ((dirty >> g) & 1u) break;
+                    const double psnr = psnr_from_sums(a, sii + rk.d_sii, sit + rk.d_sit, stt, n2w);
+                    const int acc = apply_rule(a.rule, psnr, prev);
+                    if (log) {
+                        a.dbs_accepted[off + k] = uint8_t(acc);
+                        if (a.dbs_trace) a.dbs_trace[off + k] = psnr;
+                    }
+                    if (acc) { sii += rk.d_sii; sit += rk.d_sit; prev = psnr; dirty |= 1u << g; s_list[kept++] = k; }
                 }
-                __syncthreads();                         // every thread has read the cursor
-                if (tid == 0) {
-                    if (first >= 0) *a.dbs_count += 1;
-                    *a.dbs_cursor = off + used;
+                used = k;
+                if (log) {                                           // the sums after this batch (nobody reads them here)
+                    double* S = a.sums + size_t(a.env_fixed) * 4;
+                    S[0] = sii; S[1] = sit; S[3] = prev;
                 }
+            }
+            s_wcnt[0] = kept; s_wcnt[1] = used;
+        }
+        __syncthreads();
+        n_acc = s_wcnt[0];
+        if (log && cnt > 0) {
+            const int head = first >= 0 ? first + 1 : int(cnt);  // decided against S0 by the finalisers
+            if (tid < head) {
+                a.dbs_accepted[off + tid] = (tid == first) ? 1 : 0;
+                if (a.dbs_trace) a.dbs_trace[off + tid] = a.results[tid].psnr_after;
+            }
+            if (tid == 0) {
+                *a.dbs_count += n_acc;
+                *a.dbs_cursor = off + (first >= 0 ? s_wcnt[1] : int(cnt));
             }
         }
     } else {
@@ -771,10 +815,12 @@ k_commit_t(const DeltaArgs a) {
         if (u == t_beg && tid == 0) {                 // one thread per accepted flip: state byte + sums
             int8_t* st = a.state + (size_t(d.env) * a.F + d.f) * n2 + size_t(d.r) * N + d.c;
             *st = int8_t(res.sgn > 0 ? 1 : 0);
-            double* S = a.sums + size_t(d.env) * 4;
-            S[0] += res.d_sii;
-            S[1] += res.d_sit;
-            S[3] = res.psnr_after;
+            if (!a.dbs_cursor) {                      // (the greedy DBS batch wrote its final sums above)
+                double* S = a.sums + size_t(d.env) * 4;
+                S[0] += res.d_sii;
+                S[1] += res.d_sit;
+                S[3] = res.psnr_after;
+            }
             if (a.recon_stale) {
                 uint8_t* sm = a.recon_stale + size_t(d.env) * RECON_MAX_BUFFERS;
 #pragma unroll

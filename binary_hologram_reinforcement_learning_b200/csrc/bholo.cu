@@ -44,6 +44,7 @@ struct bh_ctx {
     unsigned long long* d_acc = nullptr;
     unsigned* d_tickets = nullptr;
     long long* d_scalars = nullptr;      // [0] dbs cursor, [1] accepted count
+    double* d_dbs_s0 = nullptr;          // [4] sums + PSNR a greedy-DBS window was scored against
     // correlation sweep (allocated on first use)
     float2 *dK3 = nullptr, *dK4 = nullptr, *dK5 = nullptr, *dK6 = nullptr, *dsw_in = nullptr, *dsw_out = nullptr;
     float2* dsw_buf = nullptr;           // pad = 2: P x P working planes of the correlation passes
@@ -509,7 +510,7 @@ extern "C" int bh_destroy(bh_ctx* c) {
     cudaFree(c->dI); cudaFree(c->dT); cudaFree(c->drecon); cudaFree(c->dstate); cudaFree(c->dsums);
     cudaFree(c->dloss_partial);
     cudaFree(c->d_envs); cudaFree(c->d_actions); cudaFree(c->d_results); cudaFree(c->d_acc);
-    cudaFree(c->d_tickets); cudaFree(c->d_scalars);
+    cudaFree(c->d_tickets); cudaFree(c->d_scalars); cudaFree(c->d_dbs_s0);
     cudaFree(c->dK3); cudaFree(c->dK4); cudaFree(c->dK5); cudaFree(c->dK6); cudaFree(c->dsw_in); cudaFree(c->dsw_out);
     cudaFree(c->dsw_buf);
     cudaFree(c->dsw_it); cudaFree(c->dsw_ii); cudaFree(c->dsw_psnr);
@@ -582,6 +583,7 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
     BH_TRY(cudaMalloc(&c->d_acc, size_t(c->max_tasks) * 2 * sizeof(unsigned long long)));
     BH_TRY(cudaMalloc(&c->d_tickets, size_t(c->max_tasks) * sizeof(unsigned)));
     BH_TRY(cudaMalloc(&c->d_scalars, 4 * sizeof(long long)));
+    BH_TRY(cudaMalloc(&c->d_dbs_s0, 4 * sizeof(double)));
     BH_TRY(cudaMalloc(&c->d_recon_stale, size_t(n_env) * RECON_MAX_BUFFERS));
     BH_TRY(cudaMalloc(&c->d_recon_plan, size_t(c->max_tasks) * sizeof(ReconPlan)));
     BH_TRY(cudaEventCreateWithFlags(&c->ev_recon, cudaEventDisableTiming));
@@ -734,6 +736,7 @@ static DeltaArgs make_args(bh_ctx* c, int n, int env_fixed, const int32_t* d_env
     a.recon_stale = c->d_recon_stale;
     a.log_accept = nullptr; a.log_psnr = nullptr;
     a.dbs_accepted = nullptr; a.dbs_trace = nullptr; a.dbs_count = nullptr; a.dbs_cursor = nullptr;
+    a.dbs_s0 = nullptr;
     return a;
 }
 
@@ -1015,6 +1018,7 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
             a.offset_ptr = c->d_scalars;
             a.n_total = n;
             a.sort_window = 1;
+            a.dbs_s0 = c->d_dbs_s0;             // the finalisers publish the sums the window was scored against
             DeltaArgs ac = a;                   // the commit kernel also selects and logs
             ac.dbs_cursor = c->d_scalars; ac.dbs_count = c->d_scalars + 1;
             ac.dbs_accepted = d_acc; ac.dbs_trace = d_trace;
@@ -1046,10 +1050,13 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
             const long long consumed = c->h_scalars[0] - cursor;
             cursor = c->h_scalars[0];
             nacc = c->h_scalars[1];
-            if (k_spec <= 0) {      // adapt the speculation depth to the accept rate
+            if (k_spec <= 0) {
+                // adapt the speculation depth to the accept rate: an iteration costs ~7.5 us + ~4 us per scored
+                // candidate, a window is used up to the first candidate whose colour group was touched
+                // (profiles/r2_notes.md 7: at 50 % kept flips 2.8 of 4 candidates are used, 3.2 of 16)
                 const double per_iter = double(consumed) / iters_per_sync;
                 if (per_iter > 0.75 * K && K < kmax) K = std::min(kmax, K * 2);
-                else if (per_iter < 0.30 * K && K > 1) K = std::max(1, K / 2);
+                else if (per_iter < 0.50 * K && K > 1) K = std::max(1, K / 2);
             }
             if (resync_every > 0 && nacc - last_resync >= resync_every && cursor < n) {
                 rc = propagate_env(c, env);
