@@ -967,6 +967,30 @@ def test_fixed_point_range_dark_target_and_tiny_fields():
 
 
 @pytest.mark.gpu
+def test_dbs_windows_keep_candidates_of_untouched_colour_groups_exactly():
+    """A speculation window goes on after its first kept flip through candidates of other colour groups
+    (DBS_1024_24.py:324-352: only the flipped group changes).  Decisions AND the PSNR trace must be those of
+    the one-candidate-at-a-time loop, bit for bit, for every depth."""
+    N, F = 128, 12
+    pre, tgt, st = _problem(N, F, O.WL_RGB, 11)
+    order = np.random.default_rng(4).permutation(F * N * N)[:6000]
+    runs = {}
+    for k in (1, 3, 16, 128):
+        eng = _engine(N, F, O.WL_RGB)
+        eng.set_target(0, tgt)
+        eng.load_state(0, st)
+        acc, tr, nacc, fin = eng.dbs_run(order, k_spec=k, resync_every=0, trace=True)
+        runs[k] = (acc.copy(), tr.copy(), nacc, fin, eng.state(0).copy())
+        eng.close()
+    a1, t1, n1, f1, s1 = runs[1]
+    assert 0.2 < n1 / order.size < 0.8                  # a regime where windows do hold several kept flips
+    for k in (3, 16, 128):
+        a, t, n, f, s = runs[k]
+        assert np.array_equal(a, a1), k
+        assert np.array_equal(t, t1), k                 # identical float64 values, not just close
+        assert n == n1 and f == f1 and np.array_equal(s, s1), k
+
+
 def test_batched_dbs_equals_the_sequential_loop_of_every_image():
     """bh_dbs_run_batch: several images in flight, one candidate per image and launch; each image's decisions,
     PSNR trace and final hologram are those of its own sequential greedy loop (bh_dbs_run, no speculation)."""
