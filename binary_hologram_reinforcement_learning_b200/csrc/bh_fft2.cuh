@@ -93,6 +93,32 @@ __device__ __forceinline__ void fft2_pass2(float2 (&v)[32], const float2* s, int
     }
 }
 
+// pass 2 in two halves (an asynchronous copy can be issued between the reads of the exchange buffer and the
+// butterfly), twiddles from a shared-memory copy of the plan's block
+template <int P, bool REV, template <int> class Lay>
+__device__ __forceinline__ void fft2_pass2_read(float2 (&v)[32], const float2* s, int j) {
+    constexpr int RA = Plan2<P, REV>::RA, RB = Plan2<P, REV>::RB;
+    if (RA == 32 || j < RA) {
+#pragma unroll
+        for (int r = 0; r < RB; ++r) v[r] = s[Lay<RA>::rd(j, r)];
+    }
+}
+// stw: shared-memory copy of this plan's twiddle block, stw[(r - 1) RA + k] = exp(-2 pi i r k / P)
+template <int P, bool INV, bool REV, bool TW_GLOBAL = false>
+__device__ __forceinline__ void fft2_pass2_math(float2 (&v)[32], int j, const float2* stw) {
+    constexpr int RA = Plan2<P, REV>::RA, RB = Plan2<P, REV>::RB;
+    if (RA == 32 || j < RA) {
+#pragma unroll
+        for (int r = 1; r < RB; ++r) {
+            float2 w = TW_GLOBAL ? __ldg(stw + (r - 1) * RA + j) : stw[(r - 1) * RA + j];
+            if (INV) w.y = -w.y;
+            v[r] = cmul(v[r], w);
+        }
+        dft<RB, INV>(v);
+    }
+}
+
+
 // ---------------------------------------------------------------------------
 // pass A, real input: int8 state [frames][P][P] -> row spectra kx <= P/2 of buf [frames][P][P].
 // One warp per pair of rows (2 yp, 2 yp + 1): z = a + i b, one transform, A[k] = (Z[k] + conj Z[-k]) / 2,
@@ -425,7 +451,10 @@ k3_rows_inv_group(float2* U, float* __restrict__ I, const float* __restrict__ T,
 // HERM = false (complex input): every column is transformed, no mirror column.
 // Four CTA barriers per tile; shared memory 3 x 8 P W bytes = 96 KB at P = 1024 (cols2_smem_bytes).
 // ---------------------------------------------------------------------------
-template <int P, int W> constexpr size_t cols2_smem_bytes() { return size_t(3) * P * W * sizeof(float2) + 128 + 16; }
+// + the twiddle blocks of both plans (LDS instead of 3 x 31 LDG per thread and tile)
+template <int P, int W> constexpr size_t cols2_smem_bytes() {
+    return size_t(3) * P * W * sizeof(float2) + 128 + size_t(TwLayout<P>::total_all) * sizeof(float2) + 16;
+}
 
 // IN_TMA = false: the input tile is gathered straight into the butterfly registers (32-byte row segments,
 // 8 rows per warp instruction) instead of through s_in; only the H tile (shared by the Fg frames of a column
@@ -446,6 +475,9 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_wk + P * W);
     uint64_t& bar_in = bars[0];
     uint64_t& bar_h = bars[1];
+    float2* stw = s_wk + P * W + 16;                   // 128 bytes after the barriers
+    const float2* stw_fwd = stw + Plan2<P, false>::tw_off;
+    const float2* stw_rev = stw + Plan2<P, true>::tw_off;
     const int tid = threadIdx.x, w = tid & (W - 1), j = tid / W;
     const long long total = (long long)n_groups * NT * Fg;
     const int beg = int((long long)blockIdx.x * total / gridDim.x);
@@ -456,6 +488,7 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
         mbar_init(&bar_in, 1); mbar_init(&bar_h, 1);
         fence_barrier_init();
     }
+    for (int i = tid; i < TwLayout<P>::total_all; i += 32 * W) stw[i] = __ldg(tw + i);   // constant table
     __syncthreads();
     fft_pdl_wait();
     auto issue_in = [&](int idx) {                     // one thread
@@ -499,7 +532,8 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
         }
         fft2_pass1<P, false, false, ColLayW<W>::template L>(v, s_wk + w, j);
         __syncthreads();                               // B1
-        fft2_pass2<P, false, false, ColLayW<W>::template L>(v, s_wk + w, j, tw);
+        fft2_pass2_read<P, false, ColLayW<W>::template L>(v, s_wk + w, j);
+        fft2_pass2_math<P, false, false>(v, j, stw_fwd);
         if (h_pending) { mbar_wait(&bar_h, ph_h); ph_h ^= 1u; h_pending = false; }
         // thread j < RA holds F[j + r RA], r < RB: the entry pattern of the reversed plan
         float2 a[32];
@@ -509,7 +543,8 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
         }
         fft2_pass1<P, true, true, ColLayW<W>::template L>(a, s_in + w, j);
         __syncthreads();                               // B2
-        fft2_pass2<P, true, true, ColLayW<W>::template L>(a, s_in + w, j, tw);
+        fft2_pass2_read<P, true, ColLayW<W>::template L>(a, s_in + w, j);
+        fft2_pass2_math<P, true, true>(a, j, stw_rev);
         if (col_ok && (RB == 32 || j < RB)) {          // thread j < RB holds out[j + r RB], r < RA
 #pragma unroll
             for (int r = 0; r < RA; ++r) frame[size_t(j + r * RB) * P + kx] = a[r];
@@ -532,13 +567,95 @@ k2_cols(const __grid_constant__ CUtensorMap map_buf, const __grid_constant__ CUt
             h_pending = new_h;
         }
         if (HERM) {
-            fft2_pass2<P, true, true, ColLayW<W>::template L>(a, s_wk + w, j, tw);
+            fft2_pass2_read<P, true, ColLayW<W>::template L>(a, s_wk + w, j);
+            fft2_pass2_math<P, true, true>(a, j, stw_rev);
             if (mirror_ok && (RB == 32 || j < RB)) {
 #pragma unroll
                 for (int r = 0; r < RA; ++r) frame[size_t(j + r * RB) * P + (P - kx)] = make_float2(a[r].x, -a[r].y);
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// Latency-hiding variants of pass A and pass C (round 2, session 4).  The passes are latency bound (issue slots
+// 30-40 % busy, DRAM 25 %): a warp loads its row, waits a full L2 round trip, transforms, stores, and only then
+// asks for the next row.  Here the NEXT row travels by cp.async (LDGSTS.128, no staging registers) while the
+// current one is transformed, and the pass-2 twiddle block lives in shared memory (LDS instead of 31 LDG per
+// transform competing with the row stores for the load/store queue).
+// ---------------------------------------------------------------------------
+template <int P> constexpr int tw_block_len() { return (Plan2<P, false>::RB - 1) * Plan2<P, false>::RA; }
+template <int P> constexpr size_t rows4_fwd_smem_bytes() {
+    return size_t(tw_block_len<P>()) * sizeof(float2)
+         + size_t(ROWS_WARPS) * (RowLaySize<P, Plan2<P, false>::RA>::value * sizeof(float2) + 2 * P);
+}
+
+// pass A, real input.  The two state rows of a pair are 2 P contiguous bytes: they arrive in a per-warp staging
+// buffer by cp.async one pair ahead; the stride-RB byte gather of the butterfly entry pattern reads shared memory
+// (32 consecutive bytes per instruction: 8 banks, 4 lanes per word).
+// late_wait: the launch does not depend on its predecessor's memory (colour groups g >= 1 of one propagation:
+// the state was complete before group 0 started), so the CTAs may fill the SMs the predecessor's last wave
+// leaves idle; the wait at the END keeps the completion order of the stream transitive.
+template <int P>
+__global__ void __launch_bounds__(32 * ROWS_WARPS, 4)
+k4_rows_fwd_real(const int8_t* __restrict__ state, float2* __restrict__ buf, const float2* __restrict__ tw,
+                 int n_pairs, int late_wait) {
+    constexpr int RA = Plan2<P, false>::RA, RB = Plan2<P, false>::RB;
+    constexpr int SZ = RowLaySize<P, RA>::value;
+    constexpr int NTW = (RB - 1) * RA;
+    extern __shared__ __align__(16) float2 s2[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* stw = s2;
+    float2* sw = s2 + NTW + warp * SZ;
+    int8_t* stg = reinterpret_cast<int8_t*>(s2 + NTW + ROWS_WARPS * SZ) + warp * 2 * P;
+    fft_pdl_release();
+    for (int i = threadIdx.x; i < NTW; i += 32 * ROWS_WARPS) stw[i] = __ldg(tw + i);   // constant table
+    if (!late_wait) fft_pdl_wait();
+    const int stride = gridDim.x * ROWS_WARPS;
+    int task = blockIdx.x * ROWS_WARPS + warp;
+    auto prefetch = [&](int t) {
+        const int f = t / (P / 2), yp = t - f * (P / 2);
+        const int8_t* src = state + (size_t(f) * P + 2 * yp) * P;
+#pragma unroll
+        for (int i = lane; i < 2 * P / 16; i += 32) cpa16(stg + 16 * i, src + 16 * i);
+        cpa_commit();
+    };
+    if (task < n_pairs) prefetch(task);
+    __syncthreads();
+    for (; task < n_pairs; task += stride) {
+        const int f = task / (P / 2), yp = task - f * (P / 2);
+        cpa_wait_all();
+        __syncwarp();
+        float2 v[32];
+        if (RB == 32 || lane < RB) {
+#pragma unroll
+            for (int r = 0; r < RA; ++r)
+                v[r] = make_float2(byte_to_float(stg[lane + r * RB]), byte_to_float(stg[P + lane + r * RB]));
+        }
+        __syncwarp();                                  // the staging buffer is free
+        if (task + stride < n_pairs) prefetch(task + stride);
+        fft2_pass1<P, false, false, RowLay>(v, sw, lane);
+        __syncwarp();
+        fft2_pass2_read<P, false, RowLay>(v, sw, lane);
+        fft2_pass2_math<P, false, false>(v, lane, stw);
+        __syncwarp();
+        float2* oa = buf + (size_t(f) * P + 2 * yp) * P + lane;
+        float2* ob = oa + P;
+        const int src = (RA - lane) & (RA - 1);
+#pragma unroll
+        for (int r = 0; r <= RB / 2; ++r) {
+            float2 zm;
+            zm.x = __shfl_sync(0xffffffffu, v[RB - 1 - r].x, src);
+            zm.y = __shfl_sync(0xffffffffu, v[RB - 1 - r].y, src);
+            if (lane == 0) zm = v[(RB - r) % RB];
+            const float2 zk = v[r];
+            if (r < RB / 2 || lane == 0) {
+                oa[r * RA] = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                ob[r * RA] = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+            }
+        }
+    }
+    if (late_wait) fft_pdl_wait();
 }
 
 }  // namespace bh

@@ -168,10 +168,13 @@ static cudaError_t launch_prop2_state(const int8_t* state, float2* U, float* I, 
     const size_t smC = INVG_WARPS * row_smem + size_t(INVG_WARPS) * P * sizeof(float);
     // experiment switches (profiles/r2_notes.md): BHOLO_FFT_A / _B / _C = 1 selects the shared-memory kernel of
     // round 1 for that pass (launched per colour group), BHOLO_FFT_B = 3 the TMA-staged input tile
-    static const int selA = std::getenv("BHOLO_FFT_A") ? std::atoi(std::getenv("BHOLO_FFT_A")) : 2;
+    // BHOLO_FFT_A = 4 (default): k4_rows_fwd_real (state rows prefetched by cp.async, twiddles in shared memory)
+    static const int selA = std::getenv("BHOLO_FFT_A") ? std::atoi(std::getenv("BHOLO_FFT_A")) : 4;
     static const int selB = std::getenv("BHOLO_FFT_B") ? std::atoi(std::getenv("BHOLO_FFT_B")) : 3;
     static const int selC = std::getenv("BHOLO_FFT_C") ? std::atoi(std::getenv("BHOLO_FFT_C")) : 2;
+    static const bool late_ok = !std::getenv("BHOLO_FFT_NO_LATE_WAIT");
     auto kA = k2_rows_fwd_real<P>;
+    auto kA4 = k4_rows_fwd_real<P>;
     auto kB = colw == 8 ? (selB == 3 ? k2_cols<P, true, true, 8> : k2_cols<P, true, false, 8>)
                         : (selB == 3 ? k2_cols<P, true, true, 4> : k2_cols<P, true, false, 4>);
     auto kC = k2_rows_inv_group<P>;
@@ -185,6 +188,7 @@ static cudaError_t launch_prop2_state(const int8_t* state, float2* U, float* I, 
     if ((e = cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smB)))) return e;
     if ((e = cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smC)))) return e;
     if ((e = cudaFuncSetAttribute(kC3, cudaFuncAttributeMaxDynamicSharedMemorySize, int(invg3_smem_bytes<P>())))) return e;
+    if ((e = cudaFuncSetAttribute(kA4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rows4_fwd_smem_bytes<P>())))) return e;
     if ((e = cudaFuncSetAttribute(kA1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smr1)))) return e;
     if ((e = cudaFuncSetAttribute(kB1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * smc1)))) return e;
     if ((e = cudaFuncSetAttribute(kC1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * smr1)))) return e;
@@ -197,6 +201,11 @@ static cudaError_t launch_prop2_state(const int8_t* state, float2* U, float* I, 
     if (!(phases & 1)) {
     } else if (selA == 1) {
         kA1<<<dim3(P / (2 * TILE_W), frames), FftCfg<P>::T, smr1, st>>>(state, U, tw);
+    } else if (selA == 4) {
+        // colour groups g >= 1 of a propagation do not depend on their predecessor (pass C of group g - 1)
+        const int late = (late_ok && h_group0 > 0 && phases == 3) ? 1 : 0;
+        launch_pdl(kA4, std::min((n_pairs + ROWS_WARPS - 1) / ROWS_WARPS, sms * 4), 32 * ROWS_WARPS,
+                   rows4_fwd_smem_bytes<P>(), st, state, U, tw, n_pairs, late);
     } else {
         launch_pdl(kA, std::min((n_pairs + ROWS_WARPS - 1) / ROWS_WARPS, sms * 4 * 4), 32 * ROWS_WARPS, smA, st, state, U, tw, n_pairs);
     }
