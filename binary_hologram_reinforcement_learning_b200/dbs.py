@@ -414,7 +414,6 @@ def dbs_sweep(target_function: Callable, trainloader: Iterable, z=2e-3, pixel_pi
         eng.load_state(0, cstate)
         initial_psnr, _, _ = eng.metrics(0)
         file_name = _file_stem(current_file)
-        bin_counts = bin_population(cpre)
         if verbose:
             print(f"Starting pixel flip optimization for file {file_name}.png with initial PSNR: {initial_psnr:.6f}")
         n = eng.num_pixels
@@ -437,6 +436,7 @@ def dbs_sweep(target_function: Callable, trainloader: Iterable, z=2e-3, pixel_pi
                 and perm.shape[0] == n):
             # the whole image in one call: correlation sweep + decile statistics on the device
             att, imp, gn, psnr_map = eng.sweep_stats(cpre, OUTPUT_BINS, 0, want_map=True)
+            bin_counts = att.copy()                        # every pixel is a candidate: population = attempts per bin
             psnr_all = psnr_map.reshape(-1)[perm]
             flip_count = int(imp.sum())
             dt = time.time() - t0
@@ -446,6 +446,7 @@ def dbs_sweep(target_function: Callable, trainloader: Iterable, z=2e-3, pixel_pi
             if verbose:
                 _emit_sweep_log(file_name, initial_psnr, perm, psnr_all, cpre, N, bin_counts, t0, log_every)
             continue
+        bin_counts = bin_population(cpre)
         if eng.Fg % 2 == 0 and (hi_all - lo_all) * 4 >= n:
             psnr_map = eng.sweep_all(0)                    # every candidate in one call
         for lo in range(lo_all, hi_all, chunk):
