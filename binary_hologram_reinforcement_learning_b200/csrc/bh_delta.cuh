@@ -94,6 +94,8 @@ struct DeltaArgs {
     // observation bookkeeping: k_commit marks the plane of a kept flip stale in every
     // observation buffer (see k_recon_plan); [E][RECON_MAX_BUFFERS] or nullptr
     uint8_t* recon_stale;
+    // k_eval: units of the CTA's stream requested into L2 before the wait for the predecessor (0 = off)
+    int l2_prefetch_units;
 };
 constexpr int INLINE_MAX = 32;
 constexpr int RECON_MAX_BUFFERS = 4;
@@ -451,6 +453,34 @@ k_eval_t(const DeltaArgs a) {
     // the predecessor's memory is waited for
     long long u = beg;
     bool waited = false;
+    if (a.l2_prefetch_units > 0 && !a.offset_ptr && beg < end) {
+        // The grid's CTAs land on the SMs while the predecessor's last CTAs drain, and block at the wait.
+        // The task list (kernel parameters, or a device list nobody writes during the chain) is known, so
+        // the first units of this CTA's stream are requested into L2 meanwhile: L2 is the coherence point,
+        // a line the predecessor still writes is simply updated there.  After the wait the streaming loop
+        // starts on L2 hits instead of a cold DRAM round trip.
+        const int k0 = int(beg / upt);
+        const long long act0 = task_action(a, k0);
+        const Decoded d0 = decode_action(a, k0, act0);
+        if (d0.active && a.unit_dx == 0) {
+            const size_t px0 = size_t(beg - (long long)k0 * upt) * UNIT_PX;
+            const char* Ub = reinterpret_cast<const char*>(a.U + (size_t(d0.env) * a.F + d0.f) * n2 + px0);
+            const char* Ib = reinterpret_cast<const char*>(a.I + (size_t(d0.env) * a.G + d0.g) * n2 + px0);
+            const char* Tb = reinterpret_cast<const char*>(a.T + (size_t(d0.env) * a.G + d0.g) * n2 + px0);
+            long long avail = (long long)(k0 + 1) * upt - beg;            // units left in the first task
+            if (avail > end - beg) avail = end - beg;
+            const int pf = avail < a.l2_prefetch_units ? int(avail) : a.l2_prefetch_units;
+            // per unit: 64 lines of U, 32 of I, 32 of T (128-byte lines); thread t takes line t of a unit pair
+            for (int ln = tid; ln < pf * 128; ln += 256) {
+                const int un = ln >> 7, l = ln & 127;
+                const char* ptr = l < 64 ? Ub + size_t(un) * UNIT_PX * 8 + l * 128
+                                : (l < 96 ? Ib + size_t(un) * UNIT_PX * 4 + (l - 64) * 128
+                                          : Tb + size_t(un) * UNIT_PX * 4 + (l - 96) * 128);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+            }
+        }
+        pdl_wait(); waited = true;
+    }
     while (u < end) {
         const int k = int(u / upt);
         const long long t_beg = (long long)k * upt;

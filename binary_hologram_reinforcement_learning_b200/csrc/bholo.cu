@@ -63,6 +63,7 @@ struct bh_ctx {
     void (*k_eval_bundle)(const DeltaArgs) = nullptr;
     void (*k_commit)(const DeltaArgs) = nullptr;
     bool use_pdl = true;
+    int l2_prefetch = 4;                 // k_eval: units requested into L2 before the PDL wait (BHOLO_EVAL_L2PF; measured 0..8: 4 is best)
     bool fp64_eval = false;              // per-quad arithmetic of the delta evaluation in double (BHOLO_EVAL_FP64=1)
     bool fft2 = true;                    // register-resident passes (bh_fft2.cuh) where the side allows
     int fft2_mode = 1;                   // launch shape of those passes, see propagate_env
@@ -634,6 +635,7 @@ extern "C" int bh_create(bh_ctx** out, int device, int n_env, int N, int F, int 
         c->sms = prop.multiProcessorCount;
         const char* ev = std::getenv("BHOLO_EVAL_VARIANT");
         c->fp64_eval = std::getenv("BHOLO_EVAL_FP64") != nullptr;
+        if (const char* pf = std::getenv("BHOLO_EVAL_L2PF")) c->l2_prefetch = std::max(0, std::atoi(pf));
         c->k_eval = c->fp64_eval ? eval_variant<double>(ev ? std::atoi(ev) : 0) : eval_variant<float>(ev ? std::atoi(ev) : 0);
         BH_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, c->k_eval, 256, 0));
         c->grid_cap = std::min(MAX_DELTA_GRID, std::max(1, nb) * prop.multiProcessorCount);
@@ -743,6 +745,7 @@ static DeltaArgs make_args(bh_ctx* c, int n, int env_fixed, const int32_t* d_env
     a.acc = c->d_acc; a.tickets = c->d_tickets; a.results = d_results;
     a.results_host = nullptr; a.n_inline = 0; a.sort_window = 0;
     a.recon_stale = c->d_recon_stale;
+    a.l2_prefetch_units = c->use_pdl ? c->l2_prefetch : 0;
     a.log_accept = nullptr; a.log_psnr = nullptr;
     a.dbs_accepted = nullptr; a.dbs_trace = nullptr; a.dbs_count = nullptr; a.dbs_cursor = nullptr;
     a.dbs_s0 = nullptr;
