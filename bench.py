@@ -513,6 +513,11 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
+    # one process per GPU: run on the cores of the GPU's NUMA node before any pinned host memory is allocated
+    numa = None if os.environ.get("BHOLO_NO_NUMA_BIND") else bdist.bind_to_gpu_numa_node(local)
+    if os.environ.get("BHOLO_TOPO_DEBUG"):
+        print(f"[rank {rank}] gpu {local} numa node {bdist.gpu_numa_node(local)} bound {numa} "
+              f"cpus {sorted(os.sched_getaffinity(0))[:4]}..({len(os.sched_getaffinity(0))})", file=sys.stderr, flush=True)
     if world > 1:
         bdist.init_process_group("nccl")
     E, R, K, W = args.envs, args.rollout, args.steps, max(args.warmup, 0)
@@ -768,6 +773,8 @@ def run_b200(args):
             "sharded_sweep": sharded,
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "host_binding": {"gpu_numa_node_rank0": bdist.gpu_numa_node(local), "bound_to_node_rank0": numa,
+                             "cpus_rank0": len(os.sched_getaffinity(0))},
             "extra": extra,
         }
         emit(line)

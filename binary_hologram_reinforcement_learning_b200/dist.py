@@ -19,6 +19,50 @@ def env_info() -> Tuple[int, int, int]:
             int(os.environ.get("LOCAL_RANK", 0)))
 
 
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(local_rank: int):
+    """NUMA node of GPU `local_rank` (sysfs), or None when the platform does not say."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(local_rank: int):
+    """Run this rank on the cores of its GPU's NUMA node, BEFORE it allocates pinned host memory.
+
+    The observation blocks of the eager path are pinned host memory the GPU writes over PCIe every
+    step; first-touch places them on the node of the allocating thread, and a block on the other
+    socket sends every write across the inter-socket link.  Returns the node, or None (unknown
+    topology, or the cpuset of the container has no core of that node: nothing is changed).
+    """
+    node = gpu_numa_node(local_rank)
+    if node is None or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous slice [lo, hi) of n units for this rank (candidate sweeps)."""
     per = (n + world - 1) // world
