@@ -736,13 +736,27 @@ template <int UF, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_commit_t(const DeltaArgs a) {
     __shared__ int s_list[COMMIT_MAX_TASKS];
+    __shared__ Result s_res[COMMIT_MAX_TASKS];
     __shared__ int s_wcnt[8];
     __shared__ int s_first;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     pdl_release();
     pdl_wait();
-    // accept flag of task `tid` (results of the evaluation that precedes this launch)
-    const int flag = (tid < a.n_tasks) ? (a.results[tid].accept != 0) : 0;
+    // ONE round trip to global memory for everything the selection needs: the result record of task `tid`
+    // (decision, action, sign, delta sums) goes to shared memory, the window's reference sums and the cursor
+    // of the greedy DBS to registers -- the walk below and the per-segment set-up then read no global memory.
+    int flag = 0;
+    if (tid < a.n_tasks) {
+        const Result r = a.results[tid];
+        s_res[tid] = r;
+        flag = r.accept != 0;
+    }
+    double s0[4] = {0.0, 0.0, 0.0, 0.0};
+    long long cur0 = 0;
+    if (a.dbs_cursor && tid == 0) {
+        s0[0] = a.dbs_s0[0]; s0[1] = a.dbs_s0[1]; s0[2] = a.dbs_s0[2]; s0[3] = a.dbs_s0[3];
+    }
+    if (a.dbs_cursor && blockIdx.x == 0) cur0 = *a.dbs_cursor;
     const unsigned bal = __ballot_sync(0xffffffffu, flag);
     if (lane == 0) s_wcnt[warp] = __popc(bal);
     if (tid == 0) s_first = 0x7fffffff;
@@ -763,7 +777,7 @@ k_commit_t(const DeltaArgs a) {
         const bool log = (blockIdx.x == 0);
         long long off = 0, cnt = 0;
         if (log) {
-            off = *a.dbs_cursor;
+            off = cur0;
             cnt = a.n_total - off;
             if (cnt > a.n_tasks) cnt = a.n_tasks;
         }
@@ -771,15 +785,15 @@ k_commit_t(const DeltaArgs a) {
             int kept = 0, used = -1;
             if (first >= 0) {
                 const size_t n2w = size_t(a.N) * a.N;
-                const Result r0 = a.results[first];
-                double sii = a.dbs_s0[0] + r0.d_sii, sit = a.dbs_s0[1] + r0.d_sit, prev = r0.psnr_after;
-                const double stt = a.dbs_s0[2];
+                const Result r0 = s_res[first];
+                double sii = s0[0] + r0.d_sii, sit = s0[1] + r0.d_sit, prev = r0.psnr_after;
+                const double stt = s0[2];
                 const unsigned all = (1u << a.G) - 1u;
                 unsigned dirty = 1u << (int(r0.action / (long long)n2w) / a.Fg);
                 s_list[0] = first; kept = 1;
                 int k = first + 1;
                 for (; k < a.n_tasks && dirty != all; ++k) {
-                    const Result rk = a.results[k];
+                    const Result rk = s_res[k];
                     if (rk.action < 0) break;                        // idle slot: end of the list
                     const int g = int(rk.action / (long long)n2w) / a.Fg;
                     if ((dirty >> g) & 1u) break;
@@ -805,7 +819,7 @@ k_commit_t(const DeltaArgs a) {
             const int head = first >= 0 ? first + 1 : int(cnt);  // decided against S0 by the finalisers
             if (tid < head) {
                 a.dbs_accepted[off + tid] = (tid == first) ? 1 : 0;
-                if (a.dbs_trace) a.dbs_trace[off + tid] = a.results[tid].psnr_after;
+                if (a.dbs_trace) a.dbs_trace[off + tid] = s_res[tid].psnr_after;
             }
             if (tid == 0) {
                 *a.dbs_count += n_acc;
@@ -836,7 +850,7 @@ k_commit_t(const DeltaArgs a) {
         const int k = s_list[slot];
         const long long t_beg = (long long)slot * upt;
         const long long seg_end = (t_beg + upt < end) ? t_beg + upt : end;
-        const Result res = a.results[k];
+        const Result res = s_res[k];
         const Decoded d = decode_action(a, k, res.action);
         float2* U = a.U + (size_t(d.env) * a.F + d.f) * n2;
         float* I = a.I + (size_t(d.env) * a.G + d.g) * n2;
