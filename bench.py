@@ -55,7 +55,10 @@ def bench_config(envs: int, rollout: int) -> dict:
             "groups": GROUPS, "pad": 1, "relative": True, "recon_obs": "eager (env.py:176-181)",
             "l2": ("inputs larger than L2: 8 envs x 226 MB resident per GPU, every step streams a random "
                    "frame (16.8 MB) of each env"),
-            "episodes": "max_steps raised so no episode ends inside the timed region"}
+            "episodes": "max_steps raised so no episode ends inside the timed region",
+            "value_path": ("open-loop: the rollout's pre-drawn random actions are device resident and the 512 vectorised "
+                           "steps run in one persistent launch (bh_rollout_device); e2e: one HologramVecEnv.step call "
+                           "per vectorised step, host actions in, results + recon_image out")}
 
 
 def parse():
@@ -129,12 +132,14 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_bytes():
-    """Per-launch DRAM bytes of k_eval from the committed ncu capture, if any."""
+def ncu_traffic_bytes(key=None):
+    """Per-launch DRAM bytes of a kernel from the committed ncu capture, if any (default: k_eval)."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         with open(path) as f:
             d = json.load(f)
+            if key:
+                return d.get(key)
             return d.get("k_eval_dram_bytes_per_launch_warm_cache", d.get("k_eval_dram_bytes_per_launch"))
     except Exception:
         return None
@@ -585,13 +590,18 @@ def run_b200(args):
     vec.set_recon_obs("lazy")
 
     # ---- value: device-resident actions, CUDA events ---------------------
-    d_acts = torch.from_numpy(rng.integers(0, n_pix, size=(R * (K + W), E), dtype=np.int64)).cuda(local)
+    d_acts = torch.from_numpy(rng.integers(0, n_pix, size=(R * (K + W + 2), E), dtype=np.int64)).cuda(local)
     d_envs = torch.arange(E, dtype=torch.int32, device=f"cuda:{local}")
     d_res = torch.zeros((R, E, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=f"cuda:{local}")
     a_ptr, e_ptr, r_ptr = d_acts.data_ptr(), d_envs.data_ptr(), d_res.data_ptr()
     row_a, row_r = E * 8, E * RESULT_DTYPE.itemsize
 
     def rollout(base_row):
+        # one persistent cooperative launch per 512-step rollout (k_rollout_t: per-environment barriers instead
+        # of two launches per vectorised step; bit-identical to the step chain, tests/test_gpu_parity.py)
+        eng.rollout_device(E, e_ptr, a_ptr + base_row * row_a, R, RULE_ENV, r_ptr)
+
+    def rollout_step_chain(base_row):
         for s in range(R):
             eng.step_batch_device(E, e_ptr, a_ptr + (base_row + s) * row_a, RULE_ENV, r_ptr + s * row_r)
 
@@ -609,11 +619,21 @@ def run_b200(args):
         ev1.record(stream)
         torch.cuda.synchronize()
         windows.append((t0w, time.time()))
+        eng.rollout_status()                          # raises if a barrier of the persistent kernel gave up
+        res_host = d_res.cpu().numpy().view(RESULT_DTYPE).reshape(R, E).copy()      # last timed rollout
+        # a rollout of fresh actions through one k_eval + one k_commit launch per vectorised step (what step() uses)
+        ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rollout_step_chain((W + K) * R)
+        ec0.record(stream)
+        rollout_step_chain((W + K + 1) * R)
+        ec1.record(stream)
+        torch.cuda.synchronize()
+        step_chain_ms = ec0.elapsed_time(ec1)
+        chain_accept = float(d_res.cpu().numpy().view(RESULT_DTYPE).reshape(R, E)["accept"].mean())
     bdist.barrier()
-    launches = eng.launch_count - launches0
+    launches = K                                      # one k_rollout_t launch per bench step
     dev_ms = bdist.max_over_ranks(ev0.elapsed_time(ev1))
     value = world * E * R * K / (dev_ms / 1000.0)
-    res_host = d_res.cpu().numpy().view(RESULT_DTYPE).reshape(R, E)
     accept_rate = float(res_host["accept"].mean())
 
     # ---- rooflines of the delta kernels, measured live ---------------------
@@ -633,6 +653,7 @@ def run_b200(args):
     # whole step: one evaluation + accept_rate kept flips per env
     step_bytes = (16.0 + 24.0 * accept_rate) * N_SIDE * N_SIDE * E
     step_gbs = step_bytes / (dev_ms / (K * R) / 1000.0) / 1e9
+    chain_bytes = (16.0 + 24.0 * chain_accept) * N_SIDE * N_SIDE * E
 
     # ---- propagation (reset / re-sync) ------------------------------------
     with torch.cuda.stream(stream):
@@ -739,19 +760,29 @@ def run_b200(args):
             "steps": K, "warmup": W, "ms_per_step": dev_ms / max(K, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": bench_config(E, R),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
-                         "kernel": "k_eval (delta evaluation of 8 candidates, one per env)",
-                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": eval_ms,
+            # dominant kernel of the timed region: ONE k_rollout_t launch per bench step (R vectorised steps)
+            "roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": step_gbs / peak, "traffic": ncu_traffic_bytes("k_rollout_dram_bytes_per_launch"),
+                         "kernel": "k_rollout_t (persistent: evaluation + commit of R x E env steps, per-environment barriers)",
+                         "algorithmic_bytes_per_launch": step_bytes * R,
+                         "algorithmic_bytes_per_env_step": "(16 + 24 * accept_rate) N^2  (SURVEY 8d: 16 N^2 per evaluated, 24 N^2 per kept flip)",
+                         "ms_per_launch": dev_ms / K, "us_per_vec_step": 1e3 * dev_ms / (K * R),
                          "peak_source": peak_src},
+            # the kernels of the step-at-a-time API (HologramVecEnv.step, the e2e path, the greedy DBS windows)
+            "roofline_eval": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                              "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
+                              "kernel": "k_eval (delta evaluation of 8 candidates, one per env)",
+                              "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": eval_ms},
             "roofline_commit": {"bound": "hbm", "achieved": commit_gbs, "peak": peak, "unit": "GB/s",
                                 "frac": commit_gbs / peak, "kernel": "k_commit (8 kept flips per launch)",
                                 "algorithmic_bytes_per_launch": commit_bytes, "ms_per_launch": commit_ms},
-            "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
-                              "frac": step_gbs / peak,
-                              "what": "k_eval + k_commit of the timed region: (16 + 24 * accept_rate) N^2 B per env step",
-                              "us_per_vec_step": 1e3 * dev_ms / (K * R),
-                              "us_per_vec_step_fresh_chain_hook": 1e3 * chain_ms},
+            "roofline_step_chain": {"bound": "hbm", "achieved": chain_bytes / (step_chain_ms / R / 1000.0) / 1e9, "peak": peak,
+                                    "unit": "GB/s", "frac": chain_bytes / (step_chain_ms / R / 1000.0) / 1e9 / peak,
+                                    "accept_rate": chain_accept,
+                                    "what": "the same rollout as one k_eval + one k_commit launch per vectorised step",
+                                    "us_per_vec_step": 1e3 * step_chain_ms / R,
+                                    "env_steps_per_s": world * E * R / (step_chain_ms / 1000.0),
+                                    "us_per_vec_step_fresh_chain_hook": 1e3 * chain_ms},
             "roofline_propagate": {"bound": "hbm", "ms_24_frames": prop_ms, "pass_ms": prop_pass_ms,
                                    "achieved": prop_bytes_survey / (prop_ms / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
                                    "frac": prop_bytes_survey / (prop_ms / 1000.0) / 1e9 / peak,

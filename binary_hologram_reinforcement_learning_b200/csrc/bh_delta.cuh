@@ -132,6 +132,14 @@ __device__ __forceinline__ int ld_state_issue(const int8_t* p) {
     return v;
 }
 
+// the same through L2 (never served from a stale L1 line): k_rollout_t reads bytes other CTAs wrote earlier in
+// the same launch
+__device__ __forceinline__ int ld_state_relaxed(const int8_t* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // L2 cache-policy accesses: the streamed operands (U, I, T) are touched once per candidate and
 // marked evict-first; the impulse response is re-read by every candidate and marked evict-last
 // so it stays L2 resident (25 MB for 3 colours).
@@ -345,7 +353,8 @@ __device__ __forceinline__ long long task_action(const DeltaArgs& a, int k) {
 // column for the whole pass, the pixel offset advances by UNIT_PX per unit, and the impulse
 // response of a candidate is ONE table offset that advances by unit_dy rows (modulo P).  Scores L
 // candidates of one frame per pass over units [w0, w1) of the task, UF units in flight.
-template <int L, int UF, typename R, int NACC>
+// RW: U and I are read through the coherent path (a kernel that also writes them: k_rollout_t).
+template <int L, int UF, typename R, int NACC, bool RW = false>
 __device__ __forceinline__ void eval_run_rows(const DeltaArgs& a, const float2* U, const float* I,
                                               const float* T, const float2* h, const int* rr,
                                               const int* cc, const int* sg, long long (*acc)[NACC],
@@ -371,9 +380,10 @@ __device__ __forceinline__ void eval_run_rows(const DeltaArgs& a, const float2* 
 #pragma unroll
         for (int k = 0; k < UF; ++k) {
             const float4* Up = reinterpret_cast<const float4*>(U + p);
-            ua[k] = ld_stream4(Up, pf);
-            ub[k] = ld_stream4(Up + 1, pf);
-            iv[k] = ld_stream4(reinterpret_cast<const float4*>(I + p), pf);
+            ua[k] = RW ? ld_rw4(Up, pf) : ld_stream4(Up, pf);
+            ub[k] = RW ? ld_rw4(Up + 1, pf) : ld_stream4(Up + 1, pf);
+            iv[k] = RW ? ld_rw4(reinterpret_cast<const float4*>(I + p), pf)
+                       : ld_stream4(reinterpret_cast<const float4*>(I + p), pf);
             tv[k] = ld_stream4(reinterpret_cast<const float4*>(T + p), pf);
             p += UNIT_PX;
 #pragma unroll
@@ -398,9 +408,10 @@ __device__ __forceinline__ void eval_run_rows(const DeltaArgs& a, const float2* 
     for (; w < w1; ++w) {
         Quad q;
         const float4* Up = reinterpret_cast<const float4*>(U + p);
-        q.ua = ld_stream4(Up, pf);
-        q.ub = ld_stream4(Up + 1, pf);
-        q.iv = ld_stream4(reinterpret_cast<const float4*>(I + p), pf);
+        q.ua = RW ? ld_rw4(Up, pf) : ld_stream4(Up, pf);
+        q.ub = RW ? ld_rw4(Up + 1, pf) : ld_stream4(Up + 1, pf);
+        q.iv = RW ? ld_rw4(reinterpret_cast<const float4*>(I + p), pf)
+                  : ld_stream4(reinterpret_cast<const float4*>(I + p), pf);
         q.tv = ld_stream4(reinterpret_cast<const float4*>(T + p), pf);
         p += UNIT_PX;
         float2 hq[L][4];
@@ -732,6 +743,54 @@ __device__ __forceinline__ void commit_quad(const Quad& q, float2* U, float* I, 
     st_stream4(reinterpret_cast<float4*>(I + p), iv, pf);
 }
 
+// Row-regular images: the commit loop over units [w0, w1) of one kept flip (fixed column per thread, one table
+// offset advanced by rows), UF units in flight.  Shared by k_commit_t and k_rollout_t.
+template <int UF>
+__device__ __forceinline__ void commit_run_rows(const DeltaArgs& a, float2* U, float* I, const float2* h,
+                                                int r, int c, float sg, int w0, int w1, int tid, float invFg,
+                                                uint64_t pf, uint64_t pl) {
+    const int N = a.N, P = a.P, HP = a.HP, dy = a.unit_dy;
+    const float s2 = 2.f * sg * invFg;
+    const int y0 = (tid * 4) / N, x = tid * 4 - y0 * N;
+    const int y = w0 * dy + y0;
+    size_t p = size_t(y) * N + x;
+    const int hstep = dy * HP, hwrap = P * HP;
+    int hx = x - c; if (hx < 0) hx += P;
+    int hy = y - r; if (hy < 0) hy += P;
+    int ho = hy * HP + hx;
+    int w = w0;
+#pragma unroll 1
+    for (; w + UF <= w1; w += UF) {
+        Quad q[UF];
+#pragma unroll
+        for (int i = 0; i < UF; ++i) {
+            const float4* Up = reinterpret_cast<const float4*>(U + p + size_t(i) * UNIT_PX);
+            q[i].ua = ld_rw4(Up, pf); q[i].ub = ld_rw4(Up + 1, pf);
+            q[i].iv = ld_rw4(reinterpret_cast<const float4*>(I + p + size_t(i) * UNIT_PX), pf);
+            const float2* hp = h + ho;
+            q[i].h0 = ld_keep2(hp, pl); q[i].h1 = ld_keep2(hp + 1, pl);
+            q[i].h2 = ld_keep2(hp + 2, pl); q[i].h3 = ld_keep2(hp + 3, pl);
+            ho += hstep; if (ho >= hwrap) ho -= hwrap;
+        }
+#pragma unroll
+        for (int i = 0; i < UF; ++i) commit_quad(q[i], U, I, p + size_t(i) * UNIT_PX, s2, sg, invFg, pf);
+        p += size_t(UF) * UNIT_PX;
+    }
+#pragma unroll 1
+    for (; w < w1; ++w) {
+        Quad q;
+        const float4* Up = reinterpret_cast<const float4*>(U + p);
+        q.ua = ld_rw4(Up, pf); q.ub = ld_rw4(Up + 1, pf);
+        q.iv = ld_rw4(reinterpret_cast<const float4*>(I + p), pf);
+        const float2* hp = h + ho;
+        q.h0 = ld_keep2(hp, pl); q.h1 = ld_keep2(hp + 1, pl);
+        q.h2 = ld_keep2(hp + 2, pl); q.h3 = ld_keep2(hp + 3, pl);
+        ho += hstep; if (ho >= hwrap) ho -= hwrap;
+        commit_quad(q, U, I, p, s2, sg, invFg, pf);
+        p += UNIT_PX;
+    }
+}
+
 template <int UF, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_commit_t(const DeltaArgs a) {
@@ -872,47 +931,7 @@ k_commit_t(const DeltaArgs a) {
             }
         }
         if (a.unit_dx == 0) {
-            // row-regular image: fixed column per thread, one table offset advanced by rows
-            const int HP = a.HP, dy = a.unit_dy;
-            const int y0 = (tid * 4) / N, x = tid * 4 - y0 * N;
-            const int w0 = int(u - t_beg), w1 = int(seg_end - t_beg);
-            const int y = w0 * dy + y0;
-            size_t p = size_t(y) * N + x;
-            const int hstep = dy * HP, hwrap = P * HP;
-            int hx = x - d.c; if (hx < 0) hx += P;
-            int hy = y - d.r; if (hy < 0) hy += P;
-            int ho = hy * HP + hx;
-            int w = w0;
-#pragma unroll 1
-            for (; w + UF <= w1; w += UF) {
-                Quad q[UF];
-#pragma unroll
-                for (int i = 0; i < UF; ++i) {
-                    const float4* Up = reinterpret_cast<const float4*>(U + p + size_t(i) * UNIT_PX);
-                    q[i].ua = ld_rw4(Up, pf); q[i].ub = ld_rw4(Up + 1, pf);
-                    q[i].iv = ld_rw4(reinterpret_cast<const float4*>(I + p + size_t(i) * UNIT_PX), pf);
-                    const float2* hp = h + ho;
-                    q[i].h0 = ld_keep2(hp, pl); q[i].h1 = ld_keep2(hp + 1, pl);
-                    q[i].h2 = ld_keep2(hp + 2, pl); q[i].h3 = ld_keep2(hp + 3, pl);
-                    ho += hstep; if (ho >= hwrap) ho -= hwrap;
-                }
-#pragma unroll
-                for (int i = 0; i < UF; ++i) commit_quad(q[i], U, I, p + size_t(i) * UNIT_PX, s2, sg, invFg, pf);
-                p += size_t(UF) * UNIT_PX;
-            }
-#pragma unroll 1
-            for (; w < w1; ++w) {
-                Quad q;
-                const float4* Up = reinterpret_cast<const float4*>(U + p);
-                q.ua = ld_rw4(Up, pf); q.ub = ld_rw4(Up + 1, pf);
-                q.iv = ld_rw4(reinterpret_cast<const float4*>(I + p), pf);
-                const float2* hp = h + ho;
-                q.h0 = ld_keep2(hp, pl); q.h1 = ld_keep2(hp + 1, pl);
-                q.h2 = ld_keep2(hp + 2, pl); q.h3 = ld_keep2(hp + 3, pl);
-                ho += hstep; if (ho >= hwrap) ho -= hwrap;
-                commit_quad(q, U, I, p, s2, sg, invFg, pf);
-                p += UNIT_PX;
-            }
+            commit_run_rows<UF>(a, U, I, h, d.r, d.c, sg, int(u - t_beg), int(seg_end - t_beg), tid, invFg, pf, pl);
         } else {
             Cursor cu; cu.init(int(u - t_beg), tid, N);
             long long v = u;
@@ -936,6 +955,165 @@ k_commit_t(const DeltaArgs a) {
             }
         }
         u = seg_end;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_rollout: a whole open-loop rollout -- `steps` sequential flips per environment, actions known in advance
+// (device-resident action lists: random-policy rollouts, replays, the candidate orders of a batched greedy
+// DBS) -- in ONE persistent cooperative launch.  It removes the per-step fixed cost of the eval -> commit chain
+// (two launches: CTA ramp, first DRAM round trip, tail, grid completion -- 10 of 48 us per vectorised step).
+//
+// Every environment is owned by `cpe` co-resident CTAs, each by a fixed slice of the image's units.  A step is
+//     evaluate my slice (same per-quad arithmetic and 2^-40 fixed-point sums as k_eval_t)
+//     -> one returning atomic per sum into the environment's ring slot (total << 10 | contributors)
+//     -> spin until all cpe CTAs of THIS environment have contributed (no grid-wide barrier: environments drift
+//        apart, the other CTA of the SM belongs to another environment and keeps the memory system busy)
+//     -> every CTA turns the exact totals into PSNR and the decision itself (same float64 closed form)
+//     -> commit my slice if kept (the same thread re-reads the quads it will evaluate next: program order)
+// Decisions, results, U, I, state and sums are bit-identical to `steps` calls of k_eval_t + k_commit_t.
+// Row-regular images only (N divides UNIT_PX); the host falls back to the two-kernel chain otherwise.
+// The launch is cooperative (co-residency guaranteed or refused); a spin that exceeds ROLLOUT_SPIN_LIMIT polls
+// raises *error and ends the kernel instead of hanging the device.
+// ---------------------------------------------------------------------------
+constexpr int ROLLOUT_RING = 4;
+constexpr unsigned ROLLOUT_SPIN_LIMIT = 1u << 24;
+
+struct RolloutArgs {
+    DeltaArgs a;                       // fields, tables, sums, shape, rule (task lists unused)
+    const int32_t* envs;               // [n_env] device env ids or nullptr (identity)
+    const long long* actions;          // action of (step t, env slot e): actions[t * act_step + e * act_env]; < 0 = idle
+    long long act_step, act_env;
+    Result* results;                   // results[t * res_step + e * res_env] or nullptr
+    long long res_step, res_env;
+    uint8_t* log_accept; double* log_psnr;   // optional logs, indexed like results
+    unsigned long long* ring;          // [n_env][ROLLOUT_RING][2], zero at launch
+    int* error;                        // device flag, 0 at launch
+    int n_env, steps, cpe;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int UF, typename R>
+__global__ void __launch_bounds__(256, 2)
+k_rollout_t(const RolloutArgs ra) {
+    const DeltaArgs& a = ra.a;
+    __shared__ long long sh[2][8];
+    __shared__ int s_dec;                                  // 1 keep, 0 reject, -1 abort
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int slot_e = blockIdx.x / ra.cpe, part = blockIdx.x - slot_e * ra.cpe;
+    const int env = ra.envs ? ra.envs[slot_e] : slot_e;
+    const int N = a.N, P = a.P, upt = a.units_per_task;
+    const int w0 = int((long long)part * upt / ra.cpe), w1 = int((long long)(part + 1) * upt / ra.cpe);
+    const bool leader = (part == 0);
+    const size_t n2 = size_t(N) * N;
+    const R invFg = R(1) / R(a.Fg), c2 = R(2) / R(a.Fg);
+    const float invFg_f = 1.f / float(a.Fg);
+    const uint64_t pf = policy_evict_first(), pl = policy_evict_last();
+    unsigned long long* ring = ra.ring + size_t(slot_e) * ROLLOUT_RING * 2;
+    double S[4] = {0.0, 0.0, 0.0, 0.0};                    // running sums of the environment (thread 0 of every CTA)
+    if (tid == 0) {
+        const double* Sp = a.sums + size_t(env) * 4;
+        S[0] = Sp[0]; S[1] = Sp[1]; S[2] = Sp[2]; S[3] = Sp[3];
+    }
+    long long prev_act = -1; int prev_sgn = 0, prev_keep = 0;
+    int ring_step = 0;                                     // counts the active (non-idle) steps
+    for (int t = 0; t < ra.steps; ++t) {
+        const long long act = ra.actions[(long long)t * ra.act_step + (long long)slot_e * ra.act_env];
+        const long long ri = (long long)t * ra.res_step + (long long)slot_e * ra.res_env;
+        if (act < 0) {                                     // idle slot: every CTA of the environment sees the same
+            if (leader && tid == 0 && ra.results) {
+                Result r; r.psnr_after = 0.0; r.d_sii = 0.0; r.d_sit = 0.0; r.action = -1; r.accept = 0; r.sgn = 0;
+                ra.results[ri] = r;
+            }
+            continue;
+        }
+        const int f = int(act / (long long)n2);
+        const int pix = int(act - (long long)f * (long long)n2);
+        const int r = pix / N, c = pix - r * N, g = f / a.Fg;
+        int8_t* stp = a.state + (size_t(env) * a.F + f) * n2 + size_t(r) * N + c;
+        // sign of the flip: the resident state byte -- unless the previous step touched the same pixel (its byte
+        // is written by the leader CTA after ITS barrier, not ordered with this read): then it follows from
+        // the previous step's sign and decision.  Bytes written two or more steps ago are ordered by the
+        // barrier in between.
+        int sbyte;
+        if (act == prev_act) sbyte = prev_keep ? (prev_sgn > 0 ? 1 : 0) : (prev_sgn > 0 ? 0 : 1);
+        else sbyte = ld_state_relaxed(stp);
+        float2* U = a.U + (size_t(env) * a.F + f) * n2;
+        float* I = a.I + (size_t(env) * a.G + g) * n2;
+        const float* T = a.T + (size_t(env) * a.G + g) * n2;
+        const float2* h = a.h + size_t(g) * P * a.HP;
+        long long acc[1][4] = {{0, 0, 0, 0}};
+        const int sg0 = 1;
+        eval_run_rows<1, UF, R, 4, true>(a, U, I, T, h, &r, &c, &sg0, acc, w0, w1, tid, c2, invFg, pf, pl);
+        const int sg = 1 - 2 * sbyte;
+        long long aII = (sg < 0 ? -acc[0][0] : acc[0][0]) + acc[0][1];
+        long long aIT = (sg < 0 ? -acc[0][2] : acc[0][2]) + acc[0][3];
+        aII = warp_sum_ll(aII); aIT = warp_sum_ll(aIT);
+        if (lane == 0) { sh[0][warp] = aII; sh[1][warp] = aIT; }
+        __syncthreads();
+        if (tid == 0) {
+            long long x = 0, y = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { x += sh[0][i]; y += sh[1][i]; }
+            unsigned long long* wd = ring + size_t(ring_step % ROLLOUT_RING) * 2;
+            __threadfence();                               // my earlier stores (ring zeroing, state byte) first
+            atomicAdd(wd, ((unsigned long long)x << CNT_BITS) + 1ull);
+            atomicAdd(wd + 1, ((unsigned long long)y << CNT_BITS) + 1ull);
+            unsigned long long wx = 0, wy = 0;
+            unsigned spins = 0;
+            bool ok = false;
+            while (true) {
+                wx = ld_acquire_u64(wd); wy = ld_acquire_u64(wd + 1);
+                if (unsigned(wx & CNT_MASK) == unsigned(ra.cpe) && unsigned(wy & CNT_MASK) == unsigned(ra.cpe)) { ok = true; break; }
+                if (++spins > ROLLOUT_SPIN_LIMIT || *reinterpret_cast<volatile int*>(ra.error)) break;
+            }
+            int keep = -1;
+            if (ok) {
+                const double dII = double((long long)wx >> CNT_BITS) * FIX_INV;
+                const double dIT = double((long long)wy >> CNT_BITS) * FIX_INV;
+                const double psnr = psnr_from_sums(a, S[0] + dII, S[1] + dIT, S[2], n2);
+                keep = apply_rule(a.rule, psnr, S[3]);
+                if (leader) {
+                    if (ra.results) {
+                        Result res; res.psnr_after = psnr; res.d_sii = dII; res.d_sit = dIT;
+                        res.action = act; res.accept = keep; res.sgn = sg;
+                        ra.results[ri] = res;
+                    }
+                    if (ra.log_accept) ra.log_accept[ri] = uint8_t(keep);
+                    if (ra.log_psnr) ra.log_psnr[ri] = psnr;
+                    // the slot used two active steps from now: everyone has read it (they contributed to this step)
+                    unsigned long long* wz = ring + size_t((ring_step + 2) % ROLLOUT_RING) * 2;
+                    wz[0] = 0ull; wz[1] = 0ull;
+                    if (keep) {
+                        *stp = int8_t(sg > 0 ? 1 : 0);
+                        if (a.recon_stale) {
+                            uint8_t* sm = a.recon_stale + size_t(env) * RECON_MAX_BUFFERS;
+#pragma unroll
+                            for (int b = 0; b < RECON_MAX_BUFFERS; ++b) sm[b] |= uint8_t(1 << g);
+                        }
+                    }
+                }
+                if (keep) { S[0] += dII; S[1] += dIT; S[3] = psnr; }
+            } else {
+                atomicExch(ra.error, 1);
+            }
+            s_dec = keep;
+        }
+        __syncthreads();
+        const int keep = s_dec;
+        if (keep < 0) break;                               // abort: CTA-uniform
+        if (keep) commit_run_rows<UF>(a, U, I, h, r, c, float(sg), w0, w1, tid, invFg_f, pf, pl);
+        prev_act = act; prev_sgn = sg; prev_keep = keep;
+        ++ring_step;
+    }
+    if (leader && tid == 0) {
+        double* Sp = a.sums + size_t(env) * 4;
+        Sp[0] = S[0]; Sp[1] = S[1]; Sp[3] = S[3];
     }
 }
 

@@ -71,6 +71,8 @@ struct bh_ctx {
     // observation path (bh_recon_batch)
     uint8_t* d_recon_stale = nullptr;    // [E][RECON_MAX_BUFFERS]
     ReconPlan* d_recon_plan = nullptr;   // [max_tasks]
+    unsigned long long* d_ring = nullptr; // [E][ROLLOUT_RING][2] + error flag: barriers of the persistent rollout kernel
+    int rollout_cap = 0;                 // co-resident CTAs of k_rollout_t (0: cooperative launch unavailable)
     float* d_recon_obs[RECON_MAX_BUFFERS] = {nullptr, nullptr, nullptr, nullptr};   // device observation blocks
     cudaEvent_t ev_recon = nullptr;
     // scratch of bh_sweep_stats, kept between calls
@@ -524,7 +526,7 @@ extern "C" int bh_destroy(bh_ctx* c) {
     cudaFree(c->dK3); cudaFree(c->dK4); cudaFree(c->dK5); cudaFree(c->dK6); cudaFree(c->dsw_in); cudaFree(c->dsw_out);
     cudaFree(c->dsw_buf);
     cudaFree(c->dsw_it); cudaFree(c->dsw_ii); cudaFree(c->dsw_psnr);
-    cudaFree(c->d_recon_stale); cudaFree(c->d_recon_plan);
+    cudaFree(c->d_recon_stale); cudaFree(c->d_recon_plan); cudaFree(c->d_ring);
     for (auto& b : c->d_recon_obs) cudaFree(b);
     cudaFree(c->d_stat_map); cudaFree(c->d_stat_pre); cudaFree(c->d_stat_out);
     if (c->ev_recon) cudaEventDestroy(c->ev_recon);
@@ -885,6 +887,89 @@ extern "C" int bh_step_batch_device(bh_ctx* c, int n, const int32_t* d_env_ids, 
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// open-loop rollouts in one persistent launch (k_rollout_t)
+// ---------------------------------------------------------------------------
+static int rollout_setup(bh_ctx* c) {
+    if (c->d_ring) return 0;
+    int coop = 0, nb = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+    auto kern = c->fp64_eval ? k_rollout_t<3, double> : k_rollout_t<3, float>;
+    BH_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, 0));
+    c->rollout_cap = (coop && !std::getenv("BHOLO_NO_ROLLOUT_KERNEL")) ? nb * c->sms : 0;
+    BH_CUDA(c, cudaMalloc(&c->d_ring, (size_t(c->E) * ROLLOUT_RING * 2 + 2) * sizeof(unsigned long long)));
+    BH_CUDA(c, cudaMemsetAsync(c->d_ring, 0, (size_t(c->E) * ROLLOUT_RING * 2 + 2) * sizeof(unsigned long long), c->stream));
+    return 0;
+}
+
+// 1: launched; 0: this shape / rule needs the two-kernel chain; < 0: error
+static int launch_rollout(bh_ctx* c, int n_env, const int32_t* d_env_ids, const long long* d_actions,
+                          long long act_step, long long act_env, int steps, int rule, Result* d_results,
+                          long long res_step, long long res_env, uint8_t* log_accept, double* log_psnr) {
+    if (int rc = rollout_setup(c)) return rc;
+    const bool regular = UNIT_PX % c->N == 0;
+    const int cpe = std::min(c->rollout_cap / std::max(1, n_env), std::min(c->units_per_task, MAX_DELTA_GRID));
+    if (!regular || cpe < 1 || rule == RULE_NEVER) return 0;
+    RolloutArgs ra;
+    ra.a = make_args(c, n_env, 0, nullptr, nullptr, rule, nullptr);
+    ra.envs = d_env_ids;
+    ra.actions = d_actions;
+    ra.act_step = act_step; ra.act_env = act_env;
+    ra.results = d_results;
+    ra.res_step = res_step; ra.res_env = res_env;
+    ra.log_accept = log_accept; ra.log_psnr = log_psnr;
+    ra.ring = c->d_ring;
+    ra.error = reinterpret_cast<int*>(c->d_ring + size_t(c->E) * ROLLOUT_RING * 2);
+    ra.n_env = n_env; ra.steps = steps; ra.cpe = cpe;
+    // the ring words are zeroed, the error flag (the word behind them) is sticky until bh_rollout_status
+    BH_CUDA(c, cudaMemsetAsync(c->d_ring, 0, size_t(c->E) * ROLLOUT_RING * 2 * sizeof(unsigned long long), c->stream));
+    void* params[] = {&ra};
+    const void* kern = c->fp64_eval ? reinterpret_cast<const void*>(k_rollout_t<3, double>)
+                                    : reinterpret_cast<const void*>(k_rollout_t<3, float>);
+    BH_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(cpe * n_env), dim3(256), params, 0, c->stream));
+    c->launches += 1;
+    return 1;
+}
+
+extern "C" int bh_rollout_device(bh_ctx* c, int n_env, const int32_t* d_env_ids, const int64_t* d_actions,
+                                 int64_t act_step_stride, int64_t act_env_stride, int steps, int rule,
+                                 bh_result* d_results, int64_t res_step_stride, int64_t res_env_stride) {
+    BH_CHECK_CTX(c);
+    if (n_env < 1 || n_env > c->E || n_env > c->max_tasks || steps < 0 || !d_actions) BH_FAIL(c, -1, "bad arguments");
+    if (rule < 0 || rule > 3) BH_FAIL(c, -1, "bad rule %d", rule);
+    if (steps == 0) return 0;
+    const int rc = launch_rollout(c, n_env, d_env_ids, reinterpret_cast<const long long*>(d_actions), act_step_stride,
+                                  act_env_stride, steps, rule, reinterpret_cast<Result*>(d_results), res_step_stride,
+                                  res_env_stride, nullptr, nullptr);
+    if (rc != 0) return rc < 0 ? rc : 0;
+    // the two-kernel chain, step by step (every image size, any number of environments)
+    if (act_env_stride != 1 || (d_results && res_env_stride != 1))
+        BH_FAIL(c, -4, "this shape needs step-major action / result lists (env stride 1)");
+    if (!d_env_ids && n_env > 1) BH_FAIL(c, -1, "a batch step needs one distinct env per task");
+    for (int t = 0; t < steps; ++t) {
+        DeltaArgs a = make_args(c, n_env, 0, d_env_ids, reinterpret_cast<const long long*>(d_actions) + t * act_step_stride,
+                                rule, d_results ? reinterpret_cast<Result*>(d_results) + t * res_step_stride : c->d_results);
+        launch_eval(c, a);
+        if (rule != RULE_NEVER) launch_commit(c, a);
+    }
+    BH_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// 1 if the last rollout aborted at a barrier (a CTA waited longer than ROLLOUT_SPIN_LIMIT polls); synchronises
+extern "C" int bh_rollout_status(bh_ctx* c) {
+    BH_CHECK_CTX(c);
+    if (!c->d_ring) return 0;
+    int flag = 0;
+    BH_CUDA(c, cudaMemcpyAsync(&flag, c->d_ring + size_t(c->E) * ROLLOUT_RING * 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    BH_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (flag) {
+        cudaMemsetAsync(c->d_ring + size_t(c->E) * ROLLOUT_RING * 2, 0, sizeof(unsigned long long), c->stream);
+        BH_FAIL(c, -5, "rollout kernel aborted at a barrier (co-residency lost?)");
+    }
+    return 0;
+}
+
 extern "C" int bh_step_batch(bh_ctx* c, int n, const int32_t* env_ids, const int64_t* actions, int rule,
                              bh_result* results) {
     BH_CHECK_CTX(c);
@@ -1141,16 +1226,42 @@ extern "C" int bh_dbs_run_batch(bh_ctx* c, int n_env, const int32_t* env_ids, co
             for (int64_t i = 0; i < m; ++i)                     // [iteration][env]
                 for (int e = 0; e < n_env; ++e) h_ord[size_t(i) * n_env + e] = orders[size_t(e) * n + base + i];
             BH_DB(cudaMemcpyAsync(d_ord, h_ord, size_t(m) * n_env * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-            for (int64_t i = 0; i < m; ++i) {
-                DeltaArgs a = make_args(c, n_env, 0, d_ids, d_ord + size_t(i) * n_env, RULE_DBS, c->d_results);
-                a.log_accept = d_acc + size_t(i) * n_env;
-                a.log_psnr = d_tr ? d_tr + size_t(i) * n_env : nullptr;
-                launch_eval(c, a);
-                launch_commit(c, a);
-                if (resync_every > 0 && ++since_resync >= resync_every && base + i + 1 < n) {
+            for (int64_t i = 0; i < m;) {
+                // iterations up to the next re-synchronisation: ONE persistent launch (k_rollout_t: identical
+                // decisions and fields), or -- image sizes that are not row regular -- one k_eval + one k_commit
+                // launch per iteration
+                int64_t seg = m - i;
+                if (resync_every > 0) seg = std::min<int64_t>(seg, std::max<int64_t>(1, resync_every - since_resync));
+                seg = std::min<int64_t>(seg, 1 << 20);
+                const int launched = launch_rollout(c, n_env, d_ids, d_ord + size_t(i) * n_env, n_env, 1, int(seg), RULE_DBS,
+                                                    nullptr, n_env, 1, d_acc + size_t(i) * n_env,
+                                                    d_tr ? d_tr + size_t(i) * n_env : nullptr);
+                if (launched < 0) { cleanup(); return launched; }
+                if (!launched) {
+                    for (int64_t j = i; j < i + seg; ++j) {
+                        DeltaArgs a = make_args(c, n_env, 0, d_ids, d_ord + size_t(j) * n_env, RULE_DBS, c->d_results);
+                        a.log_accept = d_acc + size_t(j) * n_env;
+                        a.log_psnr = d_tr ? d_tr + size_t(j) * n_env : nullptr;
+                        launch_eval(c, a);
+                        launch_commit(c, a);
+                    }
+                }
+                i += seg;
+                since_resync += seg;
+                if (resync_every > 0 && since_resync >= resync_every && base + i < n) {
                     for (int e = 0; e < n_env; ++e)
                         if (int rc = propagate_env(c, ids[e])) { cleanup(); return rc; }
                     since_resync = 0;
+                }
+            }
+            if (c->d_ring) {                                   // a barrier of the persistent kernel gave up?
+                int flag = 0;
+                BH_DB(cudaMemcpyAsync(&flag, c->d_ring + size_t(c->E) * ROLLOUT_RING * 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                BH_DB(cudaStreamSynchronize(c->stream));
+                if (flag) {
+                    cudaMemsetAsync(c->d_ring + size_t(c->E) * ROLLOUT_RING * 2, 0, sizeof(unsigned long long), c->stream);
+                    cleanup();
+                    BH_FAIL(c, -5, "rollout kernel aborted at a barrier");
                 }
             }
             BH_DB(cudaGetLastError());

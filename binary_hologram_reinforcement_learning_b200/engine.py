@@ -22,7 +22,7 @@ METHOD_ASM, METHOD_FRESNEL = 0, 1
 ABI_SYMBOLS = (
     "bh_abi_version", "bh_last_error", "bh_create", "bh_destroy", "bh_set_stream",
     "bh_set_target", "bh_load_state", "bh_clone_env", "bh_resync", "bh_get_metrics", "bh_eval_flips",
-    "bh_step_batch", "bh_vec_step", "bh_vec_book_update", "bh_step_batch_device", "bh_eval_flips_device", "bh_max_tasks",
+    "bh_step_batch", "bh_vec_step", "bh_vec_book_update", "bh_step_batch_device", "bh_rollout_device", "bh_rollout_status", "bh_eval_flips_device", "bh_max_tasks",
     "bh_commit_flip", "bh_dbs_run", "bh_dbs_run_batch", "bh_sweep_all", "bh_sweep_stats", "bh_get_recon", "bh_get_state", "bh_get_field",
     "bh_recon_batch", "bh_recon_device_block", "bh_recon_planes_written", "bh_stream_sync",
     "bh_device_ptr", "bh_host_alloc", "bh_host_free", "bh_simulate", "bh_time_eval", "bh_time_step", "bh_time_commit",
@@ -91,6 +91,8 @@ def load_library(build_if_missing: bool = True):
         "bh_vec_step": (i32, [vp, i32, vp, vp, i32, vp, vp]),
         "bh_vec_book_update": (i32, [i32, vp, vp, vp, vp]),
         "bh_step_batch_device": (i32, [vp, i32, vp, vp, i32, vp]),
+        "bh_rollout_device": (i32, [vp, i32, vp, vp, i64, i64, i32, i32, vp, i64, i64]),
+        "bh_rollout_status": (i32, [vp]),
         "bh_eval_flips_device": (i32, [vp, i32, i32, vp, vp, vp]),
         "bh_max_tasks": (i32, [vp]),
         "bh_commit_flip": (i32, [vp, i32, i64]),
@@ -323,6 +325,20 @@ class HoloEngine:
         self._check(self.lib.bh_step_batch_device(self._h, n, C.c_void_p(d_env_ids),
                                                   C.c_void_p(d_actions), rule, C.c_void_p(d_results)),
                     "bh_step_batch_device")
+
+    def rollout_device(self, n_env: int, d_env_ids: int, d_actions: int, steps: int, rule: int, d_results: int = 0,
+                       act_strides=None, res_strides=None):
+        """``steps`` sequential flips per environment, actions known in advance, in one persistent launch
+        (``bh_rollout_device``).  Default layout: step-major ``[steps][n_env]`` lists (strides in elements)."""
+        a_s, a_e = act_strides if act_strides is not None else (n_env, 1)
+        r_s, r_e = res_strides if res_strides is not None else (n_env, 1)
+        self._check(self.lib.bh_rollout_device(self._h, n_env, C.c_void_p(d_env_ids or None), C.c_void_p(d_actions),
+                                               a_s, a_e, steps, rule, C.c_void_p(d_results or None), r_s, r_e),
+                    "bh_rollout_device")
+
+    def rollout_status(self):
+        """Synchronise and raise if the last rollout aborted at a barrier."""
+        self._check(self.lib.bh_rollout_status(self._h), "bh_rollout_status")
 
     def eval_flips_device(self, n: int, d_env_ids: int, d_actions: int, d_results: int, env: int = 0):
         self._check(self.lib.bh_eval_flips_device(self._h, env, n, C.c_void_p(d_env_ids or None),

@@ -242,6 +242,19 @@ int bh_simulate(int device, void* cuda_stream, const float* in, int is_complex, 
  * consecutive launches stream different frames (working set >> L2). */
 int bh_time_eval(bh_ctx* ctx, int n, const int32_t* d_env_ids, const int64_t* d_actions,
                  int n_sets, int reps, float* ms_per_launch);
+/* Open-loop rollout: `steps` sequential flips per environment with actions known in advance (device
+ * resident), in ONE persistent cooperative launch (k_rollout_t: per-environment barriers instead of two
+ * launches per step).  Replaces `steps` calls of the reference's step()  (env.py:154-260 reward path) /
+ * `steps` iterations of the DBS loop over several images (DBS_1024_24.py:313-422) when the actions do not
+ * depend on the observations.  Action of (step t, slot e) = d_actions[t * act_step_stride + e * act_env_stride]
+ * (< 0: idle), result likewise in d_results (may be NULL).  Decisions, results and the final device state are
+ * bit-identical to `steps` calls of bh_step_batch_device.  Image sizes that are not row regular (N does not
+ * divide 1024) and RULE_NEVER run the two-kernel chain step by step (env strides must be 1 then).
+ * Asynchronous on the context stream; bh_rollout_status synchronises and reports an aborted barrier. */
+int bh_rollout_device(bh_ctx* ctx, int n_env, const int32_t* d_env_ids, const int64_t* d_actions,
+                      int64_t act_step_stride, int64_t act_env_stride, int steps, int rule,
+                      bh_result* d_results, int64_t res_step_stride, int64_t res_env_stride);
+int bh_rollout_status(bh_ctx* ctx);
 /* The step chain as bh_step_batch_device launches it (k_eval -> k_commit) for `reps` steps;
  * with_commit = 0 times the evaluations alone under the same rule. */
 int bh_time_step(bh_ctx* ctx, int n, const int32_t* d_env_ids, const int64_t* d_actions,

@@ -1013,3 +1013,84 @@ def test_batched_dbs_equals_the_sequential_loop_of_every_image():
         assert fin[e] == f1
         assert np.array_equal(eng.state(e), one.state(0))
     eng.close(); one.close()
+
+
+# ---------------------------------------------------------------------------
+# round 2, session 4: persistent open-loop rollout kernel (bh_rollout_device)
+# ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("N,F,wl,E,steps,rule", [
+    (32, 4, O.WL_MONO, 1, 40, RULE_ENV),          # one unit per image: one CTA per env
+    (64, 6, O.WL_RGB, 3, 60, RULE_ENV),
+    (256, 8, O.WL_MONO, 5, 80, RULE_DBS),
+    (1024, 24, O.WL_RGB, 8, 48, RULE_ENV),        # the bench shape: 37 CTAs per env
+    (1024, 3, O.WL_RGB, 1, 24, RULE_DBS),         # one env owns the whole chip
+    (896, 3, O.WL_RGB, 2, 12, RULE_ENV),          # not row regular: falls back to the two-kernel chain
+])
+def test_rollout_kernel_is_bit_identical_to_the_step_chain(N, F, wl, E, steps, rule):
+    """bh_rollout_device (one persistent cooperative launch, per-environment barriers) against `steps` calls of
+    bh_step_batch_device on a twin context: result records, final holograms, fields, reconstructions and running
+    sums are identical bit for bit.  The action lists revisit a pixel in consecutive steps (kept and rejected),
+    contain idle slots (-1) and use both list layouts (step-major, env-major)."""
+    import torch
+    rng = np.random.default_rng(N + 7 * E)
+    acts = rng.integers(0, F * N * N, size=(steps, E)).astype(np.int64)
+    acts[3] = acts[2]                                   # same pixels again right away
+    acts[4] = acts[2]                                   # and a third time
+    acts[7, 0] = acts[5, 0]                             # same pixel two steps later
+    if E > 1:
+        acts[9, 1] = -1                                 # idle slot
+    envs = np.arange(E, dtype=np.int32)[::-1].copy()    # slot e drives environment E-1-e
+    engs = []
+    for _ in range(2):
+        eng = _engine(N, F, wl, n_env=E)
+        for e in range(E):
+            pre, tgt, st = _problem(N, F, wl, seed=40 + e)
+            eng.set_target(e, tgt)
+            eng.load_state(e, st)
+        engs.append(eng)
+    chain, roll = engs
+    d_envs = torch.from_numpy(envs).cuda()
+    d_acts = torch.from_numpy(acts).cuda()
+    d_res_a = torch.zeros(steps * E * 40, dtype=torch.uint8, device="cuda")
+    for t in range(steps):
+        chain.step_batch_device(E, d_envs.data_ptr(), d_acts.data_ptr() + t * E * 8, rule, d_res_a.data_ptr() + t * E * 40)
+    chain.stream_sync()
+    regular = 1024 % N == 0
+    if regular:
+        # env-major lists: actions[e][t], results[e][t]
+        d_acts_t = d_acts.t().contiguous()
+        d_res_b = torch.zeros(steps * E * 40, dtype=torch.uint8, device="cuda")
+        roll.rollout_device(E, d_envs.data_ptr(), d_acts_t.data_ptr(), steps, rule, d_res_b.data_ptr(),
+                            act_strides=(1, steps), res_strides=(1, steps))
+        roll.rollout_status()
+        res_b = d_res_b.cpu().numpy().view(RESULT_DTYPE).reshape(E, steps).T
+    else:
+        d_res_b = torch.zeros(steps * E * 40, dtype=torch.uint8, device="cuda")
+        roll.rollout_device(E, d_envs.data_ptr(), d_acts.data_ptr(), steps, rule, d_res_b.data_ptr())
+        roll.rollout_status()
+        res_b = d_res_b.cpu().numpy().view(RESULT_DTYPE).reshape(steps, E)
+    res_a = d_res_a.cpu().numpy().view(RESULT_DTYPE).reshape(steps, E)
+    for name in ("action", "accept", "sgn", "psnr_after", "d_sii", "d_sit"):
+        assert np.array_equal(res_a[name], res_b[name]), name
+    assert 0 < res_a["accept"].sum() < steps * E         # both decisions occur
+    for e in range(E):
+        assert np.array_equal(chain.state(e), roll.state(e))
+        assert chain.metrics(e) == roll.metrics(e)
+        assert np.array_equal(chain.recon(e), roll.recon(e))
+        for f in range(0, F, max(1, F // 3)):
+            assert np.array_equal(chain.field(e, f), roll.field(e, f))
+    # a second rollout on the same context continues from the committed state (ring and sums re-initialised)
+    if regular:
+        more = rng.integers(0, F * N * N, size=(10, E)).astype(np.int64)
+        d_more = torch.from_numpy(more).cuda()
+        for t in range(10):
+            chain.step_batch_device(E, d_envs.data_ptr(), d_more.data_ptr() + t * E * 8, rule, 0 if False else d_res_a.data_ptr())
+        roll.rollout_device(E, d_envs.data_ptr(), d_more.data_ptr(), 10, rule, 0)
+        roll.rollout_status()
+        chain.stream_sync()
+        for e in range(E):
+            assert np.array_equal(chain.state(e), roll.state(e))
+            assert chain.metrics(e) == roll.metrics(e)
+    chain.close(); roll.close()
