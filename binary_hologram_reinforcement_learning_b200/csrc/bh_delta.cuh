@@ -990,6 +990,7 @@ struct RolloutArgs {
     unsigned long long* ring;          // [n_env][ROLLOUT_RING][2], zero at launch
     int* error;                        // device flag, 0 at launch
     int n_env, steps, cpe;
+    unsigned backoff_ns;               // sleep between two polls of a barrier word
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -1067,10 +1068,17 @@ k_rollout_t(const RolloutArgs ra) {
             unsigned long long wx = 0, wy = 0;
             unsigned spins = 0;
             bool ok = false;
+            // poll the first word until it is complete, then the second (one load per poll); a short sleep between
+            // polls keeps hundreds of pollers from delaying the atomics they are waiting for
             while (true) {
-                wx = ld_acquire_u64(wd); wy = ld_acquire_u64(wd + 1);
-                if (unsigned(wx & CNT_MASK) == unsigned(ra.cpe) && unsigned(wy & CNT_MASK) == unsigned(ra.cpe)) { ok = true; break; }
-                if (++spins > ROLLOUT_SPIN_LIMIT || *reinterpret_cast<volatile int*>(ra.error)) break;
+                wx = ld_acquire_u64(wd);
+                if (unsigned(wx & CNT_MASK) == unsigned(ra.cpe)) {
+                    wy = ld_acquire_u64(wd + 1);
+                    if (unsigned(wy & CNT_MASK) == unsigned(ra.cpe)) { ok = true; break; }
+                }
+                if (++spins > ROLLOUT_SPIN_LIMIT) break;
+                if ((spins & 255u) == 0u && *reinterpret_cast<volatile int*>(ra.error)) break;
+                if (ra.backoff_ns) __nanosleep(ra.backoff_ns);
             }
             int keep = -1;
             if (ok) {

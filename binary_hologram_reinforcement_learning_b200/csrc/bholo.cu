@@ -908,7 +908,10 @@ static int launch_rollout(bh_ctx* c, int n_env, const int32_t* d_env_ids, const 
                           long long res_step, long long res_env, uint8_t* log_accept, double* log_psnr) {
     if (int rc = rollout_setup(c)) return rc;
     const bool regular = UNIT_PX % c->N == 0;
-    const int cpe = std::min(c->rollout_cap / std::max(1, n_env), std::min(c->units_per_task, MAX_DELTA_GRID));
+    int cpe = std::min(c->rollout_cap / std::max(1, n_env), std::min(c->units_per_task, MAX_DELTA_GRID));
+    static const int cpe_cap = std::getenv("BHOLO_ROLLOUT_CPE") ? std::atoi(std::getenv("BHOLO_ROLLOUT_CPE")) : 0;
+    static const int backoff = std::getenv("BHOLO_ROLLOUT_BACKOFF") ? std::atoi(std::getenv("BHOLO_ROLLOUT_BACKOFF")) : 0;
+    if (cpe_cap > 0) cpe = std::min(cpe, cpe_cap);
     if (!regular || cpe < 1 || rule == RULE_NEVER) return 0;
     RolloutArgs ra;
     ra.a = make_args(c, n_env, 0, nullptr, nullptr, rule, nullptr);
@@ -921,6 +924,7 @@ static int launch_rollout(bh_ctx* c, int n_env, const int32_t* d_env_ids, const 
     ra.ring = c->d_ring;
     ra.error = reinterpret_cast<int*>(c->d_ring + size_t(c->E) * ROLLOUT_RING * 2);
     ra.n_env = n_env; ra.steps = steps; ra.cpe = cpe;
+    ra.backoff_ns = unsigned(std::max(0, backoff));
     // the ring words are zeroed, the error flag (the word behind them) is sticky until bh_rollout_status
     BH_CUDA(c, cudaMemsetAsync(c->d_ring, 0, size_t(c->E) * ROLLOUT_RING * 2 * sizeof(unsigned long long), c->stream));
     void* params[] = {&ra};
