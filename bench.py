@@ -620,6 +620,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         windows.append((t0w, time.time()))
         eng.rollout_status()                          # raises if a barrier of the persistent kernel gave up
+        launches = eng.launch_count - launches0       # K: one k_rollout_t launch per bench step
         res_host = d_res.cpu().numpy().view(RESULT_DTYPE).reshape(R, E).copy()      # last timed rollout
         # a rollout of fresh actions through one k_eval + one k_commit launch per vectorised step (what step() uses)
         ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -631,7 +632,6 @@ def run_b200(args):
         step_chain_ms = ec0.elapsed_time(ec1)
         chain_accept = float(d_res.cpu().numpy().view(RESULT_DTYPE).reshape(R, E)["accept"].mean())
     bdist.barrier()
-    launches = K                                      # one k_rollout_t launch per bench step
     dev_ms = bdist.max_over_ranks(ev0.elapsed_time(ev1))
     value = world * E * R * K / (dev_ms / 1000.0)
     accept_rate = float(res_host["accept"].mean())

@@ -930,7 +930,14 @@ static int launch_rollout(bh_ctx* c, int n_env, const int32_t* d_env_ids, const 
     void* params[] = {&ra};
     const void* kern = c->fp64_eval ? reinterpret_cast<const void*>(k_rollout_t<3, double>)
                                     : reinterpret_cast<const void*>(k_rollout_t<3, float>);
-    BH_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(cpe * n_env), dim3(256), params, 0, c->stream));
+    const cudaError_t le = cudaLaunchCooperativeKernel(kern, dim3(cpe * n_env), dim3(256), params, 0, c->stream);
+    if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported || le == cudaErrorLaunchOutOfResources) {
+        // co-residency refused (a shared or partitioned GPU): the two-kernel chain computes the same thing
+        cudaGetLastError();
+        c->rollout_cap = 0;
+        return 0;
+    }
+    BH_CUDA(c, le);
     c->launches += 1;
     return 1;
 }
