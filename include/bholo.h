@@ -247,7 +247,8 @@ int bh_time_eval(bh_ctx* ctx, int n, const int32_t* d_env_ids, const int64_t* d_
  * launches per step).  Replaces `steps` calls of the reference's step()  (env.py:154-260 reward path) /
  * `steps` iterations of the DBS loop over several images (DBS_1024_24.py:313-422) when the actions do not
  * depend on the observations.  Action of (step t, slot e) = d_actions[t * act_step_stride + e * act_env_stride]
- * (< 0: idle), result likewise in d_results (may be NULL).  Decisions, results and the final device state are
+ * (< 0: idle), result likewise in d_results (may be NULL).  The n_env slots must name DISTINCT environments
+ * (d_env_ids NULL: slot e = environment e).  Decisions, results and the final device state are
  * bit-identical to `steps` calls of bh_step_batch_device.  Image sizes that are not row regular (N does not
  * divide 1024) and RULE_NEVER run the two-kernel chain step by step (env strides must be 1 then).
  * Asynchronous on the context stream; bh_rollout_status synchronises and reports an aborted barrier. */
