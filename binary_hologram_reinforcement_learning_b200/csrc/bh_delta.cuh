@@ -999,7 +999,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     return v;
 }
 
-template <int UF, typename R>
+// LOOK: one step of look-ahead (few environments: nobody else streams while an environment sits at its barrier).
+// After contributing to the barrier of step t a CTA evaluates the candidate of step t + 1 on its slice while the
+// barrier resolves.  The sums of a candidate do not depend on the sign of its flip nor on the running sums (both
+// enter afterwards), so they stay exact unless step t is kept AND touches the same colour group (its U_f / I_g
+// changed): then the candidate is evaluated again after the commit.  Decisions are those of the sequential loop.
+template <int UF, typename R, bool LOOK>
 __global__ void __launch_bounds__(256, 2)
 k_rollout_t(const RolloutArgs ra) {
     const DeltaArgs& a = ra.a;
@@ -1023,8 +1028,24 @@ k_rollout_t(const RolloutArgs ra) {
     }
     long long prev_act = -1; int prev_sgn = 0, prev_keep = 0;
     int ring_step = 0;                                     // counts the active (non-idle) steps
+    long long spec[4] = {0, 0, 0, 0};                      // look-ahead: this thread's sums of the next candidate
+    bool have_spec = false;
+    auto act_of = [&](int t) { return ra.actions[(long long)t * ra.act_step + (long long)slot_e * ra.act_env]; };
+    auto evaluate = [&](long long act, long long (&out)[4]) {
+        const int f = int(act / (long long)n2);
+        const int pix = int(act - (long long)f * (long long)n2);
+        const int r = pix / N, c = pix - r * N, g = f / a.Fg;
+        const float2* U = a.U + (size_t(env) * a.F + f) * n2;
+        const float* I = a.I + (size_t(env) * a.G + g) * n2;
+        const float* T = a.T + (size_t(env) * a.G + g) * n2;
+        const float2* h = a.h + size_t(g) * P * a.HP;
+        long long acc[1][4] = {{0, 0, 0, 0}};
+        const int sg0 = 1;
+        eval_run_rows<1, UF, R, 4, true>(a, U, I, T, h, &r, &c, &sg0, acc, w0, w1, tid, c2, invFg, pf, pl);
+        out[0] = acc[0][0]; out[1] = acc[0][1]; out[2] = acc[0][2]; out[3] = acc[0][3];
+    };
     for (int t = 0; t < ra.steps; ++t) {
-        const long long act = ra.actions[(long long)t * ra.act_step + (long long)slot_e * ra.act_env];
+        const long long act = act_of(t);
         const long long ri = (long long)t * ra.res_step + (long long)slot_e * ra.res_env;
         if (act < 0) {                                     // idle slot: every CTA of the environment sees the same
             if (leader && tid == 0 && ra.results) {
@@ -1040,36 +1061,44 @@ k_rollout_t(const RolloutArgs ra) {
         // sign of the flip: the resident state byte -- unless the previous step touched the same pixel (its byte
         // is written by the leader CTA after ITS barrier, not ordered with this read): then it follows from
         // the previous step's sign and decision.  Bytes written two or more steps ago are ordered by the
-        // barrier in between.
+        // barrier in between.  (Read here, after the previous barrier: the sums below do not need it.)
         int sbyte;
         if (act == prev_act) sbyte = prev_keep ? (prev_sgn > 0 ? 1 : 0) : (prev_sgn > 0 ? 0 : 1);
         else sbyte = ld_state_relaxed(stp);
-        float2* U = a.U + (size_t(env) * a.F + f) * n2;
-        float* I = a.I + (size_t(env) * a.G + g) * n2;
-        const float* T = a.T + (size_t(env) * a.G + g) * n2;
-        const float2* h = a.h + size_t(g) * P * a.HP;
-        long long acc[1][4] = {{0, 0, 0, 0}};
-        const int sg0 = 1;
-        eval_run_rows<1, UF, R, 4, true>(a, U, I, T, h, &r, &c, &sg0, acc, w0, w1, tid, c2, invFg, pf, pl);
+        long long acc[4];
+        if (LOOK && have_spec) { acc[0] = spec[0]; acc[1] = spec[1]; acc[2] = spec[2]; acc[3] = spec[3]; }
+        else evaluate(act, acc);
+        have_spec = false;
         const int sg = 1 - 2 * sbyte;
-        long long aII = (sg < 0 ? -acc[0][0] : acc[0][0]) + acc[0][1];
-        long long aIT = (sg < 0 ? -acc[0][2] : acc[0][2]) + acc[0][3];
+        long long aII = (sg < 0 ? -acc[0] : acc[0]) + acc[1];
+        long long aIT = (sg < 0 ? -acc[2] : acc[2]) + acc[3];
         aII = warp_sum_ll(aII); aIT = warp_sum_ll(aIT);
         if (lane == 0) { sh[0][warp] = aII; sh[1][warp] = aIT; }
         __syncthreads();
+        unsigned long long* wd = ring + size_t(ring_step % ROLLOUT_RING) * 2;
         if (tid == 0) {
             long long x = 0, y = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) { x += sh[0][i]; y += sh[1][i]; }
-            unsigned long long* wd = ring + size_t(ring_step % ROLLOUT_RING) * 2;
             __threadfence();                               // my earlier stores (ring zeroing, state byte) first
             atomicAdd(wd, ((unsigned long long)x << CNT_BITS) + 1ull);
             atomicAdd(wd + 1, ((unsigned long long)y << CNT_BITS) + 1ull);
+        }
+        // look-ahead: the next candidate's sums while the barrier resolves
+        int g_next = -1;
+        if (LOOK && t + 1 < ra.steps) {
+            const long long an = act_of(t + 1);
+            if (an >= 0) {
+                g_next = int(an / (long long)n2) / a.Fg;
+                evaluate(an, spec);
+                have_spec = true;
+            }
+        }
+        if (tid == 0) {
             unsigned long long wx = 0, wy = 0;
             unsigned spins = 0;
             bool ok = false;
-            // poll the first word until it is complete, then the second (one load per poll); a short sleep between
-            // polls keeps hundreds of pollers from delaying the atomics they are waiting for
+            // poll the first word until it is complete, then the second (one load per poll)
             while (true) {
                 wx = ld_acquire_u64(wd);
                 if (unsigned(wx & CNT_MASK) == unsigned(ra.cpe)) {
@@ -1115,7 +1144,13 @@ k_rollout_t(const RolloutArgs ra) {
         __syncthreads();
         const int keep = s_dec;
         if (keep < 0) break;                               // abort: CTA-uniform
-        if (keep) commit_run_rows<UF>(a, U, I, h, r, c, float(sg), w0, w1, tid, invFg_f, pf, pl);
+        if (keep) {
+            float2* U = a.U + (size_t(env) * a.F + f) * n2;
+            float* I = a.I + (size_t(env) * a.G + g) * n2;
+            const float2* h = a.h + size_t(g) * P * a.HP;
+            commit_run_rows<UF>(a, U, I, h, r, c, float(sg), w0, w1, tid, invFg_f, pf, pl);
+            if (LOOK && g_next == g) have_spec = false;    // the next candidate reads what this flip changed: again
+        }
         prev_act = act; prev_sgn = sg; prev_keep = keep;
         ++ring_step;
     }

@@ -894,7 +894,7 @@ static int rollout_setup(bh_ctx* c) {
     if (c->d_ring) return 0;
     int coop = 0, nb = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
-    auto kern = c->fp64_eval ? k_rollout_t<3, double> : k_rollout_t<3, float>;
+    auto kern = c->fp64_eval ? k_rollout_t<3, double, true> : k_rollout_t<3, float, true>;
     BH_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, 0));
     c->rollout_cap = (coop && !std::getenv("BHOLO_NO_ROLLOUT_KERNEL")) ? nb * c->sms : 0;
     BH_CUDA(c, cudaMalloc(&c->d_ring, (size_t(c->E) * ROLLOUT_RING * 2 + 2) * sizeof(unsigned long long)));
@@ -928,8 +928,13 @@ static int launch_rollout(bh_ctx* c, int n_env, const int32_t* d_env_ids, const 
     // the ring words are zeroed, the error flag (the word behind them) is sticky until bh_rollout_status
     BH_CUDA(c, cudaMemsetAsync(c->d_ring, 0, size_t(c->E) * ROLLOUT_RING * 2 * sizeof(unsigned long long), c->stream));
     void* params[] = {&ra};
-    const void* kern = c->fp64_eval ? reinterpret_cast<const void*>(k_rollout_t<3, double>)
-                                    : reinterpret_cast<const void*>(k_rollout_t<3, float>);
+    // look-ahead pays while an environment's barrier latency is exposed (few environments per GPU); with many, the
+    // other environments fill the gap and a discarded look-ahead would only cost bandwidth
+    static const int look_max = std::getenv("BHOLO_ROLLOUT_LOOK_MAX_ENVS") ? std::atoi(std::getenv("BHOLO_ROLLOUT_LOOK_MAX_ENVS")) : 2;
+    const bool look = n_env <= look_max;
+    const void* kern = c->fp64_eval
+        ? (look ? reinterpret_cast<const void*>(k_rollout_t<3, double, true>) : reinterpret_cast<const void*>(k_rollout_t<3, double, false>))
+        : (look ? reinterpret_cast<const void*>(k_rollout_t<3, float, true>) : reinterpret_cast<const void*>(k_rollout_t<3, float, false>));
     const cudaError_t le = cudaLaunchCooperativeKernel(kern, dim3(cpe * n_env), dim3(256), params, 0, c->stream);
     if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported || le == cudaErrorLaunchOutOfResources) {
         // co-residency refused (a shared or partitioned GPU): the two-kernel chain computes the same thing
@@ -1121,7 +1126,56 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
         int K = k_spec > 0 ? std::min(k_spec, c->max_tasks) : 2;
         const int iters_per_sync = 32;
         long long cursor = 0, nacc = 0, last_resync = 0;
+        // High accept rates: the strictly sequential loop in the persistent rollout kernel with one step of
+        // look-ahead (k_rollout_t<LOOK>: no launch per candidate, the next candidate is scored while the barrier
+        // of the current one resolves) beats the speculation windows, whose evaluations are discarded behind every
+        // kept flip of the same colour group: measured 114 k -> 125 k candidates/s at 50 % kept flips, 130 k -> 137 k
+        // at 36 % (profiles/r2_notes.md 8.7).  Low accept rates: the windows (many candidates per pass over the
+        // image, 320-340 k/s at 1 %) win.  Chunks of up to DBS_ROLL_CHUNK candidates; the accept rate of a chunk
+        // picks the mode of the next (BHOLO_DBS_ROLLOUT_MIN_ACCEPT, default 0.25; > 1 disables the rollout mode).
+        static const double roll_thr = std::getenv("BHOLO_DBS_ROLLOUT_MIN_ACCEPT")
+                                           ? std::atof(std::getenv("BHOLO_DBS_ROLLOUT_MIN_ACCEPT")) : 0.25;
+        const long long DBS_ROLL_CHUNK = 512;
+        bool roll_ok = k_spec <= 0 && UNIT_PX % c->N == 0 && roll_thr <= 1.0;
+        double recent_accept = 1.0;
+        bool scalars_dirty = false;
+        uint8_t* h_chunk = nullptr;
+        if (roll_ok) {
+            c->h_envs[0] = env;
+            BH_DBS(cudaMemcpyAsync(c->d_envs, c->h_envs, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            BH_DBS(cudaMallocHost(&h_chunk, size_t(DBS_ROLL_CHUNK)));
+        }
         while (cursor < n) {
+            if (roll_ok && recent_accept >= roll_thr) {
+                long long m = std::min<long long>(DBS_ROLL_CHUNK, n - cursor);
+                if (resync_every > 0) {                  // end the chunk about where the next re-synchronisation is due
+                    const double need = double(resync_every - (nacc - last_resync));
+                    m = std::min<long long>(m, std::max<long long>(16, (long long)(need / std::max(recent_accept, 0.02)) + 1));
+                }
+                const int launched = launch_rollout(c, 1, c->d_envs, d_order + cursor, 1, 0, int(m), RULE_DBS, nullptr, 1, 0,
+                                                    d_acc + cursor, d_trace ? d_trace + cursor : nullptr);
+                if (launched < 0) { cudaFreeHost(h_chunk); cleanup(); return launched; }
+                if (launched == 0) { roll_ok = false; continue; }
+                BH_DBS(cudaMemcpyAsync(h_chunk, d_acc + cursor, size_t(m), cudaMemcpyDeviceToHost, c->stream));
+                BH_DBS(cudaStreamSynchronize(c->stream));
+                long long kept = 0;
+                for (long long i = 0; i < m; ++i) kept += h_chunk[i];
+                cursor += m; nacc += kept;
+                recent_accept = double(kept) / double(m);
+                scalars_dirty = true;                    // the windows read cursor and count from the device
+                if (resync_every > 0 && nacc - last_resync >= resync_every && cursor < n) {
+                    rc = propagate_env(c, env);
+                    if (rc) { cudaFreeHost(h_chunk); cleanup(); return rc; }
+                    last_resync = nacc;
+                }
+                continue;
+            }
+            if (scalars_dirty) {
+                c->h_scalars[0] = cursor; c->h_scalars[1] = nacc;
+                BH_DBS(cudaMemcpyAsync(c->d_scalars, c->h_scalars, 2 * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+                BH_DBS(cudaStreamSynchronize(c->stream));      // h_scalars is read back below
+                scalars_dirty = false;
+            }
             DeltaArgs a = make_args(c, K, env, nullptr, d_order, RULE_DBS, c->d_results);
             a.offset_ptr = c->d_scalars;
             a.n_total = n;
@@ -1156,6 +1210,7 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
             BH_DBS(cudaMemcpyAsync(c->h_scalars, c->d_scalars, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
             BH_DBS(cudaStreamSynchronize(c->stream));
             const long long consumed = c->h_scalars[0] - cursor;
+            if (consumed > 0) recent_accept = double(c->h_scalars[1] - nacc) / double(consumed);
             cursor = c->h_scalars[0];
             nacc = c->h_scalars[1];
             if (k_spec <= 0) {
@@ -1172,6 +1227,7 @@ extern "C" int bh_dbs_run(bh_ctx* c, int env, const int64_t* order, int64_t n, i
                 last_resync = nacc;
             }
         }
+        cudaFreeHost(h_chunk);
         BH_DBS(cudaMemcpyAsync(accepted, d_acc, size_t(n), cudaMemcpyDeviceToHost, c->stream));
         if (psnr_trace)
             BH_DBS(cudaMemcpyAsync(psnr_trace, d_trace, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

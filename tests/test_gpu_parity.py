@@ -1025,7 +1025,9 @@ def test_batched_dbs_equals_the_sequential_loop_of_every_image():
     (64, 6, O.WL_RGB, 3, 60, RULE_ENV),
     (256, 8, O.WL_MONO, 5, 80, RULE_DBS),
     (1024, 24, O.WL_RGB, 8, 48, RULE_ENV),        # the bench shape: 37 CTAs per env
-    (1024, 3, O.WL_RGB, 1, 24, RULE_DBS),         # one env owns the whole chip
+    (1024, 3, O.WL_RGB, 1, 24, RULE_DBS),         # one env owns the whole chip (look-ahead variant of the kernel)
+    (256, 12, O.WL_RGB, 2, 150, RULE_DBS),        # two envs: look-ahead, many same-group neighbours
+    (128, 4, O.WL_MONO, 1, 200, RULE_ENV),        # one colour group: every kept flip invalidates the look-ahead
     (896, 3, O.WL_RGB, 2, 12, RULE_ENV),          # not row regular: falls back to the two-kernel chain
 ])
 def test_rollout_kernel_is_bit_identical_to_the_step_chain(N, F, wl, E, steps, rule):
