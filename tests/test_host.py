@@ -281,3 +281,48 @@ def test_variant_modules_and_multidiscrete_action_space():
     assert list(e.action_space.nvec) == [4, 32, 32]
     e5 = env_05.BinaryHologramEnv(ld.target_function, ld, IPS=32, CH=4, verbose=False)
     assert e5.T_PSNR_DIFF == 0.5 and e5.action_space.n == 4 * 32 * 32
+
+
+def test_cpulist_parser_and_numa_binding_is_a_noop_without_topology(monkeypatch):
+    """dist.bind_to_gpu_numa_node: sysfs cpulists parse ("0-3,8,10-11"), and without a GPU / exposed topology the
+    call changes nothing and returns None (the B200 boxes of this pool are single-node VMs)."""
+    from binary_hologram_reinforcement_learning_b200 import dist as D
+    assert D._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert D._parse_cpulist("") == set()
+    assert D._parse_cpulist("5") == {5}
+    before = os.sched_getaffinity(0)
+    assert D.bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
+    # a node whose cores are outside the container's cpuset must not empty the affinity mask
+    monkeypatch.setattr(D, "gpu_numa_node", lambda local_rank: 10 ** 6)
+    assert D.bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
+
+
+def test_bench_cpu_arm_reports_stock_and_tuned_allocator(monkeypatch):
+    """The reference arm prints the stock figure as `value` and the allocator-tuned best case beside it; the
+    mallopt switch is reversible (bench.tune_host_allocator)."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    assert bench.tune_host_allocator(True) is True
+    assert bench.tune_host_allocator(False) is True
+    calls = []
+
+    def fake_rate(seconds_budget=None, samples=None, sample_steps=8, warm=1):
+        calls.append(samples)
+        return (10.0 if len(calls) == 1 else 25.0), [0.8] * (samples or 1), 4
+    monkeypatch.setattr(bench, "cpu_reference_rate", fake_rate)
+    lines = []
+    monkeypatch.setattr(bench, "emit", lambda line: lines.append(line))
+
+    class A:
+        steps, warmup, gpus, envs, rollout = 3, 1, 1, 8, 512
+    assert bench.run_reference(A()) == 0
+    line = lines[0]
+    assert line["impl"] == "reference" and line["value"] == 10.0 and line["e2e"]["value"] == 10.0
+    assert line["cpu_baseline"]["tuned_allocator"]["value"] == 25.0
+    assert line["config"] == bench.bench_config(8, 512)
